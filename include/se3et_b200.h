@@ -1,0 +1,94 @@
+/* se3et_b200 -- C ABI of the B200-native (sm_100a) SE3ET hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain DEVICE pointers and sizes plus the
+ * CUDA stream to launch on, returns 0 on success or a negative SE3ET_ERR_* code, and
+ * never throws.  No torch types cross this boundary; the Python host side
+ * (se3et_b200/_lib.py) binds it with ctypes and passes tensor.data_ptr().
+ *
+ * The library is stateless and re-entrant: all scratch memory is passed in as a
+ * workspace sized by the matching *_workspace_bytes() call.  Conditions detected on
+ * the device (e.g. voxel grid larger than the workspace) are reported through a
+ * caller-provided `int32 status[SE3ET_STATUS_WORDS]` device buffer that the host
+ * reads together with the data-dependent output sizes (one sync).
+ *
+ * Each function cites the reference interface it replaces (paths relative to the
+ * reference repository root).
+ */
+#ifndef SE3ET_B200_H_
+#define SE3ET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* se3et_stream_t; /* cudaStream_t */
+
+enum {
+  SE3ET_OK = 0,
+  SE3ET_ERR_CUDA = -1,      /* a CUDA runtime call / launch failed (see se3et_last_error) */
+  SE3ET_ERR_ARG = -2,       /* invalid argument (null pointer, negative size, unsupported shape) */
+  SE3ET_ERR_WORKSPACE = -3, /* workspace too small */
+  SE3ET_ERR_UNSUPPORTED = -4
+};
+
+/* Device-side status words (int32 each). */
+enum {
+  SE3ET_STATUS_ERROR = 0,     /* 0 = ok, else SE3ET_DEV_* bit mask */
+  SE3ET_STATUS_M_TOTAL = 1,   /* grid_subsample: total number of output points */
+  SE3ET_STATUS_MAX_COUNT = 2, /* radius_neighbors: max neighbour count over all queries */
+  SE3ET_STATUS_REQ_KCELLS = 3, /* grid_subsample: on GRID_TOO_LARGE, cells needed / 1024 (rounded up, saturating) */
+  SE3ET_STATUS_WORDS = 8
+};
+enum {
+  SE3ET_DEV_GRID_TOO_LARGE = 1, /* voxel grid does not fit the workspace bitmap */
+  SE3ET_DEV_INDEX_RANGE = 2     /* voxel index below -1 (cannot happen for finite fp32 input) */
+};
+
+const char* se3et_last_error(void); /* thread-local text of the last SE3ET_ERR_CUDA */
+int se3et_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * grid_subsample
+ * replaces: geotransformer.ext.grid_subsampling
+ *   (geotransformer/extensions/cpu/grid_subsampling/grid_subsampling.cpp:5-83,
+ *    grid_subsampling_cpu.cpp:3-109, grid_subsampling_cpu.h:24-74; pybind.cpp:14-18)
+ * For every cloud b (stack mode, `lengths[b]` points each) and every occupied voxel,
+ * emits the input point closest to the voxel's fp32 barycentre (ties: lowest input
+ * index) and its normal.  Output order is canonical: ascending reference voxel key
+ * inside each cloud.  IEEE fp32, no contraction: bit-identical to the reference.
+ * s_points / s_normals must have room for n_total rows.  status[M_TOTAL] receives M.
+ * ------------------------------------------------------------------------------------------ */
+int se3et_grid_subsample_workspace_bytes(int64_t n_total, int64_t batch, int64_t max_cells, size_t* bytes);
+int se3et_grid_subsample(const float* points, const int64_t* lengths, const float* normals, int64_t n_total,
+                         int64_t batch, float voxel_size, float* s_points, int64_t* s_lengths, float* s_normals,
+                         int32_t* status, void* workspace, size_t workspace_bytes, int64_t max_cells,
+                         se3et_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * radius_neighbors
+ * replaces: geotransformer.ext.radius_neighbors
+ *   (geotransformer/extensions/cpu/radius_neighbors/radius_neighbors.cpp:5-76,
+ *    radius_neighbors_cpu.cpp:3-91; nanoflann.hpp:249-253,432-440,1279-1289; pybind.cpp:9-13)
+ *   and the column truncation of modules/ops/radius_search.py:24-27.
+ * For query i of cloud b: all support points j of cloud b with
+ *   d2 = ((qx-sx)^2 + (qy-sy)^2) + (qz-sz)^2 < radius*radius     (fp32, strict)
+ * ordered by (d2 ascending, j ascending).
+ *   counts  (optional, int32[nq])      neighbour count of each query
+ *   out     (optional, int64[nq,width]) first `width` neighbours as global support
+ *           indices, padded with ns_total
+ * status[MAX_COUNT] receives the maximum count.  Hashed uniform grid (cell = radius)
+ * over the support set + one warp per query.
+ * ------------------------------------------------------------------------------------------ */
+int se3et_radius_neighbors_workspace_bytes(int64_t nq_total, int64_t ns_total, int64_t batch, size_t* bytes);
+int se3et_radius_neighbors(const float* q_points, const float* s_points, const int64_t* q_lengths,
+                           const int64_t* s_lengths, int64_t nq_total, int64_t ns_total, int64_t batch,
+                           float radius, int32_t* counts, int64_t* out, int64_t width, int32_t* status,
+                           void* workspace, size_t workspace_bytes, se3et_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SE3ET_B200_H_ */

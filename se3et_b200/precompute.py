@@ -1,0 +1,73 @@
+"""GPU pyramid precompute: mirror of geotransformer/utils/data.py:13-97 (`precompute_data_stack_mode`).
+
+Same arguments and the same dict of lists, but every tensor stays on the GPU and the 3S-2 searches are issued
+back-to-back without host syncs (their neighbour-count checks are read in one transfer at the end). Normals are
+carried as zeros (the reference's open3d normals are never consumed by the model)."""
+import torch
+
+from . import _lib
+from .ops import grid_subsample, radius_search_deferred
+
+
+def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, neighbor_limits, normals=None):
+    assert num_stages == len(neighbor_limits)
+    _lib.require_cuda(points)
+    lengths = lengths.to(points.device)
+    if normals is None:
+        normals = torch.zeros_like(points)
+    points_list, lengths_list, normals_list = [], [], []
+    for i in range(num_stages):
+        if i > 0:
+            points, lengths, normals = grid_subsample(points, lengths, normals, voxel_size=voxel_size)
+        if i == num_stages - 1:
+            # data.py:34-43: at most 2000 superpoints per cloud (pair mode only, as in the reference)
+            if lengths.shape[0] == 2:
+                l0, l1 = (int(v) for v in lengths.tolist())
+                if l0 > 2000 or l1 > 2000:
+                    k0, k1 = min(l0, 2000), min(l1, 2000)
+                    points = torch.cat((points[:k0], points[l0:l0 + k1]), dim=0)
+                    normals = torch.cat((normals[:k0], normals[l0:l0 + k1]), dim=0)
+                    lengths = torch.tensor([k0, k1], dtype=torch.int64, device=points.device)
+        points_list.append(points)
+        lengths_list.append(lengths)
+        normals_list.append(normals)
+        voxel_size *= 2
+
+    neighbors_list, subsampling_list, upsampling_list = [], [], []
+    pending = []  # (list, index, limit, status)
+
+    def search(dst, q, s, ql, sl, r, limit):
+        if limit <= 0:
+            from .ops import radius_search
+            dst.append(radius_search(q, s, ql, sl, r, limit))
+            return
+        out, status = radius_search_deferred(q, s, ql, sl, r, limit)
+        dst.append(out)
+        pending.append((dst, len(dst) - 1, limit, status))
+
+    for i in range(num_stages):
+        cur_points, cur_lengths = points_list[i], lengths_list[i]
+        search(neighbors_list, cur_points, cur_points, cur_lengths, cur_lengths, radius, neighbor_limits[i])
+        if i < num_stages - 1:
+            sub_points, sub_lengths = points_list[i + 1], lengths_list[i + 1]
+            search(subsampling_list, sub_points, cur_points, sub_lengths, cur_lengths, radius, neighbor_limits[i])
+            search(upsampling_list, cur_points, sub_points, cur_lengths, sub_lengths, radius * 2,
+                   neighbor_limits[i + 1])
+        radius *= 2
+
+    if pending:
+        # one transfer for all searches: width is min(max_count, limit) as in ops/radius_search.py:24-27
+        stats = torch.stack([p[3] for p in pending]).cpu()
+        for (dst, idx, limit, _), st in zip(pending, stats):
+            max_count = int(st[_lib.STATUS_MAX_COUNT])
+            if max_count < limit:
+                dst[idx] = dst[idx][:, :max_count].contiguous()
+
+    return {
+        'points': points_list,
+        'lengths': lengths_list,
+        'neighbors': neighbors_list,
+        'subsampling': subsampling_list,
+        'upsampling': upsampling_list,
+        'normals': normals_list,
+    }
