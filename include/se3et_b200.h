@@ -88,6 +88,22 @@ int se3et_radius_neighbors(const float* q_points, const float* s_points, const i
                            float radius, int32_t* counts, int64_t* out, int64_t width, int32_t* status,
                            void* workspace, size_t workspace_bytes, se3et_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * gemm_bf16:  C[M,N] = alpha * A[M,K] * B[N,K]^T (+ bias[N]) (ReLU if act == 1)
+ * replaces: every torch.nn.Linear on the path (blocks_epn.py:658 UnaryBlockEPN.mlp,
+ *   kpconv/modules.py:75,97, geotransformer.py:278-281,314-315 in/out_proj,
+ *   rpe_transformer.py:57-60 / vanilla_transformer.py:58-62 proj_q/k/v/p, output_layer.py:16-20)
+ *   and the `kpac,karcd->prd` contraction of KPConvInterSO3.forward (blocks_epn.py:503-506)
+ *   after se3et_kpconv_gather has built A.
+ * A, B: bf16 row-major with pitches lda / ldb (elements, multiples of 8); N multiple of 16.
+ * tcgen05 tensor cores, fp32 accumulation in TMEM.  Outputs fp32 and/or bf16 (either may be NULL).
+ * batch > 1: A rows offset by a_batch_rows, B rows by b_batch_rows (0 = shared), C by c_batch_stride.
+ * ------------------------------------------------------------------------------------------ */
+int se3et_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int64_t n, int64_t k,
+                    int64_t batch, int64_t a_batch_rows, int64_t b_batch_rows, const float* bias, float alpha,
+                    int act, float* out_f32, void* out_bf16, int64_t ldc, int64_t c_batch_stride,
+                    se3et_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,45 @@
+"""Host wrapper of se3et_gemm_bf16 (tcgen05 GEMM): out = alpha * a @ b.T (+ bias) (ReLU)."""
+import torch
+
+from .. import _lib
+
+
+def linear_bf16(a, w, bias=None, alpha=1.0, relu=False, out_f32=True, out_bf16=False):
+    """a: (M, K) bf16 row-major (row pitch a.stride(0)); w: (N, K) bf16 (nn.Linear layout); bias fp32 (N,) or None.
+    Returns (fp32 or None, bf16 or None) tensors of shape (M, N)."""
+    _lib.require_cuda(a, w, bias)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1]
+    assert a.stride(1) == 1 and w.stride(1) == 1
+    m, k = a.shape
+    n = w.shape[0]
+    of = torch.empty((m, n), dtype=torch.float32, device=a.device) if out_f32 else None
+    ob = torch.empty((m, n), dtype=torch.bfloat16, device=a.device) if out_bf16 else None
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == n
+    if m == 0:
+        return of, ob
+    L = _lib.lib()
+    _lib.check(L.se3et_gemm_bf16(
+        _lib.ptr(a), _lib.i64(a.stride(0)), _lib.ptr(w), _lib.i64(w.stride(0)), _lib.i64(m), _lib.i64(n), _lib.i64(k),
+        _lib.i64(1), _lib.i64(0), _lib.i64(0), _lib.ptr(bias), _lib.f32(alpha), int(bool(relu)), _lib.ptr(of),
+        _lib.ptr(ob), _lib.i64(n), _lib.i64(0), _lib.stream_ptr()), "gemm_bf16")
+    return of, ob
+
+
+def bmm_bf16(a, b, alpha=1.0, out_f32=True, out_bf16=False):
+    """Batched: a (B, M, K) bf16, b (B, N, K) bf16 (both contiguous) -> (B, M, N) = alpha * a @ b^T."""
+    _lib.require_cuda(a, b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.is_contiguous() and b.is_contiguous()
+    bsz, m, k = a.shape
+    n = b.shape[1]
+    of = torch.empty((bsz, m, n), dtype=torch.float32, device=a.device) if out_f32 else None
+    ob = torch.empty((bsz, m, n), dtype=torch.bfloat16, device=a.device) if out_bf16 else None
+    if m == 0 or bsz == 0:
+        return of, ob
+    L = _lib.lib()
+    _lib.check(L.se3et_gemm_bf16(
+        _lib.ptr(a), _lib.i64(k), _lib.ptr(b), _lib.i64(k), _lib.i64(m), _lib.i64(n), _lib.i64(k), _lib.i64(bsz),
+        _lib.i64(m), _lib.i64(n), _lib.ptr(None), _lib.f32(alpha), 0, _lib.ptr(of), _lib.ptr(ob), _lib.i64(n),
+        _lib.i64(m * n), _lib.stream_ptr()), "gemm_bf16")
+    return of, ob
