@@ -79,14 +79,15 @@ int se3et_grid_subsample(const float* points, const int64_t* lengths, const floa
  *   counts  (optional, int32[nq])      neighbour count of each query
  *   out     (optional, int64[nq,width]) first `width` neighbours as global support
  *           indices, padded with ns_total
- * status[MAX_COUNT] receives the maximum count.  Hashed uniform grid (cell = radius)
- * over the support set + one warp per query.
+ * status[MAX_COUNT] receives the maximum count; cloud_max (optional, int32[batch]) the maximum
+ * per cloud, which is what decides the reference's matrix width when pairs are processed one at a
+ * time.  Hashed uniform grid (cell = radius) over the support set + one warp per query.
  * ------------------------------------------------------------------------------------------ */
 int se3et_radius_neighbors_workspace_bytes(int64_t nq_total, int64_t ns_total, int64_t batch, size_t* bytes);
 int se3et_radius_neighbors(const float* q_points, const float* s_points, const int64_t* q_lengths,
                            const int64_t* s_lengths, int64_t nq_total, int64_t ns_total, int64_t batch,
                            float radius, int32_t* counts, int64_t* out, int64_t width, int32_t* status,
-                           void* workspace, size_t workspace_bytes, se3et_stream_t stream);
+                           int32_t* cloud_max, void* workspace, size_t workspace_bytes, se3et_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * gemm_bf16:  C[M,N] = alpha * A[M,K] * B[N,K]^T (+ bias[N]) (ReLU if act == 1)
@@ -103,6 +104,52 @@ int se3et_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int6
                     int64_t batch, int64_t a_batch_rows, int64_t b_batch_rows, const float* bias, float alpha,
                     int act, float* out_f32, void* out_bf16, int64_t ldc, int64_t c_batch_stride,
                     se3et_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * E2PN backbone pieces.  Feature tensors are [point, anchor(6), channel]; activations bf16,
+ * pre-norm GEMM outputs fp32.  Segments (`seg_offsets`, nseg+1 point offsets) are point-cloud
+ * PAIRS: GroupNorm statistics never mix pairs (blocks_epn.py:697-701 normalises ref+src jointly).
+ * ------------------------------------------------------------------------------------------ */
+
+/* The octahedral-group index tables the gather kernel has compiled in (kanchor 6, quotient 4,
+ * K 15): kidx_rot[k][r] and ridx_rot[a][r] of KPConvInterSO3 (blocks_epn.py:228-332).  The host
+ * compares them with the module's buffers and refuses to run on a mismatch. */
+int se3et_kpconv_tables(int32_t* kidx_15x6, int32_t* ridx_6x6);
+
+/* kpconv_gather -- first half of KPConvInterSO3.forward (blocks_epn.py:454-506, 334-390):
+ *   w[n][k] = max(0, 1 - |s[idx[p][n]] - q[p] - kp[k]| / extent)      (shadow index ns => w = 0)
+ *   wf[k][a][c] = sum_n w[n][k] * x[idx[p][n]][a][c]
+ *   out[(p*6 + r)][(kc*6 + ridx[a][r])*cin + c] = sum_{k: kidx[k][r] == kc} wf[k][a][c]
+ * so that conv = out @ weights.view(36*cin, cout) (one se3et_gemm_bf16).  out: bf16 [nq*6, kpad],
+ * kpad >= 36*cin (multiple of 8), padding columns zeroed. */
+int se3et_kpconv_gather(const float* q_pts, const float* s_pts, const int64_t* neighbors, int64_t nq, int64_t ns,
+                        int64_t h, const void* x_bf16, int64_t cin, const float* kernel_points_15x3, float kp_extent,
+                        void* out_bf16, int64_t kpad, se3et_stream_t stream);
+
+/* GroupNormEPN / kpconv GroupNorm (blocks_epn.py:684-701, kpconv/modules.py:33-50): statistics per
+ * (segment, group) over rows_per_point * points * channels_per_group values.  stats: double [nseg, groups, 2]. */
+int se3et_groupnorm_stats(const float* y, int64_t rows, int64_t channels, int64_t groups, const int64_t* seg_offsets,
+                          int64_t nseg, int64_t rows_per_point, double* stats, se3et_stream_t stream);
+/* out = LeakyReLU_slope( GN_a(ya) [+ GN_b(yb)] [+ resid] ); slope 1 = no activation.  Covers UnaryBlockEPN,
+ * KPConvInterSO3Block, and the residual tail of ResnetBottleneckBlockEPN.forward (blocks_epn.py:833-852). */
+int se3et_groupnorm_apply(const float* ya, const double* stats_a, const float* gamma_a, const float* beta_a,
+                          const float* yb, const double* stats_b, const float* gamma_b, const float* beta_b,
+                          const void* resid_bf16, int64_t rows, int64_t channels, int64_t groups,
+                          const int64_t* seg_offsets, int64_t nseg, int64_t rows_per_point, float eps,
+                          float leaky_slope, float* out_f32, void* out_bf16, se3et_stream_t stream);
+/* max_pool (e2pn/blocks.py:93-110): out[q] = max_n xpad[neighbors[q][n]], zero shadow row. width = 6*C.
+ * seg_offsets/seg_width (optional): only the first seg_width[s] columns count for queries of pair s -- the
+ * reference's matrix is min(max_count, limit) wide PER PAIR and its zero shadow row enters the max only
+ * when a row is shorter than that. */
+int se3et_maxpool_nbr(const void* x_bf16, int64_t ns, int64_t width, const int64_t* neighbors, int64_t nq, int64_t h,
+                      const int64_t* seg_offsets, const int32_t* seg_width, int64_t nseg, void* out_bf16,
+                      se3et_stream_t stream);
+/* InvOutBlockEPN / eq->inv pooling (blocks_epn.py:924, conditional_transformer.py:282-283): max over anchors. */
+int se3et_anchor_max(const void* x_bf16, int64_t n, int64_t anchors, int64_t channels, void* out_bf16, int64_t out_ld,
+                     se3et_stream_t stream);
+/* nearest_upsample + cat (kpconv/functional.py:6-22, backbone.py:66-72): out[i] = [xpad[up[i][0]] | y[i]]. */
+int se3et_upsample_concat(const void* x_bf16, int64_t nx, int64_t c1, const int64_t* up_idx, int64_t up_ld,
+                          const void* y_bf16, int64_t c2, int64_t n, void* out_bf16, se3et_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,437 @@
+// E2PN backbone kernels other than the tensor-core GEMM (sm_100a):
+//   kpconv_gather   neighbour gather + kernel-point influence + rotate-by-permute  (blocks_epn.py:334-390,471-478,503-505)
+//   groupnorm_stats / groupnorm_apply   GroupNormEPN over (C/G x A x N_pair)        (blocks_epn.py:684-701)
+//   maxpool_nbr     strided shortcut max pooling                                    (e2pn/blocks.py:93-110)
+//   anchor_max      InvOutBlockEPN / eq->inv pooling, max over the anchor axis      (blocks_epn.py:924)
+//   upsample_concat nearest_upsample + torch.cat of the decoder                     (kpconv/functional.py:6-22)
+// Features are stored [point, anchor(6), channel]; activations bf16, pre-norm GEMM outputs fp32.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace se3et {
+
+// ---------------------------------------------------------------------------------------------
+// Octahedral group tables for kanchor = 6, quotient_factor = 4, K = 15 (SURVEY 8c golden constants;
+// verified against the module's kidx_rot / ridx_rot buffers by the host before every launch).
+//   kKidx[k][r]: weight-sharing class (0..5) that kernel point k falls into after rotation by anchor r
+//   kRidx[a][r]: weight anchor slot a' = ridx_rot[a][r] that input anchor a feeds for output anchor r
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int kidx_tab(int k, int r) {
+  constexpr int t[15][6] = {{0, 1, 1, 1, 1, 2}, {1, 0, 1, 2, 1, 1}, {1, 1, 0, 1, 2, 1}, {1, 2, 1, 0, 1, 1},
+                            {1, 1, 2, 1, 0, 1}, {2, 1, 1, 1, 1, 0}, {3, 3, 3, 4, 4, 4}, {3, 4, 3, 3, 4, 4},
+                            {3, 4, 4, 3, 3, 4}, {3, 3, 4, 4, 3, 4}, {4, 3, 3, 4, 4, 3}, {4, 4, 3, 3, 4, 3},
+                            {4, 4, 4, 3, 3, 3}, {4, 3, 4, 4, 3, 3}, {5, 5, 5, 5, 5, 5}};
+  return t[k][r];
+}
+__host__ __device__ constexpr int ridx_tab(int a, int r) {
+  constexpr int t[6][6] = {{0, 3, 3, 3, 3, 5}, {1, 0, 4, 5, 2, 1}, {2, 2, 0, 4, 5, 4},
+                           {3, 5, 2, 0, 4, 3}, {4, 4, 5, 2, 0, 2}, {5, 1, 1, 1, 1, 0}};
+  return t[a][r];
+}
+__constant__ int c_ridx[6][6] = {{0, 3, 3, 3, 3, 5}, {1, 0, 4, 5, 2, 1}, {2, 2, 0, 4, 5, 4},
+                                 {3, 5, 2, 0, 4, 3}, {4, 4, 5, 2, 0, 2}, {5, 1, 1, 1, 1, 0}};
+
+constexpr int kA = 6;        // anchors
+constexpr int kKP = 15;      // kernel points
+constexpr int kKC = 6;       // weight-sharing classes
+constexpr int kMaxH = 64;    // neighbour columns supported by the gather kernel
+
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+// One CTA per query point.  Threads own column pairs (a, c..c+1) of the gathered feature rows.
+//   wf[k][col]  = sum_n w[n][k] * x[idx[n]][col]                       (einsum 'pnac,pnk->pkac')
+//   A'[(p,r)][(kc, a', c)] = sum_{k : kidx[k][r] == kc} wf[k][(a, c)],  a' = ridx[a][r]
+// so that  out[(p,r), d] = sum_K A'[(p,r), K] * W[kc][a'][c][d]  is ONE GEMM with the untouched weights
+// (the reference gathers the weights instead: 'kpac,karcd->prd' with W_eff = W[kidx_rot, ridx_rot]).
+template <bool kPair>
+__global__ void __launch_bounds__(256) kpconv_gather_kernel(const float* __restrict__ q_pts,
+                                                             const float* __restrict__ s_pts,
+                                                             const int64_t* __restrict__ idx, int H, int64_t ns,
+                                                             const __nv_bfloat16* __restrict__ x, int cin,
+                                                             const float* __restrict__ kernel_points, float inv_extent,
+                                                             __nv_bfloat16* __restrict__ out, int kpad) {
+  __shared__ float sh_w[kMaxH][kKP + 1];
+  __shared__ int sh_idx[kMaxH];
+  const int64_t p = blockIdx.x;
+  const int tid = threadIdx.x;
+  if (tid < H) {
+    const int64_t j = idx[p * H + tid];
+    sh_idx[tid] = (j >= 0 && j < ns) ? (int)j : -1;  // shadow neighbour: zero feature, far point
+  }
+  __syncthreads();
+  for (int t = tid; t < H * kKP; t += blockDim.x) {
+    const int n = t / kKP, k = t - n * kKP;
+    const int j = sh_idx[n];
+    float w = 0.f;
+    if (j >= 0) {
+      const float dx = (s_pts[3 * (int64_t)j + 0] - q_pts[3 * p + 0]) - kernel_points[3 * k + 0];
+      const float dy = (s_pts[3 * (int64_t)j + 1] - q_pts[3 * p + 1]) - kernel_points[3 * k + 1];
+      const float dz = (s_pts[3 * (int64_t)j + 2] - q_pts[3 * p + 2]) - kernel_points[3 * k + 2];
+      w = fmaxf(0.f, 1.f - sqrtf(dx * dx + dy * dy + dz * dz) * inv_extent);  // 'linear' influence (blocks_epn.py:351)
+    }
+    sh_w[n][k] = w;
+  }
+  __syncthreads();
+
+  const int width = kA * cin;                   // columns of one feature row
+  const int units = kPair ? width / 2 : width;  // work items per point
+  for (int u = tid; u < units; u += blockDim.x) {
+    const int col = kPair ? 2 * u : u;
+    float acc0[kKP], acc1[kKP];
+#pragma unroll
+    for (int k = 0; k < kKP; ++k) acc0[k] = acc1[k] = 0.f;
+    for (int n = 0; n < H; ++n) {
+      const int j = sh_idx[n];
+      if (j < 0) continue;
+      float x0, x1 = 0.f;
+      if (kPair) {
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(x + (int64_t)j * width + col);
+        x0 = bf_lo(v);
+        x1 = bf_hi(v);
+      } else {
+        x0 = __bfloat162float(x[(int64_t)j * width + col]);
+      }
+#pragma unroll
+      for (int k = 0; k < kKP; ++k) {
+        const float w = sh_w[n][k];
+        acc0[k] = fmaf(w, x0, acc0[k]);
+        if (kPair) acc1[k] = fmaf(w, x1, acc1[k]);
+      }
+    }
+    const int a = col / cin, c = col - a * cin;
+#pragma unroll
+    for (int r = 0; r < kA; ++r) {
+      float s0[kKC], s1[kKC];
+#pragma unroll
+      for (int kc = 0; kc < kKC; ++kc) s0[kc] = s1[kc] = 0.f;
+#pragma unroll
+      for (int k = 0; k < kKP; ++k) {
+        // tables are compile-time constants after unrolling: s0[] stays in registers
+        const int kc = kidx_tab(k, r);
+        s0[kc] += acc0[k];
+        if (kPair) s1[kc] += acc1[k];
+      }
+      const int ap = c_ridx[a][r];
+      __nv_bfloat16* row = out + (p * kA + r) * (int64_t)kpad;
+#pragma unroll
+      for (int kc = 0; kc < kKC; ++kc) {
+        const int kk = (kc * kA + ap) * cin + c;
+        if (kPair) *reinterpret_cast<uint32_t*>(row + kk) = pack_bf16(s0[kc], s1[kc]);
+        else row[kk] = __float2bfloat16(s0[kc]);
+      }
+    }
+  }
+  // zero the K padding (only when 36*cin is not a multiple of 64)
+  const int kreal = kKC * kA * cin;
+  for (int t = tid; t < kA * (kpad - kreal); t += blockDim.x) {
+    const int r = t / (kpad - kreal), j = t - r * (kpad - kreal);
+    out[(p * kA + r) * (int64_t)kpad + kreal + j] = __float2bfloat16(0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm over (channels of a group) x (rows of a segment); a segment = one point-cloud pair.
+// rows_per_point = 6 for equivariant features (N, A, C), 1 for invariant ones (N, C).
+// stats[seg][group] = {sum, sum of squares} in double.
+// ---------------------------------------------------------------------------------------------
+constexpr int kStatRows = 128;
+
+__global__ void __launch_bounds__(256) groupnorm_stats_kernel(const float* __restrict__ y, int64_t rows, int C,
+                                                               int cpg, const int64_t* __restrict__ seg_off, int nseg,
+                                                               int rows_per_point, double* __restrict__ stats) {
+  extern __shared__ float sh_part[];  // [G_block][2]
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  const int g_first = (blockIdx.y * blockDim.x) / cpg;
+  const int g_count = (min(C, (int)((blockIdx.y + 1) * blockDim.x)) - 1) / cpg - g_first + 1;
+  const int G = C / cpg;
+  const int64_t r0 = (int64_t)blockIdx.x * kStatRows;
+  const int64_t r1 = min(rows, r0 + kStatRows);
+  int seg = segment_of(seg_off, nseg, r0 / rows_per_point);
+  int64_t r = r0;
+  while (r < r1) {
+    const int64_t seg_end = min(r1, seg_off[seg + 1] * rows_per_point);
+    float s = 0.f, ss = 0.f;
+    if (c < C)
+      for (int64_t i = r; i < seg_end; ++i) {
+        const float v = y[i * C + c];
+        s += v;
+        ss += v * v;
+      }
+    for (int i = threadIdx.x; i < 2 * g_count; i += blockDim.x) sh_part[i] = 0.f;
+    __syncthreads();
+    if (c < C) {
+      atomicAdd(&sh_part[2 * (c / cpg - g_first)], s);
+      atomicAdd(&sh_part[2 * (c / cpg - g_first) + 1], ss);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * g_count; i += blockDim.x)
+      atomicAdd(&stats[((int64_t)seg * G + g_first) * 2 + i], (double)sh_part[i]);
+    __syncthreads();
+    r = seg_end;
+    ++seg;
+    while (r < r1 && seg < nseg && seg_off[seg + 1] * rows_per_point <= r) ++seg;  // skip empty segments
+  }
+}
+
+struct NormSide {
+  const float* y;       // fp32 pre-norm values [rows, C] (nullable => side absent)
+  const double* stats;  // [nseg, G, 2]
+  const float* gamma;   // [C]
+  const float* beta;    // [C]
+};
+
+// out = act( norm_a(ya) [+ norm_b(yb)] [+ resid] ),  act = LeakyReLU(slope) when slope != 1
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(NormSide a, NormSide b,
+                                                               const __nv_bfloat16* __restrict__ resid, int64_t rows,
+                                                               int C, int cpg, const int64_t* __restrict__ seg_off,
+                                                               int nseg, int rows_per_point, float eps, float slope,
+                                                               float* __restrict__ out_f32,
+                                                               __nv_bfloat16* __restrict__ out_bf16) {
+  const int vec_per_row = C / 4;
+  const int64_t total = rows * vec_per_row;
+  const int G = C / cpg;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / vec_per_row;
+    const int c0 = (int)(i - row * vec_per_row) * 4;
+    const int seg = segment_of(seg_off, nseg, row / rows_per_point);
+    const double cnt = (double)(seg_off[seg + 1] - seg_off[seg]) * rows_per_point * cpg;
+    float v[4];
+    {
+      const float4 yv = *reinterpret_cast<const float4*>(a.y + row * C + c0);
+      const float in[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int g = (c0 + j) / cpg;
+        const double mean = a.stats[((int64_t)seg * G + g) * 2] / cnt;
+        const double var = a.stats[((int64_t)seg * G + g) * 2 + 1] / cnt - mean * mean;
+        const float rstd = rsqrtf((float)fmax(var, 0.0) + eps);
+        v[j] = (in[j] - (float)mean) * rstd * a.gamma[c0 + j] + a.beta[c0 + j];
+      }
+    }
+    if (b.y) {
+      const float4 yv = *reinterpret_cast<const float4*>(b.y + row * C + c0);
+      const float in[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int g = (c0 + j) / cpg;
+        const double mean = b.stats[((int64_t)seg * G + g) * 2] / cnt;
+        const double var = b.stats[((int64_t)seg * G + g) * 2 + 1] / cnt - mean * mean;
+        const float rstd = rsqrtf((float)fmax(var, 0.0) + eps);
+        v[j] += (in[j] - (float)mean) * rstd * b.gamma[c0 + j] + b.beta[c0 + j];
+      }
+    }
+    if (resid) {
+      const uint2 rv = *reinterpret_cast<const uint2*>(resid + row * C + c0);
+      v[0] += bf_lo(rv.x); v[1] += bf_hi(rv.x); v[2] += bf_lo(rv.y); v[3] += bf_hi(rv.y);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = v[j] >= 0.f ? v[j] : v[j] * slope;
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * C + c0) = make_float4(v[0], v[1], v[2], v[3]);
+    if (out_bf16) {
+      uint2 o;
+      o.x = pack_bf16(v[0], v[1]);
+      o.y = pack_bf16(v[2], v[3]);
+      *reinterpret_cast<uint2*>(out_bf16 + row * C + c0) = o;
+    }
+  }
+}
+
+// out[q][col] = max_n xpad[idx[q][n]][col]; shadow neighbours contribute 0 (blocks.py:100-109)
+__global__ void __launch_bounds__(256) maxpool_nbr_kernel(const __nv_bfloat16* __restrict__ x, int64_t ns, int width,
+                                                           const int64_t* __restrict__ idx, int H_full,
+                                                           const int64_t* __restrict__ seg_off,
+                                                           const int32_t* __restrict__ seg_width, int nseg,
+                                                           __nv_bfloat16* __restrict__ out) {
+  __shared__ int sh_idx[kMaxH];
+  const int64_t q = blockIdx.x;
+  int H = H_full;
+  if (seg_width) H = min(H_full, max(1, seg_width[segment_of(seg_off, nseg, q)]));
+  if (threadIdx.x < H) {
+    const int64_t j = idx[q * H_full + threadIdx.x];
+    sh_idx[threadIdx.x] = (j >= 0 && j < ns) ? (int)j : -1;
+  }
+  __syncthreads();
+  for (int u = threadIdx.x; u < width / 2; u += blockDim.x) {
+    float m0 = -INFINITY, m1 = -INFINITY;
+    for (int n = 0; n < H; ++n) {
+      const int j = sh_idx[n];
+      float x0 = 0.f, x1 = 0.f;
+      if (j >= 0) {
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(x + (int64_t)j * width + 2 * u);
+        x0 = bf_lo(v);
+        x1 = bf_hi(v);
+      }
+      m0 = fmaxf(m0, x0);
+      m1 = fmaxf(m1, x1);
+    }
+    *reinterpret_cast<uint32_t*>(out + q * width + 2 * u) = pack_bf16(m0, m1);
+  }
+}
+
+// [N, A, C] -> [N, C], max over anchors
+__global__ void __launch_bounds__(256) anchor_max_kernel(const __nv_bfloat16* __restrict__ x, int64_t n, int A, int C,
+                                                          __nv_bfloat16* __restrict__ out, int64_t out_ld) {
+  const int half = C / 2;
+  const int64_t total = n * half;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / half;
+    const int c = (int)(i - p * half) * 2;
+    float m0 = -INFINITY, m1 = -INFINITY;
+    for (int a = 0; a < A; ++a) {
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(x + (p * A + a) * C + c);
+      m0 = fmaxf(m0, bf_lo(v));
+      m1 = fmaxf(m1, bf_hi(v));
+    }
+    *reinterpret_cast<uint32_t*>(out + p * out_ld + c) = pack_bf16(m0, m1);
+  }
+}
+
+// out[i] = [ xpad[up_idx[i][0]] (c1) | y[i] (c2) ]   (nearest_upsample + cat)
+__global__ void __launch_bounds__(256) upsample_concat_kernel(const __nv_bfloat16* __restrict__ x, int64_t nx, int c1,
+                                                               const int64_t* __restrict__ up_idx, int up_ld,
+                                                               const __nv_bfloat16* __restrict__ y, int c2, int64_t n,
+                                                               __nv_bfloat16* __restrict__ out) {
+  const int w = (c1 + c2) / 2;
+  const int64_t total = n * w;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / w;
+    const int c = (int)(i - p * w) * 2;
+    uint32_t v = 0;
+    if (c < c1) {
+      const int64_t j = up_idx[p * up_ld];
+      if (j >= 0 && j < nx) v = *reinterpret_cast<const uint32_t*>(x + j * c1 + c);
+    } else {
+      v = *reinterpret_cast<const uint32_t*>(y + p * c2 + (c - c1));
+    }
+    *reinterpret_cast<uint32_t*>(out + p * (c1 + c2) + c) = v;
+  }
+}
+
+static inline int elementwise_blocks(int64_t work) {
+  int64_t b = ceil_div(work, 256);
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace se3et
+
+using namespace se3et;
+
+extern "C" int se3et_kpconv_tables(int32_t* kidx_15x6, int32_t* ridx_6x6) {
+  if (!kidx_15x6 || !ridx_6x6) return SE3ET_ERR_ARG;
+  for (int k = 0; k < 15; ++k)
+    for (int r = 0; r < 6; ++r) kidx_15x6[k * 6 + r] = kidx_tab(k, r);
+  for (int a = 0; a < 6; ++a)
+    for (int r = 0; r < 6; ++r) ridx_6x6[a * 6 + r] = ridx_tab(a, r);
+  return SE3ET_OK;
+}
+
+extern "C" int se3et_kpconv_gather(const float* q_pts, const float* s_pts, const int64_t* neighbors, int64_t nq,
+                                   int64_t ns, int64_t h, const void* x_bf16, int64_t cin,
+                                   const float* kernel_points_15x3, float kp_extent, void* out_bf16, int64_t kpad,
+                                   se3et_stream_t stream) {
+  if (nq < 0 || ns < 0 || h <= 0 || h > kMaxH || cin <= 0 || !(kp_extent > 0.f)) return SE3ET_ERR_ARG;
+  if (kpad < 36 * cin || kpad % 8 != 0) return SE3ET_ERR_ARG;
+  if (nq == 0) return SE3ET_OK;
+  if (!q_pts || !s_pts || !neighbors || !x_bf16 || !kernel_points_15x3 || !out_bf16) return SE3ET_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const auto* x = static_cast<const __nv_bfloat16*>(x_bf16);
+  auto* out = static_cast<__nv_bfloat16*>(out_bf16);
+  const int width = 6 * (int)cin;
+  if (cin % 2 == 0) {
+    const int threads = width / 2 >= 256 ? 256 : (width / 2 <= 64 ? 64 : 128);
+    kpconv_gather_kernel<true><<<(unsigned)nq, threads, 0, st>>>(q_pts, s_pts, neighbors, (int)h, ns, x, (int)cin,
+                                                                kernel_points_15x3, 1.f / kp_extent, out, (int)kpad);
+  } else {
+    kpconv_gather_kernel<false><<<(unsigned)nq, 64, 0, st>>>(q_pts, s_pts, neighbors, (int)h, ns, x, (int)cin,
+                                                            kernel_points_15x3, 1.f / kp_extent, out, (int)kpad);
+  }
+  SE3ET_LAUNCH_CHECK();
+  return SE3ET_OK;
+}
+
+extern "C" int se3et_groupnorm_stats(const float* y, int64_t rows, int64_t channels, int64_t groups,
+                                     const int64_t* seg_offsets, int64_t nseg, int64_t rows_per_point, double* stats,
+                                     se3et_stream_t stream) {
+  if (rows < 0 || channels <= 0 || groups <= 0 || channels % groups || nseg <= 0 || rows_per_point <= 0 || !stats ||
+      !seg_offsets)
+    return SE3ET_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SE3ET_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * nseg * groups, st));
+  if (rows == 0) return SE3ET_OK;
+  if (!y) return SE3ET_ERR_ARG;
+  const int cpg = (int)(channels / groups);
+  const int threads = channels >= 256 ? 256 : (int)((channels + 31) / 32 * 32);
+  dim3 grid((unsigned)ceil_div(rows, kStatRows), (unsigned)ceil_div(channels, threads));
+  const size_t smem = sizeof(float) * 2 * (threads / (cpg < threads ? cpg : threads) + 2);
+  groupnorm_stats_kernel<<<grid, threads, smem, st>>>(y, rows, (int)channels, cpg, seg_offsets, (int)nseg,
+                                                  (int)rows_per_point, stats);
+  SE3ET_LAUNCH_CHECK();
+  return SE3ET_OK;
+}
+
+extern "C" int se3et_groupnorm_apply(const float* ya, const double* stats_a, const float* gamma_a, const float* beta_a,
+                                     const float* yb, const double* stats_b, const float* gamma_b, const float* beta_b,
+                                     const void* resid_bf16, int64_t rows, int64_t channels, int64_t groups,
+                                     const int64_t* seg_offsets, int64_t nseg, int64_t rows_per_point, float eps,
+                                     float leaky_slope, float* out_f32, void* out_bf16, se3et_stream_t stream) {
+  if (rows < 0 || channels <= 0 || channels % 4 || groups <= 0 || channels % groups || nseg <= 0 ||
+      rows_per_point <= 0 || !seg_offsets)
+    return SE3ET_ERR_ARG;
+  if (rows == 0) return SE3ET_OK;
+  if (!ya || !stats_a || !gamma_a || !beta_a || (!out_f32 && !out_bf16)) return SE3ET_ERR_ARG;
+  if (yb && (!stats_b || !gamma_b || !beta_b)) return SE3ET_ERR_ARG;
+  NormSide a{ya, stats_a, gamma_a, beta_a};
+  NormSide b{yb, stats_b, gamma_b, beta_b};
+  groupnorm_apply_kernel<<<elementwise_blocks(rows * channels / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      a, b, static_cast<const __nv_bfloat16*>(resid_bf16), rows, (int)channels, (int)(channels / groups), seg_offsets,
+      (int)nseg, (int)rows_per_point, eps, leaky_slope, out_f32, static_cast<__nv_bfloat16*>(out_bf16));
+  SE3ET_LAUNCH_CHECK();
+  return SE3ET_OK;
+}
+
+extern "C" int se3et_maxpool_nbr(const void* x_bf16, int64_t ns, int64_t width, const int64_t* neighbors, int64_t nq,
+                                 int64_t h, const int64_t* seg_offsets, const int32_t* seg_width, int64_t nseg,
+                                 void* out_bf16, se3et_stream_t stream) {
+  if (seg_width && (!seg_offsets || nseg <= 0)) return SE3ET_ERR_ARG;
+  if (nq < 0 || ns < 0 || h <= 0 || h > kMaxH || width <= 0 || width % 2) return SE3ET_ERR_ARG;
+  if (nq == 0) return SE3ET_OK;
+  if (!x_bf16 || !neighbors || !out_bf16) return SE3ET_ERR_ARG;
+  const int threads = width / 2 >= 256 ? 256 : (width / 2 <= 64 ? 64 : 128);
+  maxpool_nbr_kernel<<<(unsigned)nq, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x_bf16), ns, (int)width, neighbors, (int)h, seg_offsets, seg_width, (int)nseg,
+      static_cast<__nv_bfloat16*>(out_bf16));
+  SE3ET_LAUNCH_CHECK();
+  return SE3ET_OK;
+}
+
+extern "C" int se3et_anchor_max(const void* x_bf16, int64_t n, int64_t anchors, int64_t channels, void* out_bf16,
+                                int64_t out_ld, se3et_stream_t stream) {
+  if (n < 0 || anchors <= 0 || channels <= 0 || channels % 2 || out_ld < channels || out_ld % 2) return SE3ET_ERR_ARG;
+  if (n == 0) return SE3ET_OK;
+  if (!x_bf16 || !out_bf16) return SE3ET_ERR_ARG;
+  anchor_max_kernel<<<elementwise_blocks(n * channels / 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x_bf16), n, (int)anchors, (int)channels, static_cast<__nv_bfloat16*>(out_bf16),
+      out_ld);
+  SE3ET_LAUNCH_CHECK();
+  return SE3ET_OK;
+}
+
+extern "C" int se3et_upsample_concat(const void* x_bf16, int64_t nx, int64_t c1, const int64_t* up_idx, int64_t up_ld,
+                                     const void* y_bf16, int64_t c2, int64_t n, void* out_bf16,
+                                     se3et_stream_t stream) {
+  if (n < 0 || nx < 0 || c1 <= 0 || c2 < 0 || c1 % 2 || c2 % 2 || up_ld <= 0) return SE3ET_ERR_ARG;
+  if (n == 0) return SE3ET_OK;
+  if (!x_bf16 || !up_idx || !out_bf16 || (c2 > 0 && !y_bf16)) return SE3ET_ERR_ARG;
+  upsample_concat_kernel<<<elementwise_blocks(n * (c1 + c2) / 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x_bf16), nx, (int)c1, up_idx, (int)up_ld,
+      static_cast<const __nv_bfloat16*>(y_bf16), (int)c2, n, static_cast<__nv_bfloat16*>(out_bf16));
+  SE3ET_LAUNCH_CHECK();
+  return SE3ET_OK;
+}

@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(kQueryWarps * 32) radius_query_kernel(
     const float* __restrict__ q, int64_t nq, const int64_t* __restrict__ q_off, const int64_t* __restrict__ s_off,
     int batch, const float* __restrict__ mins, const float4* __restrict__ sorted, const uint32_t* __restrict__ start,
     uint32_t mask, float inv_cell, float r2, int32_t* counts, int64_t* out, int64_t width, int64_t ns_total,
-    int32_t* status) {
+    int32_t* status, int32_t* cloud_max) {
   __shared__ unsigned long long sh_keys[kQueryWarps][kHitCap];
   __shared__ int sh_excl[kQueryWarps][32];
   __shared__ int sh_start[kQueryWarps][32];
@@ -530,6 +530,7 @@ __global__ void __launch_bounds__(kQueryWarps * 32) radius_query_kernel(
   if (lane == 0) {
     if (counts) counts[qi] = nhit;
     atomicMax(&status[SE3ET_STATUS_MAX_COUNT], nhit);
+    if (cloud_max) atomicMax(&cloud_max[b], nhit);
   }
   if (!out || width <= 0) return;
   int64_t* row = out + qi * width;
@@ -688,7 +689,8 @@ extern "C" int se3et_radius_neighbors_workspace_bytes(int64_t nq_total, int64_t 
 extern "C" int se3et_radius_neighbors(const float* q_points, const float* s_points, const int64_t* q_lengths,
                                       const int64_t* s_lengths, int64_t nq_total, int64_t ns_total, int64_t batch,
                                       float radius, int32_t* counts, int64_t* out, int64_t width, int32_t* status,
-                                      void* workspace, size_t workspace_bytes, se3et_stream_t stream) {
+                                      int32_t* cloud_max, void* workspace, size_t workspace_bytes,
+                                      se3et_stream_t stream) {
   if (!q_lengths || !s_lengths || !status || !workspace || nq_total < 0 || ns_total < 0 || batch <= 0 ||
       width < 0 || !(radius > 0.f) || ns_total >= (int64_t)1 << 31 || nq_total >= (int64_t)1 << 31)
     return SE3ET_ERR_ARG;
@@ -703,6 +705,7 @@ extern "C" int se3et_radius_neighbors(const float* q_points, const float* s_poin
 
   init_offsets_bounds_kernel<<<1, 256, 0, st>>>(q_lengths, w.q_off, s_lengths, w.s_off, (int)batch, w.bounds, status);
   SE3ET_LAUNCH_CHECK();
+  if (cloud_max) SE3ET_CUDA_CHECK(cudaMemsetAsync(cloud_max, 0, sizeof(int32_t) * batch, st));
   SE3ET_CUDA_CHECK(cudaMemsetAsync(w.hist, 0, sizeof(uint32_t) * (w.table + 1), st));
   SE3ET_CUDA_CHECK(cudaMemsetAsync(w.cursor, 0, sizeof(uint32_t) * (w.table + 1), st));
   if (ns_total > 0) {
@@ -728,7 +731,7 @@ extern "C" int se3et_radius_neighbors(const float* q_points, const float* s_poin
   if (nq_total > 0) {
     radius_query_kernel<<<(int)ceil_div(nq_total, kQueryWarps), kQueryWarps * 32, 0, st>>>(
         q_points, nq_total, w.q_off, w.s_off, (int)batch, w.mins, w.sorted, w.start, mask, inv_cell, r2, counts, out,
-        width, ns_total, status);
+        width, ns_total, status, cloud_max);
     SE3ET_LAUNCH_CHECK();
   }
   return SE3ET_OK;

@@ -81,7 +81,7 @@ def grid_subsampling(points, lengths, normals, voxel_size):
 
 def radius_neighbors_raw(q_points, s_points, q_lengths, s_lengths, radius, width, want_counts=False):
     """One launch sequence writing the first `width` sorted neighbours of every query (no sync).
-    Returns (neighbors or None, counts or None, status)."""
+    Returns (neighbors or None, counts or None, status); status = SE3ET_STATUS_WORDS words + per-cloud max counts."""
     _check(q_points, "q_points", torch.float32, "float")
     _check(s_points, "s_points", torch.float32, "float")
     dev = q_points.device
@@ -95,11 +95,13 @@ def radius_neighbors_raw(q_points, s_points, q_lengths, s_lengths, radius, width
     ws = _lib.workspace.get(nbytes.value, dev)
     out = torch.empty((nq, width), dtype=torch.int64, device=dev) if width > 0 else None
     counts = torch.empty((max(nq, 1),), dtype=torch.int32, device=dev) if want_counts else None
-    status = torch.empty((_lib.SE3ET_STATUS_WORDS,), dtype=torch.int32, device=dev)
+    # status words followed by the per-cloud maximum counts (one small buffer, read together)
+    status = torch.empty((_lib.SE3ET_STATUS_WORDS + b,), dtype=torch.int32, device=dev)
+    cloud_max = status[_lib.SE3ET_STATUS_WORDS:]
     _lib.check(L.se3et_radius_neighbors(
         _lib.ptr(q_points), _lib.ptr(s_points), _lib.ptr(q_lengths), _lib.ptr(s_lengths), _lib.i64(nq), _lib.i64(ns),
         _lib.i64(b), _lib.f32(radius), _lib.ptr(counts), _lib.ptr(out), _lib.i64(width), _lib.ptr(status),
-        _lib.ptr(ws), ctypes.c_size_t(ws.numel()), _lib.stream_ptr()), "radius_neighbors")
+        _lib.ptr(cloud_max), _lib.ptr(ws), ctypes.c_size_t(ws.numel()), _lib.stream_ptr()), "radius_neighbors")
     return out, counts, status
 
 

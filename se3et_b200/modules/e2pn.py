@@ -1,0 +1,419 @@
+"""E2PN equivariant KPConv blocks on the CUDA path -- drop-in mirrors of
+geotransformer/modules/e2pn/blocks_epn.py (same class names, constructor arguments, forward signatures and
+state_dict keys: `weights`, `kernel_points`, `anchors`, `quotient_anchors`, `kidx_rot`, `ridx_rot`, `mlp.*`,
+`norm.norm.*`), plus the invariant decoder pieces of geotransformer/modules/kpconv/modules.py.
+
+Execution model: activations travel between blocks as bf16 (N, A, C) tensors; every Linear / KPConv contraction is
+one tcgen05 GEMM producing fp32 pre-norm values; GroupNorm statistics are per point-cloud PAIR (`seg`: int64
+offsets into the stacked point axis; None = the whole tensor is one pair, exactly the reference's behaviour).
+fp32 inputs are accepted everywhere and rounded to bf16 once.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.nn.parameter import Parameter
+
+from .. import _lib
+from ..ops import e2pn_ops as K
+from ..ops.gemm import linear_bf16
+from . import octahedral
+
+
+def _act(x):
+    return x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+
+
+def _seg(seg, n_points, device):
+    if seg is None:
+        return torch.tensor([0, n_points], dtype=torch.int64, device=device)
+    return seg
+
+
+class _Bf16Cache:
+    """bf16 copy of an fp32 parameter, refreshed when the parameter changes (in-place updates bump _version)."""
+
+    def __init__(self):
+        self._key, self._val = None, None
+
+    def get(self, p, transform=None):
+        key = (p.data_ptr(), p._version, p.device)
+        if key != self._key:
+            with torch.no_grad():
+                v = p.detach() if transform is None else transform(p.detach())
+                self._val = v.to(torch.bfloat16).contiguous()
+            self._key = key
+        return self._val
+
+
+class GroupNormEPN(nn.Module):
+    """blocks_epn.py:684-701. forward(x): x (N, A, C) -> normalised (N, A, C)."""
+
+    def __init__(self, num_groups, num_channels):
+        super().__init__()
+        self.num_groups = num_groups
+        self.num_channels = num_channels
+        self.norm = nn.GroupNorm(self.num_groups, self.num_channels)
+
+    def fused(self, y, seg, rows_per_point, slope, out_f32=False, out_bf16=True, other=None, resid=None):
+        """y: fp32 (rows, C) pre-norm. other = (y_b, GroupNormEPN_b) adds a second normalised operand."""
+        stats = K.groupnorm_stats(y, self.num_groups, seg, rows_per_point)
+        kw = {}
+        if other is not None:
+            yb, nb = other
+            kw = dict(yb=yb, stats_b=K.groupnorm_stats(yb, nb.num_groups, seg, rows_per_point),
+                      gamma_b=nb.norm.weight, beta_b=nb.norm.bias)
+        return K.groupnorm_apply(y, stats, self.norm.weight, self.norm.bias, self.num_groups, seg, rows_per_point,
+                                 slope=slope, resid=resid, out_f32=out_f32, out_bf16=out_bf16, eps=self.norm.eps, **kw)
+
+    def forward(self, x, seg=None):
+        shape = x.shape
+        rpp = shape[1] if x.dim() == 3 else 1
+        y = x.reshape(-1, shape[-1]).float().contiguous()
+        f32 = x.dtype == torch.float32
+        of, ob = self.fused(y, _seg(seg, shape[0], x.device), rpp, slope=1.0, out_f32=f32, out_bf16=not f32)
+        return (of if f32 else ob).reshape(shape).squeeze()
+
+
+class KPConvInterSO3(nn.Module):
+    """blocks_epn.py:18-552, for the configuration SE3ET uses (kanchor 6, quotient_factor 4, 15 kernel points,
+    'linear' influence, 'sum' aggregation, non_sep_conv, rot_by_permute, fixed 'center')."""
+
+    def __init__(self, kernel_size, kanchor, in_channels, out_channels, KP_extent, radius, KP_influence='linear',
+                 aggregation_mode='sum', deformable=False, modulated=False, epn_kernel=False, equiv_mode_kp=False,
+                 non_sep_conv=False, rot_by_permute=False, fixed_kernel_points='center', quotient_factor=1,
+                 ignore_steer_constraint=False, gather_by_idxing=False):
+        super().__init__()
+        ok = (kernel_size == 15 and kanchor == 6 and quotient_factor == 4 and KP_influence == 'linear' and
+              aggregation_mode == 'sum' and non_sep_conv and rot_by_permute and fixed_kernel_points == 'center' and
+              not deformable and not epn_kernel and not ignore_steer_constraint)
+        if not ok:
+            raise NotImplementedError("se3et_b200.KPConvInterSO3 supports the SE3ET configuration only "
+                                      "(K=15, kanchor=6, quotient_factor=4, linear/sum, non_sep_conv, rot_by_permute)")
+        self.kanchor, self.K, self.K_real = kanchor, kernel_size, octahedral.K_REAL
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.radius, self.KP_extent = radius, KP_extent
+        self.KP_influence, self.aggregation_mode = KP_influence, aggregation_mode
+        self.quotient_factor = quotient_factor
+        t = octahedral.tables()
+        self.kernel_points = Parameter(torch.tensor(t["kp_unit"] * 0.7 * radius, dtype=torch.float32),
+                                       requires_grad=False)
+        self.quotient_anchors = Parameter(torch.tensor(t["quotient"], dtype=torch.float32), requires_grad=False)
+        self.anchors = Parameter(torch.tensor(t["anchors"], dtype=torch.float32), requires_grad=False)
+        kidx = torch.tensor(t["kidx"], dtype=torch.int64)  # (K, R)
+        ridx = torch.tensor(t["ridx"], dtype=torch.int64)  # (A, R)
+        self.register_buffer('kidx_rot', kidx[:, None, :].expand(-1, kanchor, -1).contiguous())
+        self.register_buffer('ridx_rot', ridx[None, :, :].expand(kernel_size, -1, -1).contiguous())
+        self.weights = Parameter(torch.zeros((self.K_real, kanchor, in_channels, out_channels), dtype=torch.float32),
+                                 requires_grad=True)
+        self.reset_parameters()
+        self._w_cache = _Bf16Cache()
+        self._tables_checked = False
+
+    def reset_parameters(self):
+        nn.init.kaiming_uniform_(self.weights, a=math.sqrt(5))
+
+    def _check_tables(self):
+        if not self._tables_checked:
+            kidx, ridx = K.builtin_tables()
+            if not (np.array_equal(self.kidx_rot[:, 0, :].cpu().numpy(), kidx) and
+                    np.array_equal(self.ridx_rot[0].cpu().numpy(), ridx)):
+                raise RuntimeError("KPConvInterSO3: kidx_rot/ridx_rot differ from the tables compiled into the kernel")
+            self._tables_checked = True
+
+    def _w_flat(self):
+        """(Cout, kpad) bf16, K-major: W[kc, a', c, d] -> row d, column (kc*6 + a')*Cin + c (zero padded)."""
+        kpad = K.kpad_for(self.in_channels)
+
+        def tr(w):
+            flat = w.reshape(-1, self.out_channels).t()
+            if kpad != flat.shape[1]:
+                flat = torch.nn.functional.pad(flat, (0, kpad - flat.shape[1]))
+            return flat
+        return self._w_cache.get(self.weights, tr)
+
+    def forward(self, q_pts, s_pts, neighb_inds, x):
+        """-> fp32 (Nq, A, Cout), pre-norm (blocks_epn.py:454-546)."""
+        self._check_tables()
+        a = K.kpconv_gather(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), self.kernel_points,
+                            self.KP_extent)
+        y, _ = linear_bf16(a, self._w_flat())
+        return y.view(-1, self.kanchor, self.out_channels)
+
+    def __repr__(self):
+        return 'KPConvInterSO3(radius: {:.2f}, extent: {:.2f}, in_feat: {:d}, out_feat: {:d})'.format(
+            self.radius, self.KP_extent, self.in_channels, self.out_channels)
+
+
+class UnaryBlockEPN(nn.Module):
+    """blocks_epn.py:639-665: Linear -> GroupNormEPN -> LeakyReLU(0.1) (unless no_relu)."""
+
+    def __init__(self, in_dim, out_dim, group_norm, bn_momentum, no_relu=False):
+        super().__init__()
+        self.bn_momentum, self.no_relu = bn_momentum, no_relu
+        self.in_dim, self.out_dim = in_dim, out_dim
+        self.mlp = nn.Linear(in_dim, out_dim)
+        self.norm = GroupNormEPN(group_norm, out_dim)
+        self.leaky_relu = nn.LeakyReLU(0.1)
+        self._w_cache = _Bf16Cache()
+
+    def pre_norm(self, x):
+        """fp32 (N*A, Cout) Linear output."""
+        x2 = _act(x).reshape(-1, self.in_dim)
+        y, _ = linear_bf16(x2, self._w_cache.get(self.mlp.weight), self.mlp.bias)
+        return y
+
+    def forward(self, x, batch=None, seg=None):
+        n, a = x.shape[0], x.shape[1]
+        y = self.pre_norm(x)
+        _, out = self.norm.fused(y, _seg(seg, n, x.device), a, slope=1.0 if self.no_relu else 0.1)
+        return out.view(n, a, self.out_dim)
+
+
+class LastUnaryBlockEPN(nn.Module):
+    """blocks_epn.py:668-681."""
+
+    def __init__(self, in_dim, out_dim, bias=True):
+        super().__init__()
+        self.in_dim, self.out_dim = in_dim, out_dim
+        self.mlp = nn.Linear(in_dim, out_dim, bias=bias)
+        self._w_cache = _Bf16Cache()
+
+    def forward(self, x):
+        y, _ = linear_bf16(_act(x).reshape(-1, self.in_dim), self._w_cache.get(self.mlp.weight), self.mlp.bias)
+        return y.view(*x.shape[:-1], self.out_dim)
+
+
+class KPConvInterSO3Block(nn.Module):
+    """blocks_epn.py:703-743: conv -> GroupNormEPN -> LeakyReLU."""
+
+    def __init__(self, block_name, in_dim, out_dim, radius, sigma, group_norm, config):
+        super().__init__()
+        self.block_name, self.in_dim, self.out_dim = block_name, in_dim, out_dim
+        self.conv = KPConvInterSO3(config.num_kernel_points, config.kanchor, in_dim, out_dim, sigma, radius,
+                                   config.KP_influence, config.aggregation_mode, epn_kernel=config.epn_kernel,
+                                   equiv_mode_kp=config.equiv_mode_kp, non_sep_conv=config.non_sep_conv,
+                                   rot_by_permute=config.rot_by_permute,
+                                   fixed_kernel_points=config.fixed_kernel_points,
+                                   quotient_factor=config.quotient_factor,
+                                   ignore_steer_constraint=config.ignore_steer_constraint,
+                                   gather_by_idxing=config.gather_by_idxing)
+        self.norm = GroupNormEPN(group_norm, out_dim)
+        self.leaky_relu = nn.LeakyReLU(0.1)
+
+    def fused(self, x, q_pts, s_pts, neighb_inds, seg, out_f32):
+        y = self.conv(q_pts, s_pts, neighb_inds, x).view(-1, self.out_dim)
+        return self.norm.fused(y, seg, self.conv.kanchor, slope=0.1, out_f32=out_f32, out_bf16=not out_f32)
+
+    def forward(self, x, q_pts, s_pts, neighb_inds, seg=None):
+        _, out = self.fused(x, q_pts, s_pts, neighb_inds, _seg(seg, q_pts.shape[0], q_pts.device), False)
+        return out.view(-1, self.conv.kanchor, self.out_dim)
+
+
+class SimpleBlockEPN(nn.Module):
+    """blocks_epn.py:770-796: interso3 block, then a second GroupNormEPN + LeakyReLU."""
+
+    def __init__(self, block_name, in_dim, out_dim, radius, sigma, group_norm, config):
+        super().__init__()
+        if not config.non_sep_conv:
+            raise NotImplementedError("separable (intra-SO3) convolution is not part of the SE3ET path")
+        self.block_name, self.in_dim, self.out_dim = block_name, in_dim, out_dim
+        self.non_sep_conv = config.non_sep_conv
+        self.interso3 = KPConvInterSO3Block(block_name, in_dim, out_dim, radius, sigma, group_norm, config)
+        self.norm = GroupNormEPN(group_norm, out_dim)
+        self.leaky_relu = nn.LeakyReLU(0.1)
+
+    def forward(self, x, q_pts, s_pts, neighb_inds, seg=None):
+        seg = _seg(seg, q_pts.shape[0], q_pts.device)
+        y, _ = self.interso3.fused(x, q_pts, s_pts, neighb_inds, seg, out_f32=True)
+        _, out = self.norm.fused(y, seg, 6, slope=0.1)
+        return out.view(-1, 6, self.out_dim)
+
+
+class ResnetBottleneckBlockEPN(nn.Module):
+    """blocks_epn.py:798-852."""
+
+    def __init__(self, block_name, in_dim, out_dim, radius, sigma, group_norm, config):
+        super().__init__()
+        if not config.non_sep_conv:
+            raise NotImplementedError("separable (intra-SO3) convolution is not part of the SE3ET path")
+        self.bn_momentum = config.batch_norm_momentum
+        self.block_name, self.in_dim, self.out_dim = block_name, in_dim, out_dim
+        self.relu_end = True
+        self.leaky_relu = nn.LeakyReLU(0.1)
+        self.non_sep_conv = config.non_sep_conv
+        if in_dim != out_dim // 4:
+            self.unary1 = UnaryBlockEPN(in_dim, out_dim // 4, group_norm, self.bn_momentum)
+        else:
+            self.unary1 = nn.Identity()
+        self.interso3 = KPConvInterSO3Block(block_name, out_dim // 4, out_dim // 4, radius, sigma, group_norm, config)
+        self.norm = GroupNormEPN(group_norm, out_dim // 4)
+        self.unary2 = UnaryBlockEPN(out_dim // 4, out_dim, group_norm, self.bn_momentum, no_relu=self.relu_end)
+        if in_dim != out_dim:
+            self.skip_conv = UnaryBlockEPN(in_dim, out_dim, group_norm, self.bn_momentum, no_relu=self.relu_end)
+        else:
+            self.skip_conv = nn.Identity()
+
+    def forward(self, x, q_pts, s_pts, neighb_inds, seg=None, s_seg=None, sub_width=None):
+        """seg: pair offsets of the query level; s_seg: of the support level (needed only when strided);
+        sub_width: per-pair column count of the pooling matrix when several pairs share neighb_inds."""
+        nq = q_pts.shape[0]
+        seg = _seg(seg, nq, q_pts.device)
+        x = _act(x).contiguous()
+        skip = x
+        if isinstance(self.unary1, UnaryBlockEPN):
+            s_seg = _seg(s_seg, s_pts.shape[0], s_pts.device) if 'strided' in self.block_name else seg
+            y = self.unary1(x, seg=s_seg)
+        else:
+            y = x
+        f, _ = self.interso3.fused(y, q_pts, s_pts, neighb_inds, seg, out_f32=True)
+        _, y = self.norm.fused(f, seg, 6, slope=0.1)
+        pre2 = self.unary2.pre_norm(y.view(nq, 6, -1))
+        if 'strided' in self.block_name:
+            skip = K.maxpool_nbr(skip, neighb_inds.contiguous(), seg if sub_width is not None else None, sub_width)
+        if isinstance(self.skip_conv, UnaryBlockEPN):
+            pre_s = self.skip_conv.pre_norm(skip)
+            _, out = self.unary2.norm.fused(pre2, seg, 6, slope=0.1, other=(pre_s, self.skip_conv.norm))
+        else:
+            _, out = self.unary2.norm.fused(pre2, seg, 6, slope=0.1, resid=skip.contiguous())
+        return out.view(nq, 6, self.out_dim)
+
+
+class InvOutBlockEPN(nn.Module):
+    """blocks_epn.py:854-926 with att_pooling / att_permute off (the SE3ET configs): max over anchors."""
+
+    def __init__(self, block_name, in_dim, config):
+        super().__init__()
+        if getattr(config, 'att_pooling', False) or getattr(config, 'att_permute', False):
+            raise NotImplementedError("attentive pooling is not used by any SE3ET config")
+        self.block_name, self.in_dim = block_name, in_dim
+
+    def forward(self, x, q_pts=None, s_pts=None, neighb_inds=None):
+        return K.anchor_max(_act(x).contiguous())
+
+
+class LiftBlockEPN(nn.Module):
+    """blocks_epn.py:993-1004: (N, C) -> (N, A, C)."""
+
+    def __init__(self, block_name, in_dim, config):
+        super().__init__()
+        self.block_name, self.in_dim, self.kanchor = block_name, in_dim, config.kanchor
+
+    def forward(self, x):
+        return x.unsqueeze(1).expand(-1, self.kanchor, -1)
+
+
+# ---- invariant decoder pieces (geotransformer/modules/kpconv/modules.py:33-101, functional.py:6-22) ----------
+
+
+class GroupNorm(nn.Module):
+    def __init__(self, num_groups, num_channels):
+        super().__init__()
+        self.num_groups, self.num_channels = num_groups, num_channels
+        self.norm = nn.GroupNorm(self.num_groups, self.num_channels)
+
+    def forward(self, x, seg=None):
+        y = x.float().contiguous()
+        seg = _seg(seg, x.shape[0], x.device)
+        stats = K.groupnorm_stats(y, self.num_groups, seg, 1)
+        _, out = K.groupnorm_apply(y, stats, self.norm.weight, self.norm.bias, self.num_groups, seg, 1, slope=1.0,
+                                   eps=self.norm.eps)
+        return out.squeeze()
+
+
+class UnaryBlock(nn.Module):
+    def __init__(self, in_channels, out_channels, group_norm, has_relu=True, bias=True, layer_norm=False):
+        super().__init__()
+        if layer_norm:
+            raise NotImplementedError("layer_norm UnaryBlock is not used on the SE3ET path")
+        self.in_channels, self.out_channels, self.group_norm = in_channels, out_channels, group_norm
+        self.mlp = nn.Linear(in_channels, out_channels, bias=bias)
+        self.norm = GroupNorm(group_norm, out_channels)
+        self.leaky_relu = nn.LeakyReLU(0.1) if has_relu else None
+        self._w_cache = _Bf16Cache()
+
+    def forward(self, x, seg=None):
+        y, _ = linear_bf16(_act(x).contiguous(), self._w_cache.get(self.mlp.weight), self.mlp.bias)
+        seg = _seg(seg, x.shape[0], x.device)
+        stats = K.groupnorm_stats(y, self.norm.num_groups, seg, 1)
+        _, out = K.groupnorm_apply(y, stats, self.norm.norm.weight, self.norm.norm.bias, self.norm.num_groups, seg, 1,
+                                   slope=0.1 if self.leaky_relu is not None else 1.0, eps=self.norm.norm.eps)
+        return out
+
+
+class LastUnaryBlock(nn.Module):
+    def __init__(self, in_channels, out_channels, bias=True):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.mlp = nn.Linear(in_channels, out_channels, bias=bias)
+        self._w_cache = _Bf16Cache()
+
+    def forward(self, x, out_bf16=False):
+        f, b = linear_bf16(_act(x).contiguous(), self._w_cache.get(self.mlp.weight), self.mlp.bias,
+                           out_f32=not out_bf16, out_bf16=out_bf16)
+        return b if out_bf16 else f
+
+
+def nearest_upsample(x, upsample_indices):
+    """kpconv/functional.py:6-22 (first neighbour column, zero shadow row)."""
+    x = _act(x).contiguous()
+    empty = torch.empty((upsample_indices.shape[0], 0), dtype=torch.bfloat16, device=x.device)
+    return K.upsample_concat(x, upsample_indices, empty)
+
+
+class E2PN(nn.Module):
+    """Backbone of experiments/se3et*.3dmatch/backbone.py:8-77 (num_stages=4) and se3eti.kitti/backbone.py:8-99
+    (num_stages=5).  forward(feats, data_dict) -> [feats_f, (latents...), feats_c]; feats_f is
+    fp32 (N_1, output_dim), feats_c is the equivariant (N_last, A, 16*init_dim or 32*init_dim) tensor (bf16).
+    data_dict may carry 'pair_offsets': per-level int64 offsets so that several pairs share one launch."""
+
+    def __init__(self, input_dim, output_dim, init_dim, init_radius, init_sigma, group_norm, config_epn,
+                 num_stages=4):
+        super().__init__()
+        R, S, G, c, d = init_radius, init_sigma, group_norm, config_epn, init_dim
+        self.num_stages = num_stages
+        self.preprocess = LiftBlockEPN('lift_epn', input_dim, c)
+        self.encoder1_1 = SimpleBlockEPN('simple', input_dim, d, R, S, G, c)
+        self.encoder1_2 = ResnetBottleneckBlockEPN('resnetb', d, d * 2, R, S, G, c)
+        width = d * 2
+        for s in range(2, num_stages + 1):
+            lo, hi = 2 ** (s - 2), 2 ** (s - 1)
+            setattr(self, 'encoder%d_1' % s, ResnetBottleneckBlockEPN('resnetb_strided', width, width, R * lo, S * lo, G, c))
+            setattr(self, 'encoder%d_2' % s, ResnetBottleneckBlockEPN('resnetb', width, width * 2, R * hi, S * hi, G, c))
+            setattr(self, 'encoder%d_3' % s, ResnetBottleneckBlockEPN('resnetb', width * 2, width * 2, R * hi, S * hi, G, c))
+            setattr(self, 'equ2inv%d' % s, InvOutBlockEPN('inv_epn', width * 2, c))
+            width *= 2
+        for s in range(num_stages - 1, 2, -1):  # decoder{S-1} ... decoder3: UnaryBlock(24d*2^(s-3) -> 8d*2^(s-3))
+            k = 2 ** (s - 3)
+            setattr(self, 'decoder%d' % s, UnaryBlock(d * 24 * k, d * 8 * k, G))
+        self.decoder2 = LastUnaryBlock(d * 12, output_dim)
+        self.equ2inv = InvOutBlockEPN('inv_epn', output_dim, c)
+
+    def forward(self, feats, data_dict):
+        pts, nb = data_dict['points'], data_dict['neighbors']
+        sub, up = data_dict['subsampling'], data_dict['upsampling']
+        segs = data_dict.get('pair_offsets', [None] * len(pts))
+        widths = data_dict.get('subsampling_width', [None] * len(pts))
+        x = self.preprocess(_act(feats)).contiguous()
+        x = self.encoder1_1(x, pts[0], pts[0], nb[0], seg=segs[0])
+        x = self.encoder1_2(x, pts[0], pts[0], nb[0], seg=segs[0])
+        inv = {}
+        for s in range(2, self.num_stages + 1):
+            l = s - 1
+            x = getattr(self, 'encoder%d_1' % s)(x, pts[l], pts[l - 1], sub[l - 1], seg=segs[l], s_seg=segs[l - 1],
+                                                 sub_width=widths[l - 1])
+            x = getattr(self, 'encoder%d_2' % s)(x, pts[l], pts[l], nb[l], seg=segs[l])
+            x = getattr(self, 'encoder%d_3' % s)(x, pts[l], pts[l], nb[l], seg=segs[l])
+            inv[s] = K.anchor_max(x)
+        feats_list = [x]
+        latent = inv[self.num_stages]
+        for s in range(self.num_stages - 1, 1, -1):
+            cat = K.upsample_concat(latent, up[s - 1], inv[s])
+            if s > 2:
+                latent = getattr(self, 'decoder%d' % s)(cat, seg=segs[s - 1])
+            else:
+                latent = self.decoder2(cat)
+            feats_list.append(latent)
+        feats_list.reverse()
+        return feats_list

@@ -13,6 +13,17 @@ def linear_bf16(a, w, bias=None, alpha=1.0, relu=False, out_f32=True, out_bf16=F
     assert a.stride(1) == 1 and w.stride(1) == 1
     m, k = a.shape
     n = w.shape[0]
+    if n % 16 != 0:
+        # the UMMA tile needs N % 16 == 0: zero-pad the weight rows (only reduced-width test configs get here)
+        n_pad = (n + 15) // 16 * 16
+        w_pad = torch.zeros((n_pad, k), dtype=w.dtype, device=w.device)
+        w_pad[:n] = w
+        b_pad = None
+        if bias is not None:
+            b_pad = torch.zeros((n_pad,), dtype=torch.float32, device=w.device)
+            b_pad[:n] = bias
+        of, ob = linear_bf16(a, w_pad, b_pad, alpha, relu, out_f32, out_bf16)
+        return (of[:, :n].contiguous() if of is not None else None, ob[:, :n].contiguous() if ob is not None else None)
     of = torch.empty((m, n), dtype=torch.float32, device=a.device) if out_f32 else None
     ob = torch.empty((m, n), dtype=torch.bfloat16, device=a.device) if out_bf16 else None
     if bias is not None:

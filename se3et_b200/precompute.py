@@ -10,7 +10,16 @@ from .ops import grid_subsample, radius_search_deferred
 
 
 def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, neighbor_limits, normals=None):
+    """`lengths` = [ref, src] reproduces the reference exactly (matrix widths min(max_count, limit), 2000-superpoint
+    cap). `lengths` = [ref_1, src_1, ref_2, src_2, ...] stacks several pairs in one launch sequence: the dict then
+    also carries 'pair_offsets' (per level, int64 [P+1]) and 'subsampling_width' (per level, int32 [P]: the width
+    the reference's subsampling matrix would have for that pair alone), neighbour matrices keep `limit` columns
+    (extra columns are padding) and no host sync is needed for the searches."""
     assert num_stages == len(neighbor_limits)
+    num_pairs = lengths.shape[0] // 2
+    batched = lengths.shape[0] > 2
+    if batched:
+        assert lengths.shape[0] % 2 == 0 and all(l > 0 for l in neighbor_limits)
     _lib.require_cuda(points)
     lengths = lengths.to(points.device)
     if normals is None:
@@ -34,6 +43,7 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
         voxel_size *= 2
 
     neighbors_list, subsampling_list, upsampling_list = [], [], []
+    subsampling_width = []
     pending = []  # (list, index, limit, status)
 
     def search(dst, q, s, ql, sl, r, limit):
@@ -44,6 +54,9 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
         out, status = radius_search_deferred(q, s, ql, sl, r, limit)
         dst.append(out)
         pending.append((dst, len(dst) - 1, limit, status))
+        if batched and dst is subsampling_list:
+            cloud_max = status[_lib.SE3ET_STATUS_WORDS:]
+            subsampling_width.append(cloud_max.view(num_pairs, 2).amax(dim=1).clamp(max=limit).contiguous())
 
     for i in range(num_stages):
         cur_points, cur_lengths = points_list[i], lengths_list[i]
@@ -55,7 +68,7 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
                    neighbor_limits[i + 1])
         radius *= 2
 
-    if pending:
+    if pending and not batched:
         # one transfer for all searches: width is min(max_count, limit) as in ops/radius_search.py:24-27
         stats = torch.stack([p[3] for p in pending]).cpu()
         for (dst, idx, limit, _), st in zip(pending, stats):
@@ -63,7 +76,13 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
             if max_count < limit:
                 dst[idx] = dst[idx][:, :max_count].contiguous()
 
+    extra = {}
+    if batched:
+        zero = lengths_list[0].new_zeros((1,))
+        extra['pair_offsets'] = [torch.cat([zero, l.view(num_pairs, 2).sum(dim=1).cumsum(0)]) for l in lengths_list]
+        extra['subsampling_width'] = subsampling_width
     return {
+        **extra,
         'points': points_list,
         'lengths': lengths_list,
         'neighbors': neighbors_list,
