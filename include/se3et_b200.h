@@ -105,6 +105,17 @@ int se3et_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int6
                     int act, float* out_f32, void* out_bf16, int64_t ldc, int64_t c_batch_stride,
                     se3et_stream_t stream);
 
+/* Grouped variant: problem g (blockIdx.z) reads A rows [a_row0, a_row0 + m_rows) and B rows
+ * [b_row0, b_row0 + n) of the flat operands, groups = int64 [num_groups][6] {a_row0, b_row0, m_rows, c_off,
+ * ldc, unused} on the device; max_m = largest m_rows.  transposed = 1 stores
+ * out_f32[c_off + col * ldc + row] for col < n_valid (n itself is rounded up to the UMMA tile by the caller).
+ * replaces: the `q . proj_p(embedding)` term of RPEMultiHeadAttention (rpe_transformer.py:60,71), computed
+ * as embedding[n] @ (W_p^T q[n]) per query n without materialising proj_p(embedding). */
+int se3et_gemm_grouped_bf16(const void* a, int64_t lda, int64_t a_rows_total, const void* b, int64_t ldb,
+                            int64_t b_rows_total, const int64_t* groups, int64_t num_groups, int64_t max_m, int64_t n,
+                            int64_t n_valid, int64_t k, float alpha, float* out_f32, int64_t ldc, int transposed,
+                            se3et_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * E2PN backbone pieces.  Feature tensors are [point, anchor(6), channel]; activations bf16,
  * pre-norm GEMM outputs fp32.  Segments (`seg_offsets`, nseg+1 point offsets) are point-cloud
@@ -150,6 +161,52 @@ int se3et_anchor_max(const void* x_bf16, int64_t n, int64_t anchors, int64_t cha
 /* nearest_upsample + cat (kpconv/functional.py:6-22, backbone.py:66-72): out[i] = [xpad[up[i][0]] | y[i]]. */
 int se3et_upsample_concat(const void* x_bf16, int64_t nx, int64_t c1, const int64_t* up_idx, int64_t up_ld,
                           const void* y_bf16, int64_t c2, int64_t n, void* out_bf16, se3et_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Superpoint transformer.  Clouds are flat: cloud b owns points [cloud_offsets[b], cloud_offsets[b+1]).
+ * Equivariant states are stored [point, anchor(6), channel] (the reference's (B, A, N, C) transposed back;
+ * every per-row op is layout independent).
+ * ------------------------------------------------------------------------------------------ */
+
+/* GeometricStructureEmbedding.get_embedding_indices (geotransformer.py:69-99): for every ordered pair (n, m) of a
+ * cloud, out_idx4[emb_offsets[b] + n*n_b + m] = {dist/sigma_d, angle_0, angle_1, angle_2} * (180/(sigma_a*pi)),
+ * angles against the 3 nearest neighbours of n (ties: lower index).  angle_k must be 3. */
+int se3et_geo_embed_indices(const float* points, const int64_t* cloud_offsets, int64_t nclouds, int64_t total_points,
+                            int64_t max_cloud, const int64_t* emb_offsets, float sigma_d, float sigma_a,
+                            int64_t angle_k, float* out_idx4, se3et_stream_t stream);
+/* GeometricStructureEmbedding.forward (geotransformer.py:101-115) + SinusoidalPositionalEmbedding
+ * (positional_embedding.py:18-34): out[r] = W_d emb(idx4[r].x) + max_k W_a emb(idx4[r].yzw) + bias_sum, bf16
+ * [rows, channels].  The sinusoids are generated inside the kernel as the tcgen05 A operand. */
+int se3et_geo_embed_project(const float* idx4, int64_t rows, int64_t channels, const void* w_d_bf16,
+                            const void* w_a_bf16, const float* bias_sum, void* out_bf16, se3et_stream_t stream);
+/* Fused attention: RPEMultiHeadAttention equivariant branch (rpe_transformer.py:56-131, bias = q.proj_p(emb)) and
+ * MultiHeadAttention with 4-D value (vanilla_transformer.py:58-85).  problems: int64 [num_problems][5]
+ * {q_start, n_q, kv_start, n_kv, bias_off}.  Strides in elements: *_pt per point, *_an per anchor (0 = none).
+ * bias (optional, fp32): [bias_off + ((i*A + a)*H + h)*n_kv + m].  out row = (q_start + i)*A + a, pitch ldo. */
+int se3et_flash_attention(const void* q, int64_t q_pt, int64_t q_an, const void* k, int64_t k_pt, int64_t k_an,
+                          const void* v, int64_t v_pt, int64_t v_an, const float* bias, const int64_t* problems,
+                          int64_t num_problems, int64_t max_q, int64_t anchors, int64_t heads, int64_t head_dim,
+                          float scale, void* out_bf16, int64_t ldo, se3et_stream_t stream);
+/* LayerNorm(x + resid[row / resid_div]) (rpe_transformer.py:161-163, vanilla_transformer.py:908-911 with the
+ * (N, C) -> (A, N, C) residual broadcast, output_layer.py:16-22). x fp32 [rows, channels], resid bf16 or NULL. */
+int se3et_add_layernorm(const float* x, const void* resid_bf16, int64_t resid_div, int64_t rows, int64_t channels,
+                        const float* gamma, const float* beta, float eps, float* out_f32, void* out_bf16,
+                        se3et_stream_t stream);
+/* F.normalize(x, p=2, dim=1) (experiments/se3eti.3dmatch/model.py:156-157). */
+int se3et_l2_normalize_rows(const float* x, int64_t rows, int64_t channels, float eps, float* out,
+                            se3et_stream_t stream);
+
+/* SuperPointMatching.forward (superpoint_matching.py:13-55) for num_pairs pairs at once.
+ * problems: int64 [num_pairs][5] {ref_start, n_ref, src_start, n_src, e_off}; masks uint8 (1 = keep) or NULL.
+ * e_workspace: fp32, sum of n_ref*n_src; row_sums / col_sums: fp32 per ref / src superpoint.
+ * Outputs per pair: num_correspondences (ref index, src index, score) sorted by (score desc, flat index asc),
+ * indices local to the pair, -1 padded; counts[p] = min(num_correspondences, #unmasked entries). */
+int se3et_superpoint_matching(const float* ref_feats, const float* src_feats, int64_t channels,
+                              const uint8_t* ref_masks, const uint8_t* src_masks, const int64_t* problems,
+                              int64_t num_pairs, int64_t max_ref, int64_t max_src, int64_t num_correspondences,
+                              int dual_normalization, float* e_workspace, float* row_sums, float* col_sums,
+                              int64_t* ref_idx, int64_t* src_idx, float* scores, int32_t* counts,
+                              se3et_stream_t stream);
 
 #ifdef __cplusplus
 }

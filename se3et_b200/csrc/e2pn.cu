@@ -145,7 +145,8 @@ constexpr int kStatRows = 128;
 __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const float* __restrict__ y, int64_t rows, int C,
                                                                int cpg, const int64_t* __restrict__ seg_off, int nseg,
                                                                int rows_per_point, double* __restrict__ stats) {
-  extern __shared__ float sh_part[];  // [G_block][2]
+  extern __shared__ double sh_part[];  // [G_block][2]; fp64 everywhere: the result does not depend on how rows
+                                        // are partitioned into CTAs (batched pairs == single pairs to the last bit)
   const int c = blockIdx.y * blockDim.x + threadIdx.x;
   const int g_first = (blockIdx.y * blockDim.x) / cpg;
   const int g_count = (min(C, (int)((blockIdx.y + 1) * blockDim.x)) - 1) / cpg - g_first + 1;
@@ -156,14 +157,14 @@ __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const float* __res
   int64_t r = r0;
   while (r < r1) {
     const int64_t seg_end = min(r1, seg_off[seg + 1] * rows_per_point);
-    float s = 0.f, ss = 0.f;
+    double s = 0.0, ss = 0.0;
     if (c < C)
       for (int64_t i = r; i < seg_end; ++i) {
-        const float v = y[i * C + c];
+        const double v = (double)y[i * C + c];
         s += v;
         ss += v * v;
       }
-    for (int i = threadIdx.x; i < 2 * g_count; i += blockDim.x) sh_part[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * g_count; i += blockDim.x) sh_part[i] = 0.0;
     __syncthreads();
     if (c < C) {
       atomicAdd(&sh_part[2 * (c / cpg - g_first)], s);
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const float* __res
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * g_count; i += blockDim.x)
-      atomicAdd(&stats[((int64_t)seg * G + g_first) * 2 + i], (double)sh_part[i]);
+      atomicAdd(&stats[((int64_t)seg * G + g_first) * 2 + i], sh_part[i]);
     __syncthreads();
     r = seg_end;
     ++seg;
@@ -369,7 +370,7 @@ extern "C" int se3et_groupnorm_stats(const float* y, int64_t rows, int64_t chann
   const int cpg = (int)(channels / groups);
   const int threads = channels >= 256 ? 256 : (int)((channels + 31) / 32 * 32);
   dim3 grid((unsigned)ceil_div(rows, kStatRows), (unsigned)ceil_div(channels, threads));
-  const size_t smem = sizeof(float) * 2 * (threads / (cpg < threads ? cpg : threads) + 2);
+  const size_t smem = sizeof(double) * 2 * (threads / (cpg < threads ? cpg : threads) + 2);
   groupnorm_stats_kernel<<<grid, threads, smem, st>>>(y, rows, (int)channels, cpg, seg_offsets, (int)nseg,
                                                   (int)rows_per_point, stats);
   SE3ET_LAUNCH_CHECK();

@@ -28,12 +28,15 @@ struct GemmEpilogue {
   int64_t c_batch_stride;    // elements between batches of C
   float alpha;
   int act;                   // 0 none, 1 ReLU
+  int transposed;            // 1: out_f32[c_off + col * ldc + row] (row-contiguous columns), fp32 only
+  int n_valid;               // transposed mode: only columns < n_valid are stored
 };
 
 struct GemmShape {
-  int M, N, K;               // per batch
+  int M, N, K;               // per batch (M = largest group when a group table is used)
   int64_t a_batch_rows;      // rows between batches in the flattened A map
   int64_t b_batch_rows;      // rows between batches in the flattened B map (0 = shared B)
+  const int64_t* groups;     // optional device table, 6 int64 per blockIdx.z: {a_row0, b_row0, m_rows, c_off, ldc, -}
 };
 
 template <int BN>
@@ -61,6 +64,18 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kGemmBM, n0 = blockIdx.y * BN, z = blockIdx.z;
   const int num_kb = (shape.K + kGemmBK - 1) / kGemmBK;
+  int64_t a_row0 = (int64_t)z * shape.a_batch_rows, b_row0 = (int64_t)z * shape.b_batch_rows;
+  int m_rows = shape.M;
+  int64_t c_base = (int64_t)z * ep.c_batch_stride;
+  int64_t ldc = ep.ldc;
+  if (shape.groups) {
+    a_row0 = shape.groups[6 * z + 0];
+    b_row0 = shape.groups[6 * z + 1];
+    m_rows = (int)shape.groups[6 * z + 2];
+    c_base = shape.groups[6 * z + 3];
+    ldc = shape.groups[6 * z + 4];
+    if (m0 >= m_rows) return;  // uniform for the whole CTA, before any barrier / TMEM allocation
+  }
 
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&tma_a);
@@ -80,8 +95,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      const int a_row = (int)(z * shape.a_batch_rows) + m0;
-      const int b_row = (int)(z * shape.b_batch_rows) + n0;
+      const int a_row = (int)a_row0 + m0;
+      const int b_row = (int)b_row0 + n0;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kGemmStages;
         const uint32_t phase = (kb / kGemmStages) & 1;
@@ -118,8 +133,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     const int row = m0 + lane_base + lane;
     tc::mbar_wait(tmem_full_bar, 0);
     tc::tcgen05_fence_after_sync();
-    const bool row_ok = row < shape.M;
-    const int64_t c_off = (int64_t)z * ep.c_batch_stride + (int64_t)row * ep.ldc + n0;
+    const bool row_ok = row < m_rows;
+    const int64_t c_off = c_base + (int64_t)row * ldc + n0;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
@@ -139,7 +154,11 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         if (ep.act == 1) x = fmaxf(x, 0.f);
         v[j] = x;
       }
-      if (row_ok) {
+      if (row_ok && ep.transposed) {
+#pragma unroll
+        for (int j = 0; j < kCols; ++j)
+          if (n0 + c0 + j < ep.n_valid) ep.out_f32[c_base + (int64_t)(n0 + c0 + j) * ldc + row] = v[j];
+      } else if (row_ok) {
         if (ep.out_f32) {
           float4* dst = reinterpret_cast<float4*>(ep.out_f32 + c_off + c0);
 #pragma unroll
@@ -225,23 +244,29 @@ int pick_bn(int n) {
 
 // a: [batch*a_batch_rows (or M), K] bf16 row-major with pitch lda; b: [.., K] bf16 with pitch ldb
 int gemm_bf16(const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b, int64_t ldb, int M, int N, int K, int batch,
-              int64_t a_batch_rows, int64_t b_batch_rows, const GemmEpilogue& ep, cudaStream_t st) {
+              int64_t a_batch_rows, int64_t b_batch_rows, const int64_t* groups, int64_t a_rows_total,
+              int64_t b_rows_total, const GemmEpilogue& ep, cudaStream_t st) {
   if (M <= 0 || batch <= 0) return SE3ET_OK;
   if (N <= 0 || K <= 0 || !a || !b) return SE3ET_ERR_ARG;
   const int bn = pick_bn(N);
   if (!bn) return SE3ET_ERR_UNSUPPORTED;
-  if (ep.out_f32 && ((reinterpret_cast<uintptr_t>(ep.out_f32) & 15) || (ep.ldc % 4) || (ep.c_batch_stride % 4)))
+  if (ep.transposed && (!ep.out_f32 || ep.out_bf16)) return SE3ET_ERR_ARG;
+  if (!ep.transposed && ep.out_f32 &&
+      ((reinterpret_cast<uintptr_t>(ep.out_f32) & 15) || (ep.ldc % 4) || (ep.c_batch_stride % 4) || groups))
     return SE3ET_ERR_ARG;
   if (ep.out_bf16 && ((reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) || (ep.ldc % 8) || (ep.c_batch_stride % 8)))
     return SE3ET_ERR_ARG;
   CUtensorMap ta, tb;
-  const int64_t a_rows = batch > 1 ? (int64_t)(batch - 1) * a_batch_rows + M : M;
-  const int64_t b_rows = (batch > 1 && b_batch_rows > 0) ? (int64_t)(batch - 1) * b_batch_rows + N : N;
+  int64_t a_rows = batch > 1 ? (int64_t)(batch - 1) * a_batch_rows + M : M;
+  int64_t b_rows = (batch > 1 && b_batch_rows > 0) ? (int64_t)(batch - 1) * b_batch_rows + N : N;
+  if (a_rows_total > 0) a_rows = a_rows_total;  // true extents: rows beyond them are zero-filled by TMA
+  if (b_rows_total > 0) b_rows = b_rows_total;
+  if (groups && (a_rows_total <= 0 || b_rows_total <= 0)) return SE3ET_ERR_ARG;
   int rc = make_tmap_bf16_2d(&ta, a, a_rows, K, lda, kGemmBM);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tb, b, b_rows, K, ldb, bn);
   if (rc) return rc;
-  GemmShape shape{M, N, K, a_batch_rows, b_batch_rows};
+  GemmShape shape{M, N, K, a_batch_rows, b_batch_rows, groups};
   switch (bn) {
     case 256: return launch_gemm<256>(ta, tb, shape, ep, batch, st);
     case 128: return launch_gemm<128>(ta, tb, shape, ep, batch, st);
@@ -254,6 +279,29 @@ int gemm_bf16(const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b, int64
 }  // namespace se3et
 
 using namespace se3et;
+
+extern "C" int se3et_gemm_grouped_bf16(const void* a, int64_t lda, int64_t a_rows_total, const void* b, int64_t ldb,
+                                       int64_t b_rows_total, const int64_t* groups, int64_t num_groups, int64_t max_m,
+                                       int64_t n, int64_t n_valid, int64_t k, float alpha, float* out_f32, int64_t ldc,
+                                       int transposed, se3et_stream_t stream) {
+  if (max_m < 0 || n <= 0 || k <= 0 || num_groups < 0 || !groups || !out_f32 || max_m > INT32_MAX) return SE3ET_ERR_ARG;
+  if (num_groups == 0 || max_m == 0) return SE3ET_OK;
+  if (num_groups > 65535) return SE3ET_ERR_UNSUPPORTED;
+  GemmEpilogue ep;
+  ep.out_f32 = out_f32;
+  ep.out_bf16 = nullptr;
+  ep.bias = nullptr;
+  ep.ldc = ldc;
+  ep.c_batch_stride = 0;
+  ep.alpha = alpha;
+  ep.act = 0;
+  ep.transposed = transposed ? 1 : 0;
+  ep.n_valid = (int)(n_valid > 0 ? n_valid : n);
+  if (!transposed) return SE3ET_ERR_UNSUPPORTED;
+  return gemm_bf16(static_cast<const __nv_bfloat16*>(a), lda, static_cast<const __nv_bfloat16*>(b), ldb, (int)max_m,
+                   (int)n, (int)k, (int)num_groups, 0, 0, groups, a_rows_total, b_rows_total, ep,
+                   static_cast<cudaStream_t>(stream));
+}
 
 extern "C" int se3et_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int64_t n, int64_t k,
                                int64_t batch, int64_t a_batch_rows, int64_t b_batch_rows, const float* bias,
@@ -269,6 +317,9 @@ extern "C" int se3et_gemm_bf16(const void* a, int64_t lda, const void* b, int64_
   ep.c_batch_stride = c_batch_stride;
   ep.alpha = alpha;
   ep.act = act;
+  ep.transposed = 0;
+  ep.n_valid = (int)n;
+  if (batch > 65535) return SE3ET_ERR_UNSUPPORTED;
   return gemm_bf16(static_cast<const __nv_bfloat16*>(a), lda, static_cast<const __nv_bfloat16*>(b), ldb, (int)m, (int)n,
-                   (int)k, (int)batch, a_batch_rows, b_batch_rows, ep, static_cast<cudaStream_t>(stream));
+                   (int)k, (int)batch, a_batch_rows, b_batch_rows, nullptr, 0, 0, ep, static_cast<cudaStream_t>(stream));
 }

@@ -1,0 +1,270 @@
+// SuperPointMatching (geotransformer/superpoint_matching.py:13-55) for a batch of pairs:
+//   E = exp(-clamp(2 - 2 <r, s>, 0))  on unit features, masked rows / columns removed,
+//   score = (E / rowsum) * (E / colsum)            (dual normalisation)
+//   global top-k over the flattened matrix with the canonical order (score desc, flat index asc).
+// Deterministic: row / column sums are fixed-order reductions (no atomics), selection is an exact radix select.
+#include "common.cuh"
+
+namespace se3et {
+
+struct MatchProblem {  // device table, one per pair
+  int64_t ref_start, n_ref, src_start, n_src, e_off;  // e_off: offset of this pair's n_ref x n_src matrix
+};
+
+// one CTA per (ref row, pair): E row + its sum
+__global__ void __launch_bounds__(256) spm_exp_rows_kernel(const float* __restrict__ ref, const float* __restrict__ src,
+                                                            int C, const uint8_t* __restrict__ ref_mask,
+                                                            const uint8_t* __restrict__ src_mask,
+                                                            const MatchProblem* __restrict__ problems,
+                                                            float* __restrict__ e, float* __restrict__ row_sum) {
+  extern __shared__ float sh_row[];  // ref feature row [C], then per-warp partial sums
+  const MatchProblem pr = problems[blockIdx.y];
+  const int n = blockIdx.x;
+  if (n >= pr.n_ref) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const float* r = ref + (pr.ref_start + n) * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sh_row[c] = r[c];
+  __syncthreads();
+  const bool row_on = !ref_mask || ref_mask[pr.ref_start + n];
+  float* erow = e + pr.e_off + (int64_t)n * pr.n_src;
+  float part = 0.f;  // this warp's columns, ascending order
+  for (int m = warp; m < pr.n_src; m += nwarps) {
+    const float* s = src + (pr.src_start + m) * C;
+    float dot = 0.f;
+    for (int c = lane; c < C; c += 32) dot = fmaf(sh_row[c], s[c], dot);
+    dot = warp_sum(dot);
+    const bool on = row_on && (!src_mask || src_mask[pr.src_start + m]);
+    const float v = on ? expf(-fmaxf(2.f - 2.f * dot, 0.f)) : 0.f;
+    if (lane == 0) erow[m] = v;
+    part += v;
+  }
+  float* sh_part = sh_row + C;
+  if (lane == 0) sh_part[warp] = part;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < nwarps; ++w) t += sh_part[w];
+    row_sum[pr.ref_start + n] = t;
+  }
+}
+
+// one thread per column (fixed-order sum over rows)
+__global__ void __launch_bounds__(128) spm_col_sums_kernel(const float* __restrict__ e,
+                                                            const MatchProblem* __restrict__ problems,
+                                                            float* __restrict__ col_sum) {
+  const MatchProblem pr = problems[blockIdx.y];
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= pr.n_src) return;
+  const float* col = e + pr.e_off + m;
+  float t = 0.f;
+  for (int n = 0; n < pr.n_ref; ++n) t += col[(int64_t)n * pr.n_src];
+  col_sum[pr.src_start + m] = t;
+}
+
+constexpr int kSelThreads = 1024;
+constexpr int kSelMaxK = 1024;
+
+__device__ __forceinline__ float spm_score(const float* __restrict__ e, const float* __restrict__ rs,
+                                           const float* __restrict__ cs, int64_t i, int n_src, bool dual) {
+  const float v = e[i];
+  if (!dual) return v;
+  const int n = (int)(i / n_src), m = (int)(i - (int64_t)n * n_src);
+  const float r = rs[n], c = cs[m];
+  if (!(r > 0.f) || !(c > 0.f)) return 0.f;  // masked row / column
+  return (v / r) * (v / c);
+}
+
+// block-wide exclusive prefix sum of a 0/1 flag, returns total through `total`
+__device__ __forceinline__ int block_prefix(int flag, int* sh_warp, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+  const int in_warp = __popc(ballot & ((1u << lane) - 1u));
+  if (lane == 0) sh_warp[warp] = __popc(ballot);
+  __syncthreads();
+  int off = 0, tot = 0;
+  for (int w = 0; w < kSelThreads / 32; ++w) {
+    const int c = sh_warp[w];
+    if (w < warp) off += c;
+    tot += c;
+  }
+  __syncthreads();
+  total = tot;
+  return off + in_warp;
+}
+
+// one CTA per pair: exact k-th largest by 3-pass radix select on the float bits, ordered collection, bitonic sort
+__global__ void __launch_bounds__(kSelThreads) spm_topk_kernel(const float* __restrict__ e,
+                                                                const float* __restrict__ row_sum,
+                                                                const float* __restrict__ col_sum,
+                                                                const uint8_t* __restrict__ ref_mask,
+                                                                const uint8_t* __restrict__ src_mask,
+                                                                const MatchProblem* __restrict__ problems, int k_req,
+                                                                int dual, int64_t* __restrict__ ref_idx,
+                                                                int64_t* __restrict__ src_idx,
+                                                                float* __restrict__ scores, int32_t* __restrict__ counts) {
+  __shared__ unsigned int hist[2048];
+  __shared__ int sh_warp[kSelThreads / 32];
+  __shared__ unsigned long long cand[kSelMaxK];
+  __shared__ unsigned int sh_prefix, sh_remaining;
+  __shared__ int sh_valid;
+  const MatchProblem pr = problems[blockIdx.x];
+  const int n_src = (int)pr.n_src;
+  const int64_t total = pr.n_ref * pr.n_src;
+  const float* ep = e + pr.e_off;
+  const float* rs = row_sum + pr.ref_start;
+  const float* cs = col_sum + pr.src_start;
+  int64_t* out_r = ref_idx + (int64_t)blockIdx.x * k_req;
+  int64_t* out_s = src_idx + (int64_t)blockIdx.x * k_req;
+  float* out_v = scores + (int64_t)blockIdx.x * k_req;
+
+  // number of unmasked entries = (#valid rows) * (#valid cols)
+  if (threadIdx.x == 0) sh_valid = 0;
+  __syncthreads();
+  {
+    int vr = 0, vc = 0;
+    for (int i = threadIdx.x; i < pr.n_ref; i += kSelThreads) vr += (!ref_mask || ref_mask[pr.ref_start + i]) ? 1 : 0;
+    for (int i = threadIdx.x; i < pr.n_src; i += kSelThreads) vc += (!src_mask || src_mask[pr.src_start + i]) ? 1 : 0;
+    // pack both counts into one atomic word (each < 65536 is not guaranteed: use two passes)
+    atomicAdd(&sh_valid, vr);
+    __syncthreads();
+    const int rows_valid = sh_valid;
+    __syncthreads();
+    if (threadIdx.x == 0) sh_valid = 0;
+    __syncthreads();
+    atomicAdd(&sh_valid, vc);
+    __syncthreads();
+    const long long nvalid = (long long)rows_valid * sh_valid;
+    __syncthreads();
+    if (threadIdx.x == 0) sh_valid = (int)(nvalid < k_req ? nvalid : k_req);
+    __syncthreads();
+  }
+  const int k = sh_valid;  // min(num_correspondences, numel) (superpoint_matching.py:43)
+  if (threadIdx.x == 0) counts[blockIdx.x] = k;
+  if (k == 0) return;
+
+  // ---- radix select: bits of a non-negative float order like unsigned integers
+  unsigned int prefix = 0, prefix_mask = 0;
+  unsigned int remaining = (unsigned)k;  // rank (1-based, from the top) inside the current bucket
+  const int shifts[3] = {21, 10, 0};
+  const int widths[3] = {11, 11, 10};
+  for (int pass = 0; pass < 3; ++pass) {
+    const int shift = shifts[pass], nb = 1 << widths[pass];
+    for (int i = threadIdx.x; i < nb; i += kSelThreads) hist[i] = 0;
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < total; i += kSelThreads) {
+      const int n = (int)(i / n_src), m = (int)(i - (int64_t)n * n_src);
+      if ((ref_mask && !ref_mask[pr.ref_start + n]) || (src_mask && !src_mask[pr.src_start + m])) continue;
+      const unsigned int bits = __float_as_uint(spm_score(ep, rs, cs, i, n_src, dual));
+      if ((bits & prefix_mask) == prefix) atomicAdd(&hist[(bits >> shift) & (nb - 1)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int acc = 0;
+      int b = nb - 1;
+      for (; b > 0; --b) {
+        if (acc + hist[b] >= remaining) break;
+        acc += hist[b];
+      }
+      sh_prefix = prefix | ((unsigned)b << shift);
+      sh_remaining = remaining - acc;
+    }
+    __syncthreads();
+    prefix = sh_prefix;
+    remaining = sh_remaining;
+    prefix_mask |= (unsigned)(nb - 1) << shift;
+    __syncthreads();
+  }
+  const unsigned int thr_bits = prefix;  // bits of the k-th largest score; `remaining` of the ties are taken
+
+  // ---- ordered collection (ascending flat index): everything above the threshold, then the first ties
+  int n_above = 0, n_tie = 0;
+  for (int64_t base = 0; base < total; base += kSelThreads) {
+    const int64_t i = base + threadIdx.x;
+    unsigned int bits = 0;
+    bool valid = false;
+    if (i < total) {
+      const int n = (int)(i / n_src), m = (int)(i - (int64_t)n * n_src);
+      valid = !((ref_mask && !ref_mask[pr.ref_start + n]) || (src_mask && !src_mask[pr.src_start + m]));
+      if (valid) bits = __float_as_uint(spm_score(ep, rs, cs, i, n_src, dual));
+    }
+    int tot;
+    const int above = valid && bits > thr_bits;
+    int pos = block_prefix(above, sh_warp, tot);
+    if (above) cand[n_above + pos] = ((unsigned long long)(~bits) << 32) | (unsigned int)i;
+    n_above += tot;
+    const int tie = valid && bits == thr_bits;
+    pos = block_prefix(tie, sh_warp, tot);
+    // ties go after all "above" entries: slots [k - remaining, k)
+    if (tie && n_tie + pos < (int)remaining)
+      cand[k - (int)remaining + n_tie + pos] = ((unsigned long long)(~bits) << 32) | (unsigned int)i;
+    n_tie += tot;
+  }
+  __syncthreads();
+  // ---- sort the k candidates by (score desc, flat index asc): key = (~bits, index) ascending
+  int n2 = 1;
+  while (n2 < k) n2 <<= 1;
+  for (int i = k + threadIdx.x; i < n2; i += kSelThreads) cand[i] = ~0ull;
+  __syncthreads();
+  for (int kk = 2; kk <= n2; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n2; i += kSelThreads) {
+        const int p = i ^ j;
+        if (p > i) {
+          const unsigned long long x = cand[i], y = cand[p];
+          const bool up = (i & kk) == 0;
+          if ((x > y) == up) { cand[i] = y; cand[p] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < k_req; i += kSelThreads) {
+    if (i < k) {
+      const unsigned long long c = cand[i];
+      const unsigned int flat = (unsigned int)(c & 0xffffffffull);
+      out_r[i] = flat / n_src;
+      out_s[i] = flat % n_src;
+      out_v[i] = __uint_as_float(~(unsigned int)(c >> 32));
+    } else {
+      out_r[i] = -1;
+      out_s[i] = -1;
+      out_v[i] = 0.f;
+    }
+  }
+}
+
+}  // namespace se3et
+
+using namespace se3et;
+
+extern "C" int se3et_superpoint_matching(const float* ref_feats, const float* src_feats, int64_t channels,
+                                         const uint8_t* ref_masks, const uint8_t* src_masks, const int64_t* problems,
+                                         int64_t num_pairs, int64_t max_ref, int64_t max_src,
+                                         int64_t num_correspondences, int dual_normalization, float* e_workspace,
+                                         float* row_sums, float* col_sums, int64_t* ref_idx, int64_t* src_idx,
+                                         float* scores, int32_t* counts, se3et_stream_t stream) {
+  if (num_pairs < 0 || channels <= 0 || max_ref < 0 || max_src < 0 || num_correspondences <= 0 ||
+      num_correspondences > kSelMaxK || num_pairs > 65535)
+    return SE3ET_ERR_ARG;
+  if (num_pairs == 0) return SE3ET_OK;
+  if (!ref_feats || !src_feats || !problems || !e_workspace || !row_sums || !col_sums || !ref_idx || !src_idx ||
+      !scores || !counts)
+    return SE3ET_ERR_ARG;
+  if (max_ref * max_src >= ((int64_t)1 << 32)) return SE3ET_ERR_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const auto* pr = reinterpret_cast<const MatchProblem*>(problems);
+  if (max_ref > 0 && max_src > 0) {
+    dim3 g1((unsigned)max_ref, (unsigned)num_pairs);
+    spm_exp_rows_kernel<<<g1, 256, sizeof(float) * (channels + 8), st>>>(ref_feats, src_feats, (int)channels, ref_masks,
+                                                                         src_masks, pr, e_workspace, row_sums);
+    SE3ET_LAUNCH_CHECK();
+    dim3 g2((unsigned)ceil_div(max_src, 128), (unsigned)num_pairs);
+    spm_col_sums_kernel<<<g2, 128, 0, st>>>(e_workspace, pr, col_sums);
+    SE3ET_LAUNCH_CHECK();
+  }
+  spm_topk_kernel<<<(unsigned)num_pairs, kSelThreads, 0, st>>>(e_workspace, row_sums, col_sums, ref_masks, src_masks, pr,
+                                                              (int)num_correspondences, dual_normalization, ref_idx,
+                                                              src_idx, scores, counts);
+  SE3ET_LAUNCH_CHECK();
+  return SE3ET_OK;
+}

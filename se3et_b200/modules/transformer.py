@@ -1,0 +1,447 @@
+"""Superpoint transformer + coarse matching on the CUDA path -- mirrors of the reference modules
+(same class names, constructor arguments and state_dict keys):
+
+  geotransformer/modules/geotransformer/geotransformer.py   GeometricStructureEmbedding, GeometricTransformer
+  geotransformer/modules/transformer/rpe_transformer.py      RPEMultiHeadAttention, RPEAttentionLayer, RPETransformerLayer
+  geotransformer/modules/transformer/vanilla_transformer.py  MultiHeadAttention, AttentionLayer, TransformerLayer
+  geotransformer/modules/transformer/output_layer.py         AttentionOutput
+  geotransformer/modules/transformer/conditional_transformer.py  RPEConditionalTransformer
+  geotransformer/modules/transformer/positional_embedding.py SinusoidalPositionalEmbedding
+  geotransformer/modules/geotransformer/superpoint_matching.py  SuperPointMatching
+
+Block lists made of 'self_eq' and 'cross' (SE3ET-I / I2) run fully on the CUDA path.
+
+Execution model: all clouds of all pairs are stored flat, ordered [ref_0..ref_{P-1}, src_0..src_{P-1}], equivariant
+states as bf16 (T*A, C) rows in (point, anchor) order.  The (N, N, C) geometric embedding is built once per forward
+(bf16) and `q . proj_p(embedding)` is evaluated as `embedding[n] @ (W_p^T q[n])`, so proj_p(embedding) and the
+(N, N, 3, C) tensor of the reference are never materialised.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..ops import e2pn_ops as K
+from ..ops import transformer_ops as T
+from ..ops.gemm import linear_bf16
+from .e2pn import _Bf16Cache, _act
+
+
+class CloudContext:
+    """Flat layout bookkeeping for a batch of pairs. sizes = [n_ref_0.., n_src_0..] (python ints)."""
+
+    def __init__(self, ref_sizes, src_sizes, anchors, heads, device):
+        self.sizes = [int(v) for v in ref_sizes] + [int(v) for v in src_sizes]
+        self.A, self.H = anchors, heads
+        nref = len(ref_sizes)
+        paired = len(src_sizes) == nref
+        self.P = nref if paired else 0
+        sz = np.asarray(self.sizes, dtype=np.int64)
+        cu = np.concatenate([[0], np.cumsum(sz)])
+        eoff = np.concatenate([[0], np.cumsum(sz * sz)])
+        self.T, self.R = int(cu[-1]), int(eoff[-1])
+        self.Tr = int(cu[nref])
+        self.max_n = int(sz.max()) if len(sz) else 0
+        ah = anchors * heads
+        b = len(sz)
+        P = self.P
+        self_pr = np.stack([cu[:-1], sz, cu[:-1], sz, eoff[:-1] * ah], 1)
+        # cross attention: q rows / kv rows are relative to the side's slice of the flat arrays
+        ref_pr = np.stack([cu[:P], sz[:P], cu[P:2 * P] - cu[P], sz[P:2 * P], np.zeros(P, np.int64)], 1)
+        src_pr = np.stack([cu[P:2 * P] - cu[P], sz[P:2 * P], cu[:P], sz[:P], np.zeros(P, np.int64)], 1)
+        host = np.concatenate([cu, eoff[:-1], self_pr.reshape(-1), ref_pr.reshape(-1), src_pr.reshape(-1)]).astype(np.int64)
+        dev = torch.from_numpy(host).to(device, non_blocking=True)
+        o = 0
+        self.cu = dev[o:o + b + 1]; o += b + 1
+        self.eoff = dev[o:o + b]; o += b
+        self.self_problems = dev[o:o + 5 * b].view(b, 5); o += 5 * b
+        self.ref_problems = dev[o:o + 5 * P].view(P, 5); o += 5 * P
+        self.src_problems = dev[o:o + 5 * P].view(P, 5)
+        self.max_ref = int(sz[:P].max()) if P else 0
+        self.max_src = int(sz[P:2 * P].max()) if P else 0
+        # grouped-GEMM table of the positional score term: one group per (cloud, query point)
+        sizes_t = torch.from_numpy(sz).to(device, non_blocking=True)
+        cloud = torch.repeat_interleave(torch.arange(b, device=device), sizes_t, output_size=self.T)
+        nloc = torch.arange(self.T, device=device) - self.cu[cloud]
+        nb = sizes_t[cloud]
+        a_row0 = self.eoff[cloud] + nloc * nb
+        self.rpe_groups = torch.stack([a_row0, torch.arange(self.T, device=device) * ah, nb, a_row0 * ah, nb,
+                                       torch.zeros_like(nb)], 1).contiguous()
+
+
+class SinusoidalPositionalEmbedding(nn.Module):
+    """positional_embedding.py:8-34 (kept for the div_term buffer; the kernel regenerates the same table)."""
+
+    def __init__(self, d_model):
+        super().__init__()
+        if d_model % 2 != 0:
+            raise ValueError(f'Sinusoidal positional encoding with odd d_model: {d_model}')
+        self.d_model = d_model
+        div_indices = torch.arange(0, d_model, 2).float()
+        self.register_buffer('div_term', torch.exp(div_indices * (-np.log(10000.0) / d_model)))
+
+
+class GeometricStructureEmbedding(nn.Module):
+    """geotransformer.py:19-121 with n_level_equiv = 0 (SE3ET-I / I2)."""
+
+    def __init__(self, hidden_dim, sigma_d, sigma_a, angle_k, reduction_a='max', kanchor=1, n_level_equiv=0):
+        super().__init__()
+        if reduction_a != 'max' or n_level_equiv != 0:
+            raise NotImplementedError("CUDA path: reduction_a='max', n_level_equiv=0")
+        self.sigma_d, self.sigma_a, self.angle_k = sigma_d, sigma_a, angle_k
+        self.factor_a = 180.0 / (self.sigma_a * np.pi)
+        self.embedding = SinusoidalPositionalEmbedding(hidden_dim)
+        self.proj_d = nn.Linear(hidden_dim, hidden_dim)
+        self.proj_a = nn.Linear(hidden_dim, hidden_dim)
+        self.n_level_equiv, self.kanchor, self.reduction_a = n_level_equiv, kanchor, reduction_a
+        self._wd, self._wa = _Bf16Cache(), _Bf16Cache()
+
+    def embed(self, points_flat, ctx):
+        """-> bf16 (sum n_b^2, C): row eoff[b] + n*n_b + m is the embedding of the pair (n, m) of cloud b."""
+        idx4 = T.geo_embed_indices(points_flat, ctx.cu, ctx.max_n, ctx.eoff, ctx.R, self.sigma_d, self.sigma_a,
+                                   self.angle_k)
+        bias_sum = (self.proj_d.bias + self.proj_a.bias).detach().float().contiguous()
+        return T.geo_embed_project(idx4, self._wd.get(self.proj_d.weight), self._wa.get(self.proj_a.weight), bias_sum)
+
+    def forward(self, points):
+        """points (B=1, N, 3) -> (1, N, N, C) as the reference (fp32)."""
+        assert points.shape[0] == 1
+        n = points.shape[1]
+        ctx = CloudContext([n], [], 1, 1, points.device)
+        e = self.embed(points[0].contiguous().float(), ctx)
+        return e.view(1, n, n, -1).float()
+
+
+class AttentionOutput(nn.Module):
+    """output_layer.py:7-22: LayerNorm(x + squeeze(ReLU(expand(x))))."""
+
+    def __init__(self, d_model, dropout=None, activation_fn='ReLU'):
+        super().__init__()
+        if activation_fn != 'ReLU' or dropout:
+            raise NotImplementedError("CUDA path: ReLU, no dropout (inference)")
+        self.expand = nn.Linear(d_model, d_model * 2)
+        self.squeeze = nn.Linear(d_model * 2, d_model)
+        self.norm = nn.LayerNorm(d_model)
+        self._we, self._ws = _Bf16Cache(), _Bf16Cache()
+
+    def fused(self, x, out=None):
+        """x bf16 (rows, C) -> bf16 (rows, C)."""
+        _, h = linear_bf16(x, self._we.get(self.expand.weight), self.expand.bias, relu=True, out_f32=False, out_bf16=True)
+        z, _ = linear_bf16(h, self._ws.get(self.squeeze.weight), self.squeeze.bias)
+        _, y = T.add_layernorm(z, x, 1, self.norm.weight, self.norm.bias, self.norm.eps)
+        return y
+
+    def forward(self, input_states):
+        shape = input_states.shape
+        y = self.fused(_act(input_states).reshape(-1, shape[-1]).contiguous())
+        return y.view(shape).to(input_states.dtype)
+
+
+class RPEMultiHeadAttention(nn.Module):
+    """rpe_transformer.py:18-131 (equivariant branch)."""
+
+    def __init__(self, d_model, num_heads, dropout=None, equivariant=False, d_equiv_embed=0):
+        super().__init__()
+        if d_model % num_heads != 0:
+            raise ValueError('`d_model` ({}) must be a multiple of `num_heads` ({}).'.format(d_model, num_heads))
+        if dropout or d_equiv_embed:
+            raise NotImplementedError("CUDA path: no dropout, d_equiv_embed = 0")
+        self.d_model, self.num_heads = d_model, num_heads
+        self.d_model_per_head = d_model // num_heads
+        self.equivariant, self.d_equiv_embed = equivariant, d_equiv_embed
+        self.proj_q = nn.Linear(d_model, d_model)
+        self.proj_k = nn.Linear(d_model, d_model)
+        self.proj_v = nn.Linear(d_model, d_model)
+        self.proj_p = nn.Linear(d_model, d_model)
+        self._wqkv, self._wpt = _Bf16Cache(), _Bf16Cache()
+
+    def fused(self, x, emb, ctx):
+        """x bf16 (T*A, C) equivariant states, emb bf16 (R, C) -> attention output bf16 (T*A, C)."""
+        c, h, a = self.d_model, self.num_heads, ctx.A
+        hc = self.d_model_per_head
+        w = self._wqkv.get(self.proj_q.weight, lambda q: torch.cat([q, self.proj_k.weight.detach(),
+                                                                    self.proj_v.weight.detach()], 0))
+        b = torch.cat([self.proj_q.bias, self.proj_k.bias, self.proj_v.bias]).detach()
+        _, qkv = linear_bf16(x, w, b, out_f32=False, out_bf16=True)  # (T*A, 3C)
+        # qp[(n,a), h, :] = W_p[h]^T q[(n,a), h]  (the proj_p bias only shifts every key equally: softmax-invariant)
+        wpt = self._wpt.get(self.proj_p.weight, lambda p: p.t())
+        rows = x.shape[0]
+        qp = torch.empty((rows, h * c), dtype=torch.bfloat16, device=x.device)
+        for i in range(h):
+            linear_bf16(qkv[:, i * hc:(i + 1) * hc], wpt[:, i * hc:(i + 1) * hc], out_f32=False,
+                        out_bf16=qp[:, i * c:(i + 1) * c])
+        ah = a * h
+        s_p = torch.empty((ctx.R * ah,), dtype=torch.float32, device=x.device)
+        T.gemm_grouped_t(emb, ctx.R, qp.view(rows * h, c), rows * h, ctx.rpe_groups, ctx.max_n, (ah + 15) // 16 * 16, ah,
+                         c, s_p)
+        hidden = torch.empty((rows, c), dtype=torch.bfloat16, device=x.device)
+        T.flash_attention(qkv, a * 3 * c, 3 * c, qkv[:, c:], a * 3 * c, 3 * c, qkv[:, 2 * c:], a * 3 * c, 3 * c, s_p,
+                          ctx.self_problems, ctx.max_n, a, h, hc, hidden)
+        return hidden
+
+    def forward(self, input_q, input_k, input_v, embed_qk, key_weights=None, key_masks=None, attention_factors=None,
+                embed_eq=None):
+        """Self-attention form only (input_q is input_k is input_v): (1, A, N, C), embed (1, N, N, C)."""
+        if key_weights is not None or key_masks is not None or attention_factors is not None or embed_eq is not None:
+            raise NotImplementedError("CUDA path: plain equivariant self-attention")
+        assert input_q.shape[0] == 1 and input_q.dim() == 4
+        _, a, n, c = input_q.shape
+        ctx = CloudContext([n], [], a, self.num_heads, input_q.device)
+        x = _act(input_q[0]).transpose(0, 1).reshape(n * a, c).contiguous()
+        hid = self.fused(x, _act(embed_qk).reshape(n * n, c).contiguous(), ctx)
+        return hid.view(n, a, c).transpose(0, 1).unsqueeze(0).to(input_q.dtype), None
+
+
+class RPEAttentionLayer(nn.Module):
+    def __init__(self, d_model, num_heads, dropout=None, equivariant=False, d_equiv_embed=0):
+        super().__init__()
+        self.attention = RPEMultiHeadAttention(d_model, num_heads, dropout=dropout, equivariant=equivariant,
+                                               d_equiv_embed=d_equiv_embed)
+        self.linear = nn.Linear(d_model, d_model)
+        self.norm = nn.LayerNorm(d_model)
+        self._wl = _Bf16Cache()
+
+    def fused(self, x, emb, ctx):
+        hid = self.attention.fused(x, emb, ctx)
+        y, _ = linear_bf16(hid, self._wl.get(self.linear.weight), self.linear.bias)
+        _, out = T.add_layernorm(y, x, 1, self.norm.weight, self.norm.bias, self.norm.eps)
+        return out
+
+
+class RPETransformerLayer(nn.Module):
+    """rpe_transformer.py:168-194."""
+
+    def __init__(self, d_model, num_heads, dropout=None, activation_fn='ReLU', equivariant=False, d_equiv_embed=0):
+        super().__init__()
+        if not equivariant:
+            raise NotImplementedError("CUDA path: 'self_eq' blocks (equivariant RPE self-attention)")
+        self.attention = RPEAttentionLayer(d_model, num_heads, dropout=dropout, equivariant=equivariant,
+                                           d_equiv_embed=d_equiv_embed)
+        self.output = AttentionOutput(d_model, dropout=dropout, activation_fn=activation_fn)
+
+    def fused(self, x, emb, ctx):
+        return self.output.fused(self.attention.fused(x, emb, ctx))
+
+    def forward(self, input_states, memory_states, position_states, memory_weights=None, memory_masks=None,
+                attention_factors=None, equiv_states=None):
+        if memory_states is not input_states or memory_masks is not None:
+            raise NotImplementedError("CUDA path: self-attention without masks")
+        _, a, n, c = input_states.shape
+        ctx = CloudContext([n], [], a, self.attention.attention.num_heads, input_states.device)
+        x = _act(input_states[0]).transpose(0, 1).reshape(n * a, c).contiguous()
+        out = self.fused(x, _act(position_states).reshape(n * n, c).contiguous(), ctx)
+        return out.view(n, a, c).transpose(0, 1).unsqueeze(0).to(input_states.dtype), None
+
+
+class MultiHeadAttention(nn.Module):
+    """vanilla_transformer.py:23-85, invariant q/k with an equivariant (4-D) value."""
+
+    def __init__(self, d_model, num_heads, dropout=None):
+        super().__init__()
+        if d_model % num_heads != 0:
+            raise ValueError('`d_model` ({}) must be a multiple of `num_heads` ({}).'.format(d_model, num_heads))
+        if dropout:
+            raise NotImplementedError("CUDA path: no dropout (inference)")
+        self.d_model, self.num_heads = d_model, num_heads
+        self.d_model_per_head = d_model // num_heads
+        self.proj_q = nn.Linear(d_model, d_model)
+        self.proj_k = nn.Linear(d_model, d_model)
+        self.proj_v = nn.Linear(d_model, d_model)
+        self._wq, self._wk, self._wv = _Bf16Cache(), _Bf16Cache(), _Bf16Cache()
+
+    def fused(self, q_inv, k_inv, v_eq, problems, max_q, anchors):
+        """q_inv bf16 (Nq, C), k_inv bf16 (Nk, C), v_eq bf16 (Nk*A, C) -> bf16 (Nq*A, C)."""
+        c, h, hc = self.d_model, self.num_heads, self.d_model_per_head
+        _, q = linear_bf16(q_inv, self._wq.get(self.proj_q.weight), self.proj_q.bias, out_f32=False, out_bf16=True)
+        _, k = linear_bf16(k_inv, self._wk.get(self.proj_k.weight), self.proj_k.bias, out_f32=False, out_bf16=True)
+        _, v = linear_bf16(v_eq, self._wv.get(self.proj_v.weight), self.proj_v.bias, out_f32=False, out_bf16=True)
+        hidden = torch.empty((q_inv.shape[0] * anchors, c), dtype=torch.bfloat16, device=q_inv.device)
+        T.flash_attention(q, c, 0, k, c, 0, v, anchors * c, c, None, problems, max_q, anchors, h, hc, hidden)
+        return hidden
+
+
+class AttentionLayer(nn.Module):
+    def __init__(self, d_model, num_heads, dropout=None, equivariant=False, attn_mode=None, alternative_impl=False,
+                 kanchor=4, attn_r_positive='sq', attn_r_positive_rot_supervise='sigmoid'):
+        super().__init__()
+        if equivariant:
+            raise NotImplementedError("CUDA path: 'cross' blocks (MultiHeadAttentionEQ modes are not built yet)")
+        self.equivariant = equivariant
+        self.attention = MultiHeadAttention(d_model, num_heads, dropout=dropout)
+        self.linear = nn.Linear(d_model, d_model)
+        self.norm = nn.LayerNorm(d_model)
+        self._wl = _Bf16Cache()
+
+    def fused(self, q_inv, k_inv, v_eq, problems, max_q, anchors):
+        hid = self.attention.fused(q_inv, k_inv, v_eq, problems, max_q, anchors)
+        y, _ = linear_bf16(hid, self._wl.get(self.linear.weight), self.linear.bias)
+        # (N, C) residual broadcast onto (A, N, C) (vanilla_transformer.py:911)
+        _, out = T.add_layernorm(y, q_inv, anchors, self.norm.weight, self.norm.bias, self.norm.eps)
+        return out
+
+
+class TransformerLayer(nn.Module):
+    """vanilla_transformer.py:917-946."""
+
+    def __init__(self, d_model, num_heads, dropout=None, activation_fn='ReLU', equivariant=False, attn_mode=None,
+                 alternative_impl=False, kanchor=4, attn_r_positive='sq', attn_r_positive_rot_supervise='sigmoid'):
+        super().__init__()
+        self.equivariant = equivariant
+        self.attention = AttentionLayer(d_model, num_heads, dropout=dropout, equivariant=equivariant,
+                                        attn_mode=attn_mode, alternative_impl=alternative_impl, kanchor=kanchor,
+                                        attn_r_positive=attn_r_positive,
+                                        attn_r_positive_rot_supervise=attn_r_positive_rot_supervise)
+        self.output = AttentionOutput(d_model, dropout=dropout, activation_fn=activation_fn)
+
+    def fused(self, q_inv, k_inv, v_eq, problems, max_q, anchors):
+        return self.output.fused(self.attention.fused(q_inv, k_inv, v_eq, problems, max_q, anchors))
+
+    def forward(self, input_states, memory_states, value_states=None, memory_weights=None, memory_masks=None,
+                attention_factors=None, attention_masks=None, gt_indices=None, gt_overlap=None):
+        """input (1, N, C), memory (1, M, C), value (1, A, M, C) -> (1, A, N, C)."""
+        if value_states is None or value_states.dim() != 4 or memory_masks is not None:
+            raise NotImplementedError("CUDA path: invariant q/k with an equivariant value, no masks")
+        n, m = input_states.shape[1], memory_states.shape[1]
+        a, c = value_states.shape[1], value_states.shape[-1]
+        dev = input_states.device
+        problems = torch.tensor([[0, n, 0, m, 0]], dtype=torch.int64, device=dev)
+        v = _act(value_states[0]).transpose(0, 1).reshape(m * a, c).contiguous()
+        out = self.fused(_act(input_states[0]).contiguous(), _act(memory_states[0]).contiguous(), v, problems, n, a)
+        return out.view(n, a, c).transpose(0, 1).unsqueeze(0).to(input_states.dtype), None
+
+
+def _check_block_type(block):
+    if 'self' not in block and 'cross' not in block:
+        raise ValueError('Unsupported block type "{}".'.format(block))
+
+
+class RPEConditionalTransformer(nn.Module):
+    """conditional_transformer.py:98-390 for block lists of 'self_eq' and 'cross'."""
+
+    def __init__(self, blocks, d_model, num_heads, dropout=None, activation_fn='ReLU', return_attention_scores=False,
+                 return_attention_weights=False, anchor_matching=False, parallel=False, na=4, attn_r_positive='sq',
+                 attn_r_positive_rot_supervise='sigmoid', align_mode='0', alternative_impl=False, d_equiv_embed=0):
+        super().__init__()
+        if return_attention_scores or return_attention_weights or anchor_matching or parallel:
+            raise NotImplementedError("CUDA path: inference configuration of SE3ET-I / I2")
+        self.blocks, self.na = blocks, na
+        layers = []
+        for i, block in enumerate(blocks):
+            _check_block_type(block)
+            if block == 'self_eq':
+                if i + 1 >= len(blocks) or blocks[i + 1] != 'cross':
+                    raise NotImplementedError("CUDA path: every 'self_eq' block is followed by a 'cross' block")
+                layers.append(RPETransformerLayer(d_model, num_heads, dropout=dropout, activation_fn=activation_fn,
+                                                  equivariant=True, d_equiv_embed=d_equiv_embed))
+            elif block == 'cross':
+                layers.append(TransformerLayer(d_model, num_heads, dropout=dropout, activation_fn=activation_fn,
+                                               equivariant=False, kanchor=na))
+            else:
+                raise NotImplementedError("CUDA path: block '%s' is not built yet ('self_eq' and 'cross' are)" % block)
+        self.layers = nn.ModuleList(layers)
+
+    def run(self, x_eq, emb, ctx):
+        """x_eq bf16 (T*A, C), clouds ordered [refs | srcs] -> invariant bf16 (T, C)."""
+        a = ctx.A
+        c = x_eq.shape[1]
+        tr = ctx.Tr
+        x_inv = None
+        for layer, block in zip(self.layers, self.blocks):
+            if block == 'self_eq':
+                x_eq = layer.fused(x_eq, emb, ctx)
+                x_inv = K.anchor_max(x_eq.view(-1, a, c))
+            else:
+                if x_inv is None:
+                    x_inv = K.anchor_max(x_eq.view(-1, a, c))
+                new_eq = torch.empty_like(x_eq)
+                new_inv = torch.empty_like(x_inv)
+                # the reference side is updated first; the source side then attends to the UPDATED reference
+                # (conditional_transformer.py:297-302)
+                r = layer.fused(x_inv[:tr], x_inv[tr:], x_eq[tr * a:], ctx.ref_problems, ctx.max_ref, a)
+                new_eq[:tr * a] = r
+                K.anchor_max(r.view(-1, a, c), out=new_inv[:tr])
+                s = layer.fused(x_inv[tr:], new_inv[:tr], new_eq[:tr * a], ctx.src_problems, ctx.max_src, a)
+                new_eq[tr * a:] = s
+                K.anchor_max(s.view(-1, a, c), out=new_inv[tr:])
+                x_eq, x_inv = new_eq, new_inv
+        return x_inv
+
+
+class GeometricTransformer(nn.Module):
+    """geotransformer.py:124-317.  forward() keeps the reference signature (one pair); forward_clouds() runs a
+    batch of pairs in one launch sequence."""
+
+    def __init__(self, input_dim, output_dim, hidden_dim, num_heads, blocks, sigma_d, sigma_a, angle_k, dropout=None,
+                 activation_fn='ReLU', supervise_rotation=False, anchor_matching=False, reduction_a='max', na=None,
+                 attn_r_positive='sq', attn_r_positive_rot_supervise='sigmoid', align_mode='0', alternative_impl=False,
+                 n_level_equiv=0):
+        super().__init__()
+        if na is None or supervise_rotation or anchor_matching:
+            raise NotImplementedError("CUDA path: equivariant features (na = kanchor), no rotation supervision")
+        self.n_level_equiv, self.na = n_level_equiv, na
+        self.hidden_dim, self.num_heads = hidden_dim, num_heads
+        self.embedding = GeometricStructureEmbedding(hidden_dim, sigma_d, sigma_a, angle_k, reduction_a=reduction_a,
+                                                     kanchor=na, n_level_equiv=n_level_equiv)
+        self.in_proj = nn.Linear(input_dim, hidden_dim)
+        self.transformer = RPEConditionalTransformer(blocks, hidden_dim, num_heads, dropout=dropout,
+                                                     activation_fn=activation_fn, na=na,
+                                                     attn_r_positive=attn_r_positive,
+                                                     attn_r_positive_rot_supervise=attn_r_positive_rot_supervise,
+                                                     align_mode=align_mode, alternative_impl=alternative_impl)
+        self.out_proj = nn.Linear(hidden_dim, output_dim)
+        self._wi, self._wo = _Bf16Cache(), _Bf16Cache()
+
+    def forward_clouds(self, points, feats, ref_sizes, src_sizes):
+        """points fp32 (T, 3), feats (T, A, Cin), clouds ordered [ref_0.., src_0..] with the given sizes.
+        -> fp32 (T, output_dim) in the same order."""
+        _lib.require_cuda(points, feats)
+        ctx = CloudContext(ref_sizes, src_sizes, self.na, self.num_heads, points.device)
+        assert ctx.T == points.shape[0] == feats.shape[0]
+        emb = self.embedding.embed(points.contiguous().float(), ctx)
+        x = _act(feats).reshape(ctx.T * self.na, -1).contiguous()
+        _, x = linear_bf16(x, self._wi.get(self.in_proj.weight), self.in_proj.bias, out_f32=False, out_bf16=True)
+        x_inv = self.transformer.run(x, emb, ctx)
+        out, _ = linear_bf16(x_inv, self._wo.get(self.out_proj.weight), self.out_proj.bias)
+        return out
+
+    def forward(self, ref_points, src_points, ref_feats, src_feats, ref_masks=None, src_masks=None, gt_indices=None,
+                gt_overlap=None, ref_normal=None, src_normal=None):
+        """(1, N, 3), (1, M, 3), (1, N, A, C), (1, M, A, C) -> (ref (1, N, Cout), src (1, M, Cout), None x 4)."""
+        if ref_masks is not None or src_masks is not None or ref_normal is not None or src_normal is not None:
+            raise NotImplementedError("CUDA path: no masks / normals (the reference's 3DMatch and KITTI configs)")
+        assert ref_points.shape[0] == 1 and src_points.shape[0] == 1
+        n, m = ref_points.shape[1], src_points.shape[1]
+        points = torch.cat([ref_points[0], src_points[0]], 0)
+        feats = torch.cat([_act(ref_feats[0]), _act(src_feats[0])], 0)
+        out = self.forward_clouds(points, feats, [n], [m])
+        return out[:n].unsqueeze(0), out[n:].unsqueeze(0), None, None, None, None
+
+
+class SuperPointMatching(nn.Module):
+    """superpoint_matching.py:7-55; ties in the top-k are ordered by flat index (the reference leaves them to
+    torch.topk)."""
+
+    def __init__(self, num_correspondences, dual_normalization=True):
+        super().__init__()
+        self.num_correspondences = num_correspondences
+        self.dual_normalization = dual_normalization
+
+    def forward_pairs(self, ref_feats, src_feats, ref_sizes, src_sizes, ref_masks=None, src_masks=None):
+        """Batched: ref_feats (sum n_ref, C), src_feats (sum n_src, C) fp32 unit rows.
+        -> ref_idx (P, k), src_idx (P, k) pair-local int64 (-1 padded), scores (P, k), counts (P,) int32."""
+        rs, ss = np.asarray(ref_sizes, np.int64), np.asarray(src_sizes, np.int64)
+        rcu = np.concatenate([[0], np.cumsum(rs)])
+        scu = np.concatenate([[0], np.cumsum(ss)])
+        eo = np.concatenate([[0], np.cumsum(rs * ss)])
+        problems = torch.from_numpy(np.stack([rcu[:-1], rs, scu[:-1], ss, eo[:-1]], 1).astype(np.int64)).to(
+            ref_feats.device, non_blocking=True)
+        ri, si, sc, cnt, _ = T.superpoint_matching(ref_feats.float().contiguous(), src_feats.float().contiguous(),
+                                                   ref_masks, src_masks, problems, int(rs.max()), int(ss.max()),
+                                                   int(eo[-1]), self.num_correspondences, self.dual_normalization)
+        return ri, si, sc, cnt
+
+    def forward(self, ref_feats, src_feats, ref_masks=None, src_masks=None):
+        n, m = ref_feats.shape[0], src_feats.shape[0]
+        ri, si, sc, cnt = self.forward_pairs(ref_feats, src_feats, [n], [m], ref_masks, src_masks)
+        k = int(cnt[0])  # min(num_correspondences, number of unmasked entries), as the reference
+        return ri[0, :k], si[0, :k], sc[0, :k]

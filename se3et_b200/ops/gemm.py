@@ -4,8 +4,19 @@ import torch
 from .. import _lib
 
 
+def _out(spec, m, n, dtype, device):
+    """spec: False/None -> no output, True -> allocate, tensor -> write into it (row pitch = stride(0))."""
+    if spec is None or spec is False:
+        return None
+    if spec is True:
+        return torch.empty((m, n), dtype=dtype, device=device)
+    assert spec.dtype == dtype and spec.shape == (m, n) and spec.stride(1) == 1
+    return spec
+
+
 def linear_bf16(a, w, bias=None, alpha=1.0, relu=False, out_f32=True, out_bf16=False):
     """a: (M, K) bf16 row-major (row pitch a.stride(0)); w: (N, K) bf16 (nn.Linear layout); bias fp32 (N,) or None.
+    out_f32 / out_bf16: True to allocate, or a preallocated (M, N) view (columns contiguous) to write into.
     Returns (fp32 or None, bf16 or None) tensors of shape (M, N)."""
     _lib.require_cuda(a, w, bias)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
@@ -24,17 +35,29 @@ def linear_bf16(a, w, bias=None, alpha=1.0, relu=False, out_f32=True, out_bf16=F
             b_pad[:n] = bias
         of, ob = linear_bf16(a, w_pad, b_pad, alpha, relu, out_f32, out_bf16)
         return (of[:, :n].contiguous() if of is not None else None, ob[:, :n].contiguous() if ob is not None else None)
-    of = torch.empty((m, n), dtype=torch.float32, device=a.device) if out_f32 else None
-    ob = torch.empty((m, n), dtype=torch.bfloat16, device=a.device) if out_bf16 else None
+    of = _out(out_f32, m, n, torch.float32, a.device)
+    ob = _out(out_bf16, m, n, torch.bfloat16, a.device)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == n
     if m == 0:
         return of, ob
     L = _lib.lib()
-    _lib.check(L.se3et_gemm_bf16(
-        _lib.ptr(a), _lib.i64(a.stride(0)), _lib.ptr(w), _lib.i64(w.stride(0)), _lib.i64(m), _lib.i64(n), _lib.i64(k),
-        _lib.i64(1), _lib.i64(0), _lib.i64(0), _lib.ptr(bias), _lib.f32(alpha), int(bool(relu)), _lib.ptr(of),
-        _lib.ptr(ob), _lib.i64(n), _lib.i64(0), _lib.stream_ptr()), "gemm_bf16")
+
+    def call(f32, b16):
+        ref = f32 if f32 is not None else b16
+        _lib.check(L.se3et_gemm_bf16(
+            _lib.ptr(a), _lib.i64(a.stride(0) if m > 1 else k), _lib.ptr(w), _lib.i64(w.stride(0) if n > 1 else k),
+            _lib.i64(m), _lib.i64(n), _lib.i64(k), _lib.i64(1), _lib.i64(0), _lib.i64(0), _lib.ptr(bias),
+            _lib.f32(alpha), int(bool(relu)), _lib.ptr(f32), _lib.ptr(b16), _lib.i64(ref.stride(0) if m > 1 else n),
+            _lib.i64(0), _lib.stream_ptr()), "gemm_bf16")
+
+    if of is not None and ob is not None and (m == 1 or of.stride(0) == ob.stride(0)):
+        call(of, ob)
+    else:
+        if of is not None:
+            call(of, None)
+        if ob is not None:
+            call(None, ob)
     return of, ob
 
 

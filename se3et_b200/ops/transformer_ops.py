@@ -1,0 +1,105 @@
+"""Host wrappers of the superpoint-transformer and matching kernels (include/se3et_b200.h)."""
+import torch
+
+from .. import _lib
+
+
+def geo_embed_indices(points, cu, max_cloud, eoff, total_rows, sigma_d, sigma_a, angle_k):
+    """points (T,3) fp32, cu (B+1) int64 cloud offsets, eoff (B) int64 row offsets (sum of n_b^2) -> (rows, 4) fp32."""
+    _lib.require_cuda(points, cu, eoff)
+    assert points.dtype == torch.float32 and points.is_contiguous()
+    out = torch.empty((total_rows, 4), dtype=torch.float32, device=points.device)
+    _lib.check(_lib.lib().se3et_geo_embed_indices(
+        _lib.ptr(points), _lib.ptr(cu), _lib.i64(cu.numel() - 1), _lib.i64(points.shape[0]), _lib.i64(max_cloud),
+        _lib.ptr(eoff), _lib.f32(sigma_d), _lib.f32(sigma_a), _lib.i64(angle_k), _lib.ptr(out), _lib.stream_ptr()),
+        "geo_embed_indices")
+    return out
+
+
+def geo_embed_project(idx4, w_d, w_a, bias_sum):
+    """idx4 (rows,4) fp32; w_d, w_a (C,C) bf16; bias_sum (C,) fp32 = b_d + b_a -> (rows, C) bf16."""
+    rows, c = idx4.shape[0], w_d.shape[0]
+    out = torch.empty((rows, c), dtype=torch.bfloat16, device=idx4.device)
+    _lib.check(_lib.lib().se3et_geo_embed_project(_lib.ptr(idx4), _lib.i64(rows), _lib.i64(c), _lib.ptr(w_d),
+                                                 _lib.ptr(w_a), _lib.ptr(bias_sum), _lib.ptr(out), _lib.stream_ptr()),
+               "geo_embed_project")
+    return out
+
+
+def gemm_grouped_t(a, a_rows, b, b_rows, groups, max_m, n, n_valid, k, out, alpha=1.0):
+    """Grouped GEMM with transposed fp32 stores (see se3et_gemm_grouped_bf16)."""
+    _lib.check(_lib.lib().se3et_gemm_grouped_bf16(
+        _lib.ptr(a), _lib.i64(a.stride(0)), _lib.i64(a_rows), _lib.ptr(b), _lib.i64(b.stride(0)), _lib.i64(b_rows),
+        _lib.ptr(groups), _lib.i64(groups.shape[0]), _lib.i64(max_m), _lib.i64(n), _lib.i64(n_valid), _lib.i64(k),
+        _lib.f32(alpha), _lib.ptr(out), _lib.i64(0), 1, _lib.stream_ptr()), "gemm_grouped_bf16")
+    return out
+
+
+def flash_attention(q, q_pt, q_an, k, k_pt, k_an, v, v_pt, v_an, bias, problems, max_q, anchors, heads, head_dim,
+                    out, scale=None):
+    """q/k/v: bf16 tensors whose data_ptr is the element (point 0, anchor 0, head 0, 0); strides in elements.
+    problems: int64 (P,5) device; out: bf16 (rows*anchors, >= heads*head_dim) written at row (q_start+i)*A + a."""
+    if scale is None:
+        scale = 1.0 / head_dim ** 0.5
+    _lib.check(_lib.lib().se3et_flash_attention(
+        _lib.ptr(q), _lib.i64(q_pt), _lib.i64(q_an), _lib.ptr(k), _lib.i64(k_pt), _lib.i64(k_an), _lib.ptr(v),
+        _lib.i64(v_pt), _lib.i64(v_an), _lib.ptr(bias), _lib.ptr(problems), _lib.i64(problems.shape[0]),
+        _lib.i64(max_q), _lib.i64(anchors), _lib.i64(heads), _lib.i64(head_dim), _lib.f32(scale), _lib.ptr(out),
+        _lib.i64(out.stride(0)), _lib.stream_ptr()), "flash_attention")
+    return out
+
+
+def add_layernorm(x, resid, resid_div, gamma, beta, eps=1e-5, out_f32=False, out_bf16=True):
+    """LayerNorm(x + resid[row // resid_div]); x fp32 (rows, C), resid bf16 or None."""
+    rows, c = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if resid is not None:
+        assert resid.dtype == torch.bfloat16 and resid.is_contiguous()
+    of = torch.empty((rows, c), dtype=torch.float32, device=x.device) if out_f32 else None
+    ob = torch.empty((rows, c), dtype=torch.bfloat16, device=x.device) if out_bf16 else None
+    _lib.check(_lib.lib().se3et_add_layernorm(_lib.ptr(x), _lib.ptr(resid), _lib.i64(resid_div), _lib.i64(rows),
+                                             _lib.i64(c), _lib.ptr(gamma), _lib.ptr(beta), _lib.f32(eps), _lib.ptr(of),
+                                             _lib.ptr(ob), _lib.stream_ptr()), "add_layernorm")
+    return of, ob
+
+
+def l2_normalize_rows(x, eps=1e-12):
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().se3et_l2_normalize_rows(_lib.ptr(x), _lib.i64(x.shape[0]), _lib.i64(x.shape[1]),
+                                                 _lib.f32(eps), _lib.ptr(out), _lib.stream_ptr()), "l2_normalize_rows")
+    return out
+
+
+def superpoint_matching(ref_feats, src_feats, ref_masks, src_masks, problems, max_ref, max_src, e_total,
+                        num_correspondences, dual_normalization=True):
+    """Batched SuperPointMatching. ref_feats (Tr, C) / src_feats (Ts, C) fp32 unit rows; masks uint8/bool or None;
+    problems int64 (P,5) {ref_start, n_ref, src_start, n_src, e_off}.
+    Returns ref_idx (P,k) int64, src_idx (P,k) int64, scores (P,k) fp32, counts (P,) int32 (pair-local indices)."""
+    _lib.require_cuda(ref_feats, src_feats, problems)
+    assert ref_feats.dtype == torch.float32 and src_feats.dtype == torch.float32
+    assert ref_feats.is_contiguous() and src_feats.is_contiguous()
+    dev = ref_feats.device
+    p = problems.shape[0]
+    k = int(num_correspondences)
+
+    def mask8(mk):
+        if mk is None:
+            return None
+        mk = mk.contiguous()
+        return mk.view(torch.uint8) if mk.dtype == torch.bool else mk.to(torch.uint8)
+
+    rm, sm = mask8(ref_masks), mask8(src_masks)
+    e = torch.empty((max(e_total, 1),), dtype=torch.float32, device=dev)
+    rs = torch.empty((max(ref_feats.shape[0], 1),), dtype=torch.float32, device=dev)
+    cs = torch.empty((max(src_feats.shape[0], 1),), dtype=torch.float32, device=dev)
+    ri = torch.empty((p, k), dtype=torch.int64, device=dev)
+    si = torch.empty((p, k), dtype=torch.int64, device=dev)
+    sc = torch.empty((p, k), dtype=torch.float32, device=dev)
+    cnt = torch.empty((p,), dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().se3et_superpoint_matching(
+        _lib.ptr(ref_feats), _lib.ptr(src_feats), _lib.i64(ref_feats.shape[1]), _lib.ptr(rm), _lib.ptr(sm),
+        _lib.ptr(problems), _lib.i64(p), _lib.i64(max_ref), _lib.i64(max_src), _lib.i64(k),
+        int(bool(dual_normalization)), _lib.ptr(e), _lib.ptr(rs), _lib.ptr(cs), _lib.ptr(ri), _lib.ptr(si), _lib.ptr(sc),
+        _lib.ptr(cnt), _lib.stream_ptr()), "superpoint_matching")
+    return ri, si, sc, cnt, e

@@ -184,7 +184,6 @@ def test_backbone_batched_pairs_equal_single_pairs(gold, pyramid):
         na = a.shape[0]
         assert o.shape[0] == na + b.shape[0]
         ea, eb = rel_err(o[:na], a), rel_err(o[na:], b)
-        # pair A starts at row 0 in both runs => bit-identical; pair B's GroupNorm partial sums are partitioned
-        # differently (fp32 summation order), a 1e-6 perturbation that bf16 activation rounding amplifies to the
-        # bf16 noise floor (~5e-3) over 11 blocks -- far below the 2e-2 parity tolerance, far above a stats mix-up
-        assert ea < 1e-5 and eb < 1e-2, (lvl, ea, eb)
+        # GroupNorm statistics are accumulated in fp64, so they do not depend on how rows are split over CTAs;
+        # what is left is fp64 summation-order noise (1e-16) that can flip a bf16 rounding once in a blue moon
+        assert ea < 2e-3 and eb < 2e-3, (lvl, ea, eb)
