@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Headline benchmark: SE3ET-I 3DMatch-shaped inference, synthetic pairs, pairs/sec (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (one process per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path on the host cores
+
+A step = one pass of the hot path (pyramid precompute -> E2PN backbone -> superpoint transformer -> SuperPointMatching)
+over a batch of `--pairs` synthetic 3DMatch-shaped pairs per GPU, random-init SE3ET-I weights.
+  value : pairs/sec, inputs resident in HBM, CUDA events, max over ranks           (whole job, all GPUs)
+  e2e   : pairs/sec through model.forward_pairs(host arrays): pinned H2D of the points + D2H of the correspondences
+  roofline : dominant kernel (picked from the live per-entry-point event timings), achieved vs measured peak
+  cpu_baseline : oracle/_ref (unmodified reference C++ precompute) + the torch-CPU port of the forward, bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "3dmatch_shape_pairs_per_sec"
+VARIANT = "se3eti.3dmatch"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([v.strip() for v in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_pairs(count, first=0):
+    from se3et_b200 import synthetic
+    pairs = [synthetic.make_3dmatch_pair(first + i) for i in range(count)]
+    return [(p["ref_points"], p["src_points"]) for p in pairs]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: reference C++ precompute (oracle/_ref) + torch-CPU port of the forward
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_forward_factory():
+    import torch
+    from oracle import e2pn as oe
+    from oracle import points as op
+    from oracle import transformer as ot
+    from se3et_b200.model import create_model, make_cfg
+    cfg = make_cfg(VARIANT)
+    torch.manual_seed(0)
+    sd = {k: v.detach().clone() for k, v in create_model(cfg).state_dict().items()}
+    impl = "ref_raw" if op.have_ref() else "oracle"
+    b, g = cfg.backbone, cfg.geotransformer
+
+    def run(ref, src):
+        pts = np.concatenate([ref, src])
+        lens = np.array([len(ref), len(src)])
+        d = op.precompute_data_stack_mode(pts, lens, b.num_stages, b.init_voxel_size, b.init_radius,
+                                          cfg.neighbor_limits, impl=impl)
+        with torch.no_grad():
+            fl = oe.e2pn_forward(sd, torch.ones(len(pts), 1), d, b.init_sigma, b.group_norm)
+            n = int(d["lengths"][-1][0])
+            pc = torch.from_numpy(d["points"][-1])
+            r, s, _, _ = ot.geometric_transformer(sd, pc[:n], pc[n:], fl[-1][:n], fl[-1][n:], g.blocks, g.hidden_dim,
+                                                  g.num_heads, g.sigma_d, g.sigma_a, g.angle_k)
+            r = torch.nn.functional.normalize(r, p=2, dim=1)
+            s = torch.nn.functional.normalize(s, p=2, dim=1)
+            return ot.superpoint_matching(r, s, torch.ones(len(r), dtype=torch.bool), torch.ones(len(s), dtype=torch.bool),
+                                          cfg.coarse_matching.num_correspondences)
+    return run, ("reference-c++ precompute + port forward" if impl == "ref_raw" else "port")
+
+
+def run_cpu(steps, warmup, pairs_per_step=1):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    run, kind_note = cpu_forward_factory()
+    clouds = make_pairs(max(1, pairs_per_step))
+    for _ in range(warmup):
+        run(*clouds[0])
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        for c in clouds[:pairs_per_step]:
+            run(*c)
+            done += 1
+    dt = time.perf_counter() - t0
+    return done / dt, dt, cores, kind_note, done
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), min(args.warmup, 1)
+    steps = min(steps, 4)  # each step is one full pair through the CPU path (several seconds)
+    value, dt, cores, note, done = run_cpu(steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "SE3ET-I 3DMatch-shaped inference, 1 synthetic pair per step (bounded sample of the "
+                               "64-pair batch), random-init weights", "variant": VARIANT},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
+                         "sample": "%d synthetic 3DMatch-shaped pair(s): %s, torch threads = %d" % (done, note, cores)},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=64, help="pairs per step per GPU")
+    ap.add_argument("--pairs-per-launch", type=int, default=16, help="pairs stacked into one launch sequence")
+    ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic pairs generated (cycled)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from se3et_b200 import _lib
+    from se3et_b200.model import create_model, make_cfg
+
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    args.warmup = max(args.warmup, 3)
+
+    cfg = make_cfg(VARIANT)
+    torch.manual_seed(0)
+    model = create_model(cfg).to(dev).eval()
+
+    # synthetic pairs: `distinct` different ones, cycled to `pairs` (pair i of rank r is seed 1000 + (r*pairs+i) % distinct)
+    distinct = make_pairs(min(args.distinct, args.pairs), first=0)
+    clouds = [distinct[(rank * args.pairs + i) % len(distinct)] for i in range(args.pairs)]
+    ppl = max(1, min(args.pairs_per_launch, args.pairs))
+    groups = [clouds[i:i + ppl] for i in range(0, len(clouds), ppl)]
+    dev_inputs = []
+    for g in groups:
+        lens = np.array([len(c) for pair in g for c in pair], dtype=np.int64)
+        pts = torch.from_numpy(np.concatenate([c for pair in g for c in pair])).to(dev)
+        dev_inputs.append((pts, torch.from_numpy(lens)))
+    in_bytes = sum(int(p.numel()) * 4 for p, _ in dev_inputs)
+    pinned = torch.empty((max(int(l.sum()) for _, l in dev_inputs), 3), dtype=torch.float32).pin_memory()
+
+    def step_device():
+        for pts, lens in dev_inputs:
+            model.forward_stacked(pts, lens)
+
+    def step_e2e():
+        out_bytes = 0
+        for g in groups:
+            res = model.forward_pairs(g, pinned=pinned)
+            out_bytes += sum(r[0].nbytes + r[1].nbytes + r[2].nbytes for r in res)
+        return out_bytes
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    L = _lib.lib()
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+
+    # ---- timed region: K steps, CUDA events, per-entry-point events for the roofline
+    timed_names = ["se3et_kpconv_gather", "se3et_gemm_bf16", "se3et_groupnorm_apply", "se3et_groupnorm_stats",
+                   "se3et_radius_neighbors", "se3et_geo_embed_project", "se3et_flash_attention"]
+    L.enabled = True
+    L.reset(timed=timed_names)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    L.enabled = False
+    ms = e0.elapsed_time(e1)
+    launches = L.launches()
+    per_api = {n: L.timed_ms(n) for n in timed_names}
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * args.pairs * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public API (host buffers in, host results out)
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    out_bytes = 0
+    for _ in range(args.steps):
+        out_bytes = step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * args.pairs * args.steps / e2e_s
+
+    if rank == 0:
+        peaks = load_peaks()
+        # dominant entry point by summed device time inside the timed region
+        dom = max(per_api, key=lambda n: per_api[n][0])
+        dom_ms, dom_calls = per_api[dom]
+        pair_units = args.pairs * args.steps  # pairs processed by this rank in the timed region
+        # algorithmic work per pair (DESIGN.md "Kernels"): bytes or flops
+        ALG = {
+            "se3et_radius_neighbors": ("hbm", 27.8e6), "se3et_groupnorm_apply": ("hbm", 0.62e9),
+            "se3et_groupnorm_stats": ("hbm", 0.41e9), "se3et_kpconv_gather": ("hbm", 1.9e9 + 3.4e9 / 2),
+            "se3et_gemm_bf16": ("tensor", (139.3 + 46.5 + 30.0) * 1e9), "se3et_geo_embed_project": ("tensor", 135e9),
+            "se3et_flash_attention": ("tensor", 6.2e9),
+        }
+        bound, per_pair = ALG[dom]
+        if bound == "hbm":
+            achieved = per_pair * pair_units / (dom_ms / 1e3) / 1e9
+            peak, unit = peaks["hbm_gbs"], "GB/s"
+        else:
+            achieved = per_pair * pair_units / (dom_ms / 1e3) / 1e12
+            peak, unit = peaks["bf16_tflops"], "TFLOP/s"
+        roofline = {"kernel": dom, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+                    "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"],
+                    "share_of_step": dom_ms / ms, "calls": dom_calls,
+                    "per_entry_point_ms": {n: round(v[0], 3) for n, v in per_api.items()}}
+        cpu = None
+        if not args.no_cpu_baseline:
+            v, dt, cores, note, done = run_cpu(2, 1)
+            cpu = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
+                   "sample": "%d synthetic 3DMatch-shaped pairs of the same workload (%s), torch threads = %d, %.1f s"
+                             % (done, note, cores, dt)}
+        line = {
+            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "SE3ET-I 3DMatch-shaped inference, batch of %d synthetic pairs per GPU per step "
+                                   "(~15k pts/cloud, voxel 0.025 m, 4 stages), random-init weights" % args.pairs,
+                       "variant": VARIANT, "pairs_per_gpu_per_step": args.pairs, "pairs_per_launch": ppl,
+                       "distinct_pairs": len(distinct), "parallelism": "pairs sharded over %d GPU(s), no collective" % world,
+                       "l2": "working set per launch (activations of %d stacked pairs, > 1 GB) exceeds the 126 MB L2" % ppl},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes},
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -22,6 +22,58 @@ _ERRORS = {-1: "CUDA error", -2: "invalid argument", -3: "workspace too small", 
 
 _lib = None
 
+# kernels launched by one call of each entry point (cudaMemsetAsync nodes are not counted)
+KERNELS_PER_CALL = {
+    "se3et_grid_subsample": 16, "se3et_radius_neighbors": 9, "se3et_gemm_bf16": 1, "se3et_gemm_grouped_bf16": 1,
+    "se3et_kpconv_gather": 1, "se3et_groupnorm_stats": 1, "se3et_groupnorm_apply": 1, "se3et_maxpool_nbr": 1,
+    "se3et_anchor_max": 1, "se3et_upsample_concat": 1, "se3et_geo_embed_indices": 1, "se3et_geo_embed_project": 1,
+    "se3et_flash_attention": 1, "se3et_add_layernorm": 1, "se3et_l2_normalize_rows": 1,
+    "se3et_superpoint_matching": 3,
+}
+
+
+class _Instrumented:
+    """Thin proxy over the ctypes library: counts calls per entry point and, for the names in `timed`, brackets the
+    call with CUDA events on the current stream (bench.py reads both; nothing is recorded unless enabled)."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        self.counts = {}
+        self.timed = set()
+        self.events = {}
+        self.enabled = False
+
+    def __getattr__(self, name):
+        fn = getattr(self._cdll, name)
+        if not name.startswith("se3et_"):
+            return fn
+
+        def call(*args):
+            if not self.enabled:
+                return fn(*args)
+            self.counts[name] = self.counts.get(name, 0) + 1
+            if name in self.timed:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                rc = fn(*args)
+                b.record()
+                self.events.setdefault(name, []).append((a, b))
+                return rc
+            return fn(*args)
+
+        call.restype = getattr(fn, "restype", None)
+        return call
+
+    def reset(self, timed=()):
+        self.counts, self.events, self.timed = {}, {}, set(timed)
+
+    def launches(self):
+        return sum(KERNELS_PER_CALL.get(k, 1) * v for k, v in self.counts.items())
+
+    def timed_ms(self, name):
+        ev = self.events.get(name, [])
+        return sum(a.elapsed_time(b) for a, b in ev), len(ev)
+
 
 def declared_symbols():
     """Every function name declared in include/se3et_b200.h."""
@@ -44,8 +96,10 @@ def lib():
         if not os.path.exists(path):
             raise RuntimeError(
                 "se3et_b200: %s is missing and could not be built; the hot path has no CPU fallback" % path)
-        _lib = ctypes.CDLL(path)
-        _lib.se3et_last_error.restype = ctypes.c_char_p
+        cdll = ctypes.CDLL(path)
+        cdll.se3et_last_error.restype = ctypes.c_char_p
+        _lib = _Instrumented(cdll)
+        _lib._name = cdll._name
     return _lib
 
 

@@ -1,0 +1,167 @@
+"""Hot-path model wiring: mirror of experiments/<variant>/{config,model}.py up to and including coarse matching.
+
+    cfg = make_cfg('se3eti.3dmatch')            # experiments/se3eti.3dmatch/config.py:60-239 (the fields the path reads)
+    model = create_model(cfg).cuda().eval()     # experiments/se3eti.3dmatch/model.py:231-233
+    out = model(data_dict)                      # one pair, reference data_dict (model.py:80-172)
+    out = model.forward_pairs(clouds)           # P pairs in one launch sequence, host arrays in / device tensors out
+
+state_dict keys are the reference's (`backbone.*`, `transformer.*`), so a reference checkpoint loads with
+strict=False (the fine-matching / optimal-transport modules downstream of SuperPointMatching are out of scope).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .modules.e2pn import E2PN
+from .modules.transformer import GeometricTransformer, SuperPointMatching
+from .ops import transformer_ops as T
+from .precompute import precompute_data_stack_mode
+
+
+class Cfg(dict):
+    """Attribute dict (stand-in for easydict, which the reference configs use)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+_VARIANTS = {
+    # name: (init_dim, group_norm, backbone_out, hidden, tr_out, stages, voxel, base_radius, sigma_d, limits)
+    'se3eti.3dmatch': (64, 32, 256, 256, 256, 4, 0.025, 2.5, 0.2, [38, 36, 36, 38]),
+    'se3eti2.3dmatch': (32, 16, 128, 128, 128, 4, 0.025, 2.5, 0.2, [38, 36, 36, 38]),
+    'se3eti.kitti': (64, 32, 256, 128, 256, 5, 0.3, 4.25, 4.8, [40, 40, 40, 40, 40]),
+}
+
+
+def make_cfg(variant='se3eti.3dmatch'):
+    if variant not in _VARIANTS:
+        raise NotImplementedError("variant %r: the CUDA path covers %s" % (variant, sorted(_VARIANTS)))
+    d, g, bo, hid, to, stages, voxel, base_r, sigma_d, limits = _VARIANTS[variant]
+    c = Cfg(variant=variant)
+    c.backbone = Cfg(num_stages=stages, init_voxel_size=voxel, kernel_size=15, base_radius=base_r, base_sigma=2.0,
+                     init_radius=base_r * voxel, init_sigma=2.0 * voxel, group_norm=g, input_dim=1, init_dim=d,
+                     output_dim=bo)
+    c.epn = Cfg(kanchor=6, quotient_factor=4, num_kernel_points=15, non_sep_conv=True, equiv_mode_kp=True,
+                fixed_kernel_points='center', rot_by_permute=True, ignore_steer_constraint=False, epn_kernel=False,
+                att_pooling=False, att_permute=False, dual_feature=False, gather_by_idxing=False,
+                use_batch_norm=True, batch_norm_momentum=0.99, KP_extent=1.0, KP_influence='linear',
+                aggregation_mode='sum')
+    c.geotransformer = Cfg(input_dim=d * (16 if stages == 4 else 32), hidden_dim=hid, output_dim=to, num_heads=4,
+                           blocks=['self_eq', 'cross', 'self_eq', 'cross', 'self_eq', 'cross'], sigma_d=sigma_d,
+                           sigma_a=15, angle_k=3, supervise_rotation=False, reduction_a='max', align_mode='0',
+                           alternative_impl=False, n_level_equiv=0, attn_r_positive='softplus',
+                           attn_r_positive_rot_supervise='minus')
+    c.coarse_matching = Cfg(num_targets=128, overlap_threshold=0.1, num_correspondences=256, dual_normalization=True)
+    c.neighbor_limits = list(limits)  # demo.py:52 for 3DMatch; KITTI limits are calibrated per dataset (data.py:212-252)
+    return c
+
+
+class GeoTransformer(nn.Module):
+    """experiments/se3eti.3dmatch/model.py:20-172 (KPFCNN encoder -> conditional transformer -> coarse matching)."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        b, g = cfg.backbone, cfg.geotransformer
+        self.backbone = E2PN(b.input_dim, b.output_dim, b.init_dim, b.init_radius, b.init_sigma, b.group_norm, cfg.epn,
+                             num_stages=b.num_stages)
+        self.transformer = GeometricTransformer(
+            g.input_dim, g.output_dim, g.hidden_dim, g.num_heads, g.blocks, g.sigma_d, g.sigma_a, g.angle_k,
+            supervise_rotation=g.supervise_rotation, reduction_a=g.reduction_a, na=cfg.epn.kanchor,
+            attn_r_positive=g.attn_r_positive, attn_r_positive_rot_supervise=g.attn_r_positive_rot_supervise,
+            align_mode=g.align_mode, alternative_impl=g.alternative_impl, n_level_equiv=g.n_level_equiv)
+        self.coarse_matching = SuperPointMatching(cfg.coarse_matching.num_correspondences,
+                                                  cfg.coarse_matching.dual_normalization)
+
+    # ---- one pair, reference data_dict -------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, data_dict, ref_node_masks=None, src_node_masks=None):
+        out = {}
+        feats = data_dict['features']
+        ref_length_c = int(data_dict['lengths'][-1][0])
+        ref_length_f = int(data_dict['lengths'][1][0])
+        points_c = data_dict['points'][-1]
+        feats_list = self.backbone(feats, data_dict)
+        feats_c, feats_f = feats_list[-1], feats_list[0]
+        n_c = points_c.shape[0]
+        ref_c, src_c = self.transformer.forward_clouds(points_c, feats_c, [ref_length_c], [n_c - ref_length_c]).split(
+            [ref_length_c, n_c - ref_length_c])
+        ref_n = T.l2_normalize_rows(ref_c.contiguous())
+        src_n = T.l2_normalize_rows(src_c.contiguous())
+        out['ref_points_c'], out['src_points_c'] = points_c[:ref_length_c], points_c[ref_length_c:]
+        out['ref_feats_c'], out['src_feats_c'] = ref_n, src_n
+        out['ref_feats_f'], out['src_feats_f'] = feats_f[:ref_length_f], feats_f[ref_length_f:]
+        ri, si, sc = self.coarse_matching(ref_n, src_n, ref_node_masks, src_node_masks)
+        out['ref_node_corr_indices'], out['src_node_corr_indices'], out['node_corr_scores'] = ri, si, sc
+        return out
+
+    # ---- P pairs, one launch sequence ---------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_stacked(self, points, lengths):
+        """points fp32 (N, 3) on the GPU, clouds stacked [ref_0, src_0, ref_1, src_1, ...]; lengths int64 (2P,) on the
+        HOST. Returns dict with per-pair correspondences (P, k) and the flat coarse features."""
+        _lib.require_cuda(points)
+        cfg = self.cfg
+        num_pairs = lengths.shape[0] // 2
+        dev = points.device
+        b = cfg.backbone
+        dd = precompute_data_stack_mode(points, lengths.to(dev), b.num_stages, b.init_voxel_size, b.init_radius,
+                                        cfg.neighbor_limits)
+        feats = torch.ones((points.shape[0], 1), dtype=torch.bfloat16, device=dev)
+        feats_list = self.backbone(feats, dd)
+        feats_c, feats_f = feats_list[-1], feats_list[0]
+        len_c = dd['lengths'][-1].cpu().numpy()  # already synchronised by the subsampling that produced it
+        ref_sizes, src_sizes = len_c[0::2], len_c[1::2]
+        points_c = dd['points'][-1]
+        if num_pairs > 1:
+            # transformer order: all reference clouds, then all source clouds
+            starts = np.concatenate([[0], np.cumsum(len_c)])[:-1]
+            order = np.concatenate([np.arange(starts[i], starts[i] + len_c[i]) for i in
+                                    list(range(0, 2 * num_pairs, 2)) + list(range(1, 2 * num_pairs, 2))])
+            order_t = torch.from_numpy(order).to(dev, non_blocking=True)
+            points_c = points_c.index_select(0, order_t)
+            feats_c = feats_c.index_select(0, order_t)
+        tr = int(ref_sizes.sum())
+        both = self.transformer.forward_clouds(points_c, feats_c, ref_sizes.tolist(), src_sizes.tolist())
+        normed = T.l2_normalize_rows(both)
+        ri, si, sc, cnt = self.coarse_matching.forward_pairs(normed[:tr], normed[tr:], ref_sizes, src_sizes)
+        return {
+            'ref_node_corr_indices': ri, 'src_node_corr_indices': si, 'node_corr_scores': sc, 'num_corr': cnt,
+            'ref_feats_c': normed[:tr], 'src_feats_c': normed[tr:], 'ref_sizes': ref_sizes, 'src_sizes': src_sizes,
+            'feats_f': feats_f, 'points_c': points_c, 'data_dict': dd,
+        }
+
+    @torch.no_grad()
+    def forward_pairs(self, clouds, pinned=None):
+        """Public end-to-end entry: clouds = [(ref (n,3) float32 ndarray, src (m,3) float32 ndarray), ...] on the HOST.
+        Copies the stacked points to the GPU (from pinned memory), runs the whole hot path and returns the
+        correspondences on the HOST: list of (ref_idx, src_idx, scores) numpy arrays."""
+        lens = np.array([len(c) for pair in clouds for c in pair], dtype=np.int64)
+        total = int(lens.sum())
+        if pinned is None or pinned.shape[0] < total:
+            pinned = torch.empty((total, 3), dtype=torch.float32).pin_memory()
+        o = 0
+        host = pinned.numpy()
+        for pair in clouds:
+            for c in pair:
+                host[o:o + len(c)] = c
+                o += len(c)
+        dev = next(self.parameters()).device
+        points = pinned[:total].to(dev, non_blocking=True)
+        out = self.forward_stacked(points, torch.from_numpy(lens))
+        ri = out['ref_node_corr_indices'].cpu().numpy()
+        si = out['src_node_corr_indices'].cpu().numpy()
+        sc = out['node_corr_scores'].cpu().numpy()
+        cnt = out['num_corr'].cpu().numpy()
+        return [(ri[p, :cnt[p]], si[p, :cnt[p]], sc[p, :cnt[p]]) for p in range(len(clouds))]
+
+
+def create_model(config):
+    return GeoTransformer(config)
