@@ -105,6 +105,18 @@ int se3et_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int6
                     int act, float* out_f32, void* out_bf16, int64_t ldc, int64_t c_batch_stride,
                     se3et_stream_t stream);
 
+/* gemm_bf16 with the GroupNorm statistics of its fp32 output accumulated in the epilogue:
+ * out_f32[M,N] = A[M,K] * B[N,K]^T (+ bias), stats[seg][g] += {sum, sum of squares} over the rows of pair `seg`
+ * (row r belongs to point r / rows_per_point) and the channels of group g.  stats is zeroed by the call.
+ * replaces: the Linear / KPConv contraction followed by the statistics pass of GroupNormEPN
+ *   (blocks_epn.py:658-663, 697-701) without re-reading the activations.
+ * Returns SE3ET_ERR_UNSUPPORTED when N / groups is neither a power of two <= 32 nor a multiple of 32
+ * (the host then uses se3et_groupnorm_stats). */
+int se3et_gemm_bf16_gnstats(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int64_t n, int64_t k,
+                            const float* bias, float* out_f32, int64_t ldc, double* stats,
+                            const int64_t* seg_offsets, int64_t nseg, int64_t groups, int64_t rows_per_point,
+                            se3et_stream_t stream);
+
 /* Grouped variant: problem g (blockIdx.z) reads A rows [a_row0, a_row0 + m_rows) and B rows
  * [b_row0, b_row0 + n) of the flat operands, groups = int64 [num_groups][6] {a_row0, b_row0, m_rows, c_off,
  * ldc, unused} on the device; max_m = largest m_rows.  transposed = 1 stores

@@ -8,34 +8,18 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "kpconv_tables.cuh"
 
 namespace se3et {
 
-// ---------------------------------------------------------------------------------------------
-// Octahedral group tables for kanchor = 6, quotient_factor = 4, K = 15 (SURVEY 8c golden constants;
-// verified against the module's kidx_rot / ridx_rot buffers by the host before every launch).
-//   kKidx[k][r]: weight-sharing class (0..5) that kernel point k falls into after rotation by anchor r
-//   kRidx[a][r]: weight anchor slot a' = ridx_rot[a][r] that input anchor a feeds for output anchor r
-// ---------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int kidx_tab(int k, int r) {
-  constexpr int t[15][6] = {{0, 1, 1, 1, 1, 2}, {1, 0, 1, 2, 1, 1}, {1, 1, 0, 1, 2, 1}, {1, 2, 1, 0, 1, 1},
-                            {1, 1, 2, 1, 0, 1}, {2, 1, 1, 1, 1, 0}, {3, 3, 3, 4, 4, 4}, {3, 4, 3, 3, 4, 4},
-                            {3, 4, 4, 3, 3, 4}, {3, 3, 4, 4, 3, 4}, {4, 3, 3, 4, 4, 3}, {4, 4, 3, 3, 4, 3},
-                            {4, 4, 4, 3, 3, 3}, {4, 3, 4, 4, 3, 3}, {5, 5, 5, 5, 5, 5}};
-  return t[k][r];
-}
-__host__ __device__ constexpr int ridx_tab(int a, int r) {
-  constexpr int t[6][6] = {{0, 3, 3, 3, 3, 5}, {1, 0, 4, 5, 2, 1}, {2, 2, 0, 4, 5, 4},
-                           {3, 5, 2, 0, 4, 3}, {4, 4, 5, 2, 0, 2}, {5, 1, 1, 1, 1, 0}};
-  return t[a][r];
-}
 __constant__ int c_ridx[6][6] = {{0, 3, 3, 3, 3, 5}, {1, 0, 4, 5, 2, 1}, {2, 2, 0, 4, 5, 4},
                                  {3, 5, 2, 0, 4, 3}, {4, 4, 5, 2, 0, 2}, {5, 1, 1, 1, 1, 0}};
 
-constexpr int kA = 6;        // anchors
-constexpr int kKP = 15;      // kernel points
-constexpr int kKC = 6;       // weight-sharing classes
 constexpr int kMaxH = 64;    // neighbour columns supported by the gather kernel
+
+int kpconv_gather_mma(const float* q_pts, const float* s_pts, const int64_t* neighbors, int64_t nq, int64_t ns, int h,
+                      const __nv_bfloat16* x, int cin, const float* kp, float inv_extent, __nv_bfloat16* out, int kpad,
+                      cudaStream_t st);  // kpconv.cu
 
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
@@ -243,6 +227,79 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(NormSide a, NormSi
   }
 }
 
+// Streaming form of the same operation for power-of-two row widths (every SE3ET layer): a thread owns a fixed
+// group of 4 channels and walks down the rows, so the per-(pair, group) mean / rstd and the affine parameters are
+// loaded and folded once per pair instead of once per element; the row -> pair lookup advances linearly.
+struct NormCols {
+  float mean[4], s[4], beta[4];
+};
+__device__ __forceinline__ void load_norm_cols(const NormSide& n, int seg, int G, int cpg, int c0, double cnt, float eps,
+                                               NormCols& o) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int g = (c0 + j) / cpg;
+    const double mean = n.stats[((int64_t)seg * G + g) * 2] / cnt;
+    const double var = n.stats[((int64_t)seg * G + g) * 2 + 1] / cnt - mean * mean;
+    const float rstd = rsqrtf((float)fmax(var, 0.0) + eps);
+    o.mean[j] = (float)mean;
+    o.s[j] = rstd * n.gamma[c0 + j];
+    o.beta[j] = n.beta[c0 + j];
+  }
+}
+
+template <bool kHasB>
+__global__ void __launch_bounds__(256) groupnorm_apply_rows_kernel(NormSide a, NormSide b,
+                                                                    const __nv_bfloat16* __restrict__ resid,
+                                                                    int64_t rows, int C, int cpg,
+                                                                    const int64_t* __restrict__ seg_off, int nseg,
+                                                                    int rows_per_point, float eps, float slope,
+                                                                    float* __restrict__ out_f32,
+                                                                    __nv_bfloat16* __restrict__ out_bf16) {
+  const int V = C >> 2;  // float4 vectors per row; a power of two <= 256, so it divides the thread count
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (int)(tid % V) * 4;
+  const int64_t row_step = (int64_t)gridDim.x * blockDim.x / V;
+  const int G = C / cpg;
+  int seg = -1;
+  int64_t seg_end = 0;  // first row past the current pair
+  NormCols na, nb;
+  for (int64_t row = tid / V; row < rows; row += row_step) {
+    if (row >= seg_end) {
+      if (seg < 0) seg = segment_of(seg_off, nseg, row / rows_per_point);
+      while (seg + 1 < nseg && seg_off[seg + 1] * rows_per_point <= row) ++seg;
+      seg_end = seg_off[seg + 1] * rows_per_point;
+      if (seg == nseg - 1) seg_end = rows;
+      const double cnt = (double)(seg_off[seg + 1] - seg_off[seg]) * rows_per_point * cpg;
+      load_norm_cols(a, seg, G, cpg, c0, cnt, eps, na);
+      if (kHasB) load_norm_cols(b, seg, G, cpg, c0, cnt, eps, nb);
+    }
+    const float4 ya = __ldcs(reinterpret_cast<const float4*>(a.y + row * C + c0));
+    float v[4] = {(ya.x - na.mean[0]) * na.s[0] + na.beta[0], (ya.y - na.mean[1]) * na.s[1] + na.beta[1],
+                  (ya.z - na.mean[2]) * na.s[2] + na.beta[2], (ya.w - na.mean[3]) * na.s[3] + na.beta[3]};
+    if (kHasB) {
+      const float4 yb = __ldcs(reinterpret_cast<const float4*>(b.y + row * C + c0));
+      v[0] += (yb.x - nb.mean[0]) * nb.s[0] + nb.beta[0];
+      v[1] += (yb.y - nb.mean[1]) * nb.s[1] + nb.beta[1];
+      v[2] += (yb.z - nb.mean[2]) * nb.s[2] + nb.beta[2];
+      v[3] += (yb.w - nb.mean[3]) * nb.s[3] + nb.beta[3];
+    }
+    if (resid) {
+      const uint2 rv = *reinterpret_cast<const uint2*>(resid + row * C + c0);
+      v[0] += bf_lo(rv.x); v[1] += bf_hi(rv.x); v[2] += bf_lo(rv.y); v[3] += bf_hi(rv.y);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = v[j] >= 0.f ? v[j] : v[j] * slope;
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * C + c0) = make_float4(v[0], v[1], v[2], v[3]);
+    if (out_bf16) {
+      uint2 o;
+      o.x = pack_bf16(v[0], v[1]);
+      o.y = pack_bf16(v[2], v[3]);
+      *reinterpret_cast<uint2*>(out_bf16 + row * C + c0) = o;
+    }
+  }
+}
+
+
 // out[q][col] = max_n xpad[idx[q][n]][col]; shadow neighbours contribute 0 (blocks.py:100-109)
 __global__ void __launch_bounds__(256) maxpool_nbr_kernel(const __nv_bfloat16* __restrict__ x, int64_t ns, int width,
                                                            const int64_t* __restrict__ idx, int H_full,
@@ -345,6 +402,9 @@ extern "C" int se3et_kpconv_gather(const float* q_pts, const float* s_pts, const
   const auto* x = static_cast<const __nv_bfloat16*>(x_bf16);
   auto* out = static_cast<__nv_bfloat16*>(out_bf16);
   const int width = 6 * (int)cin;
+  if (cin % 16 == 0 && kpad == 36 * cin && ns > 0)  // tensor-core producer (kpconv.cu)
+    return kpconv_gather_mma(q_pts, s_pts, neighbors, nq, ns, (int)h, x, (int)cin, kernel_points_15x3, 1.f / kp_extent,
+                             out, (int)kpad, st);
   if (cin % 2 == 0) {
     const int threads = width / 2 >= 256 ? 256 : (width / 2 <= 64 ? 64 : 128);
     kpconv_gather_kernel<true><<<(unsigned)nq, threads, 0, st>>>(q_pts, s_pts, neighbors, (int)h, ns, x, (int)cin,
@@ -390,6 +450,26 @@ extern "C" int se3et_groupnorm_apply(const float* ya, const double* stats_a, con
   if (yb && (!stats_b || !gamma_b || !beta_b)) return SE3ET_ERR_ARG;
   NormSide a{ya, stats_a, gamma_a, beta_a};
   NormSide b{yb, stats_b, gamma_b, beta_b};
+  const int64_t vecs = channels / 4;
+  if (vecs <= 256 && (vecs & (vecs - 1)) == 0) {
+    // fixed-column streaming kernel; grid sized to a multiple of the SM count, every thread gets >= 1 row
+    int64_t blocks = ceil_div(rows * vecs, 256);
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    auto* rb = static_cast<const __nv_bfloat16*>(resid_bf16);
+    auto* ob = static_cast<__nv_bfloat16*>(out_bf16);
+    if (yb)
+      groupnorm_apply_rows_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(
+          a, b, rb, rows, (int)channels, (int)(channels / groups), seg_offsets, (int)nseg, (int)rows_per_point, eps,
+          leaky_slope, out_f32, ob);
+    else
+      groupnorm_apply_rows_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(
+          a, b, rb, rows, (int)channels, (int)(channels / groups), seg_offsets, (int)nseg, (int)rows_per_point, eps,
+          leaky_slope, out_f32, ob);
+    SE3ET_LAUNCH_CHECK();
+    return SE3ET_OK;
+  }
   groupnorm_apply_kernel<<<elementwise_blocks(rows * channels / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       a, b, static_cast<const __nv_bfloat16*>(resid_bf16), rows, (int)channels, (int)(channels / groups), seg_offsets,
       (int)nseg, (int)rows_per_point, eps, leaky_slope, out_f32, static_cast<__nv_bfloat16*>(out_bf16));

@@ -30,6 +30,13 @@ struct GemmEpilogue {
   int act;                   // 0 none, 1 ReLU
   int transposed;            // 1: out_f32[c_off + col * ldc + row] (row-contiguous columns), fp32 only
   int n_valid;               // transposed mode: only columns < n_valid are stored
+  // optional fused GroupNorm statistics of the stored fp32 values (se3et_gemm_bf16_gnstats):
+  double* gn_stats = nullptr; // [nseg, groups, 2] {sum, sum of squares}, zeroed by the host before the launch
+  const int64_t* gn_seg_off = nullptr; // [nseg + 1] point offsets of the pairs
+  int gn_nseg = 0;
+  int gn_cpg = 1;                // channels per group: a power of two <= 32, or a multiple of 32
+  int gn_groups = 0;
+  int gn_rpp = 1;                // rows per point (6 for equivariant features)
 };
 
 struct GemmShape {
@@ -45,8 +52,70 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = kGemmStages * kStageBytes;
-  static constexpr int kTotal = kBarOffset + 128 + 1024;  // + barriers + alignment slack
+  static constexpr int kGnOffset = kBarOffset + 128;      // 4 epilogue warps x 64 groups x {sum, sumsq} floats
+  static constexpr int kTotal = kGnOffset + 4 * 64 * 2 * 4 + 1024;  // + barriers + GN scratch + alignment slack
 };
+
+
+// Sums N per-lane values across the 32 lanes of a warp with N/2 + N/4 + ... shuffles (each exchange halves the
+// number of values a lane still carries).  Afterwards lane l (with the low 5 - log2(N) bits clear) holds the
+// total of value index l >> (5 - log2(N)) in v[0].
+template <int N>
+__device__ __forceinline__ void warp_multi_reduce(float (&v)[N], int lane) {
+  static_assert(N >= 1 && N <= 32 && (N & (N - 1)) == 0, "N must be a power of two");
+  int off = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1, off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = upper ? v[i] : v[i + n / 2];
+      const float keep = upper ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+}
+
+// GroupNorm partial sums of one epilogue chunk: `vals` = the thread's 32 (or kCols) consecutive columns of its row.
+// kGroups = groups inside the chunk (kCols / cpg, or 1 when cpg >= kCols).
+template <int kCols, int kGroups>
+__device__ __forceinline__ void gn_chunk_partials(const float (&vals)[kCols], bool row_ok, bool uniform, int lane,
+                                                   float* warp_acc /* smem [64][2] of this warp */, int group0_local,
+                                                   double* stats_row /* global, this row's pair, or null */,
+                                                   int group0_global) {
+  constexpr int kPer = kCols / kGroups;
+  float s[kGroups], ss[kGroups];
+#pragma unroll
+  for (int g = 0; g < kGroups; ++g) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const float x = vals[g * kPer + j];
+      a += x;
+      b += x * x;
+    }
+    s[g] = row_ok ? a : 0.f;
+    ss[g] = row_ok ? b : 0.f;
+  }
+  if (uniform) {
+    warp_multi_reduce<kGroups>(s, lane);
+    warp_multi_reduce<kGroups>(ss, lane);
+    constexpr int kShift = kGroups == 32 ? 0 : kGroups == 16 ? 1 : kGroups == 8 ? 2 : kGroups == 4 ? 3 : kGroups == 2 ? 4 : 5;
+    if ((lane & ((1 << kShift) - 1)) == 0) {
+      const int g = lane >> kShift;
+      warp_acc[2 * (group0_local + g)] += s[0];
+      warp_acc[2 * (group0_local + g) + 1] += ss[0];
+    }
+  } else if (row_ok && stats_row) {
+    // tile straddles a pair boundary (one tile per boundary): every row adds straight to its own pair
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+      atomicAdd(stats_row + 2 * (group0_global + g), (double)s[g]);
+      atomicAdd(stats_row + 2 * (group0_global + g) + 1, (double)ss[g]);
+    }
+  }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -135,6 +204,23 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     tc::tcgen05_fence_after_sync();
     const bool row_ok = row < m_rows;
     const int64_t c_off = c_base + (int64_t)row * ldc + n0;
+    // fused GroupNorm statistics: per-warp accumulators in smem, one set of fp64 atomics per tile
+    float* gn_acc = reinterpret_cast<float*>(smem + S::kGnOffset);
+    float* warp_acc = gn_acc + (warp & 3) * 128;
+    bool gn_uniform = false;
+    int gn_seg = 0;
+    double* gn_row_stats = nullptr;
+    if (ep.gn_stats) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) warp_acc[lane * 4 + i] = 0.f;
+      const int last = min(m0 + kGemmBM, m_rows) - 1;
+      gn_seg = segment_of(ep.gn_seg_off, ep.gn_nseg, m0 / ep.gn_rpp);
+      gn_uniform = segment_of(ep.gn_seg_off, ep.gn_nseg, last / ep.gn_rpp) == gn_seg;
+      if (!gn_uniform && row_ok)
+        gn_row_stats = ep.gn_stats +
+                       (int64_t)segment_of(ep.gn_seg_off, ep.gn_nseg, row / ep.gn_rpp) * ep.gn_groups * 2;
+      __syncwarp();
+    }
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
@@ -153,6 +239,18 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         if (ep.bias) x += __ldg(ep.bias + n0 + c0 + j);
         if (ep.act == 1) x = fmaxf(x, 0.f);
         v[j] = x;
+      }
+      if (ep.gn_stats) {
+        const int cpg = ep.gn_cpg;
+        const int g_glob = (n0 + c0) / cpg, g_loc = g_glob - n0 / cpg;
+#define SE3ET_GN_CASE(G) gn_chunk_partials<kCols, (G)>(v, row_ok, gn_uniform, lane, warp_acc, g_loc, gn_row_stats, g_glob)
+        if (cpg >= kCols) SE3ET_GN_CASE(1);
+        else if (cpg * 2 == kCols) SE3ET_GN_CASE(2);
+        else if (cpg * 4 == kCols) SE3ET_GN_CASE(4);
+        else if (cpg * 8 == kCols) SE3ET_GN_CASE(8);
+        else if (cpg * 16 == kCols) SE3ET_GN_CASE(16);
+        else if (kCols == 32) SE3ET_GN_CASE(kCols == 32 ? 32 : 1);
+#undef SE3ET_GN_CASE
       }
       if (row_ok && ep.transposed) {
 #pragma unroll
@@ -179,6 +277,17 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             u.w = *reinterpret_cast<uint32_t*>(&p3);
             dst[j] = u;
           }
+        }
+      }
+    }
+    if (ep.gn_stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+      if (gn_uniform) {
+        const int e = (warp & 3) * 32 + lane;
+        const int ngr2 = 2 * ((n0 + BN - 1) / ep.gn_cpg - n0 / ep.gn_cpg + 1);
+        for (int i = e; i < ngr2; i += 128) {
+          const float t = gn_acc[i] + gn_acc[128 + i] + gn_acc[256 + i] + gn_acc[384 + i];
+          atomicAdd(ep.gn_stats + ((int64_t)gn_seg * ep.gn_groups + n0 / ep.gn_cpg) * 2 + i, (double)t);
         }
       }
     }
@@ -322,4 +431,41 @@ extern "C" int se3et_gemm_bf16(const void* a, int64_t lda, const void* b, int64_
   if (batch > 65535) return SE3ET_ERR_UNSUPPORTED;
   return gemm_bf16(static_cast<const __nv_bfloat16*>(a), lda, static_cast<const __nv_bfloat16*>(b), ldb, (int)m, (int)n,
                    (int)k, (int)batch, a_batch_rows, b_batch_rows, nullptr, 0, 0, ep, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int se3et_gemm_bf16_gnstats(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int64_t n,
+                                       int64_t k, const float* bias, float* out_f32, int64_t ldc, double* stats,
+                                       const int64_t* seg_offsets, int64_t nseg, int64_t groups,
+                                       int64_t rows_per_point, se3et_stream_t stream) {
+  if (m < 0 || n <= 0 || k <= 0 || m > INT32_MAX || n > INT32_MAX || k > INT32_MAX) return SE3ET_ERR_ARG;
+  if (!out_f32 || !stats || !seg_offsets || nseg <= 0 || groups <= 0 || n % groups || rows_per_point <= 0)
+    return SE3ET_ERR_ARG;
+  const int bn = pick_bn((int)n);
+  if (!bn) return SE3ET_ERR_UNSUPPORTED;
+  const int64_t cpg = n / groups;
+  const int chunk = bn >= 32 ? 32 : bn;
+  const bool pow2 = (cpg & (cpg - 1)) == 0;
+  // the epilogue reduces groups inside 32-column chunks: cpg | chunk, or chunk | cpg; <= 64 groups per tile
+  if (!((pow2 && cpg <= chunk) || cpg % chunk == 0) || bn / cpg > 64) return SE3ET_ERR_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SE3ET_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * nseg * groups, st));
+  if (m == 0) return SE3ET_OK;
+  GemmEpilogue ep;
+  ep.out_f32 = out_f32;
+  ep.out_bf16 = nullptr;
+  ep.bias = bias;
+  ep.ldc = ldc;
+  ep.c_batch_stride = 0;
+  ep.alpha = 1.f;
+  ep.act = 0;
+  ep.transposed = 0;
+  ep.n_valid = (int)n;
+  ep.gn_stats = stats;
+  ep.gn_seg_off = seg_offsets;
+  ep.gn_nseg = (int)nseg;
+  ep.gn_cpg = (int)cpg;
+  ep.gn_groups = (int)groups;
+  ep.gn_rpp = (int)rows_per_point;
+  return gemm_bf16(static_cast<const __nv_bfloat16*>(a), lda, static_cast<const __nv_bfloat16*>(b), ldb, (int)m, (int)n,
+                   (int)k, 1, 0, 0, nullptr, 0, 0, ep, st);
 }

@@ -17,7 +17,7 @@ from torch.nn.parameter import Parameter
 
 from .. import _lib
 from ..ops import e2pn_ops as K
-from ..ops.gemm import linear_bf16
+from ..ops.gemm import linear_bf16, linear_gn_stats
 from . import octahedral
 
 
@@ -56,14 +56,17 @@ class GroupNormEPN(nn.Module):
         self.num_channels = num_channels
         self.norm = nn.GroupNorm(self.num_groups, self.num_channels)
 
-    def fused(self, y, seg, rows_per_point, slope, out_f32=False, out_bf16=True, other=None, resid=None):
-        """y: fp32 (rows, C) pre-norm. other = (y_b, GroupNormEPN_b) adds a second normalised operand."""
-        stats = K.groupnorm_stats(y, self.num_groups, seg, rows_per_point)
+    def fused(self, y, seg, rows_per_point, slope, out_f32=False, out_bf16=True, other=None, resid=None, stats=None):
+        """y: fp32 (rows, C) pre-norm (stats: its statistics when the producing GEMM already accumulated them).
+        other = (y_b, GroupNormEPN_b, stats_b or None) adds a second normalised operand."""
+        if stats is None:
+            stats = K.groupnorm_stats(y, self.num_groups, seg, rows_per_point)
         kw = {}
         if other is not None:
-            yb, nb = other
-            kw = dict(yb=yb, stats_b=K.groupnorm_stats(yb, nb.num_groups, seg, rows_per_point),
-                      gamma_b=nb.norm.weight, beta_b=nb.norm.bias)
+            yb, nb, sb = other
+            if sb is None:
+                sb = K.groupnorm_stats(yb, nb.num_groups, seg, rows_per_point)
+            kw = dict(yb=yb, stats_b=sb, gamma_b=nb.norm.weight, beta_b=nb.norm.bias)
         return K.groupnorm_apply(y, stats, self.norm.weight, self.norm.bias, self.num_groups, seg, rows_per_point,
                                  slope=slope, resid=resid, out_f32=out_f32, out_bf16=out_bf16, eps=self.norm.eps, **kw)
 
@@ -141,6 +144,13 @@ class KPConvInterSO3(nn.Module):
         y, _ = linear_bf16(a, self._w_flat())
         return y.view(-1, self.kanchor, self.out_channels)
 
+    def forward_stats(self, q_pts, s_pts, neighb_inds, x, groups, seg):
+        """forward() plus the per-pair GroupNorm statistics of its output (accumulated in the GEMM epilogue)."""
+        self._check_tables()
+        a = K.kpconv_gather(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), self.kernel_points,
+                            self.KP_extent)
+        return linear_gn_stats(a, self._w_flat(), None, groups, seg, self.kanchor)
+
     def __repr__(self):
         return 'KPConvInterSO3(radius: {:.2f}, extent: {:.2f}, in_feat: {:d}, out_feat: {:d})'.format(
             self.radius, self.KP_extent, self.in_channels, self.out_channels)
@@ -158,16 +168,17 @@ class UnaryBlockEPN(nn.Module):
         self.leaky_relu = nn.LeakyReLU(0.1)
         self._w_cache = _Bf16Cache()
 
-    def pre_norm(self, x):
-        """fp32 (N*A, Cout) Linear output."""
+    def pre_norm(self, x, seg, rows_per_point):
+        """fp32 (N*A, Cout) Linear output and its per-pair GroupNorm statistics."""
         x2 = _act(x).reshape(-1, self.in_dim)
-        y, _ = linear_bf16(x2, self._w_cache.get(self.mlp.weight), self.mlp.bias)
-        return y
+        return linear_gn_stats(x2, self._w_cache.get(self.mlp.weight), self.mlp.bias, self.norm.num_groups, seg,
+                               rows_per_point)
 
     def forward(self, x, batch=None, seg=None):
         n, a = x.shape[0], x.shape[1]
-        y = self.pre_norm(x)
-        _, out = self.norm.fused(y, _seg(seg, n, x.device), a, slope=1.0 if self.no_relu else 0.1)
+        seg = _seg(seg, n, x.device)
+        y, stats = self.pre_norm(x, seg, a)
+        _, out = self.norm.fused(y, seg, a, slope=1.0 if self.no_relu else 0.1, stats=stats)
         return out.view(n, a, self.out_dim)
 
 
@@ -203,8 +214,9 @@ class KPConvInterSO3Block(nn.Module):
         self.leaky_relu = nn.LeakyReLU(0.1)
 
     def fused(self, x, q_pts, s_pts, neighb_inds, seg, out_f32):
-        y = self.conv(q_pts, s_pts, neighb_inds, x).view(-1, self.out_dim)
-        return self.norm.fused(y, seg, self.conv.kanchor, slope=0.1, out_f32=out_f32, out_bf16=not out_f32)
+        y, stats = self.conv.forward_stats(q_pts, s_pts, neighb_inds, x, self.norm.num_groups, seg)
+        return self.norm.fused(y, seg, self.conv.kanchor, slope=0.1, out_f32=out_f32, out_bf16=not out_f32,
+                               stats=stats)
 
     def forward(self, x, q_pts, s_pts, neighb_inds, seg=None):
         _, out = self.fused(x, q_pts, s_pts, neighb_inds, _seg(seg, q_pts.shape[0], q_pts.device), False)
@@ -269,14 +281,15 @@ class ResnetBottleneckBlockEPN(nn.Module):
             y = x
         f, _ = self.interso3.fused(y, q_pts, s_pts, neighb_inds, seg, out_f32=True)
         _, y = self.norm.fused(f, seg, 6, slope=0.1)
-        pre2 = self.unary2.pre_norm(y.view(nq, 6, -1))
+        pre2, st2 = self.unary2.pre_norm(y.view(nq, 6, -1), seg, 6)
         if 'strided' in self.block_name:
             skip = K.maxpool_nbr(skip, neighb_inds.contiguous(), seg if sub_width is not None else None, sub_width)
         if isinstance(self.skip_conv, UnaryBlockEPN):
-            pre_s = self.skip_conv.pre_norm(skip)
-            _, out = self.unary2.norm.fused(pre2, seg, 6, slope=0.1, other=(pre_s, self.skip_conv.norm))
+            pre_s, st_s = self.skip_conv.pre_norm(skip, seg, 6)
+            _, out = self.unary2.norm.fused(pre2, seg, 6, slope=0.1, other=(pre_s, self.skip_conv.norm, st_s),
+                                            stats=st2)
         else:
-            _, out = self.unary2.norm.fused(pre2, seg, 6, slope=0.1, resid=skip.contiguous())
+            _, out = self.unary2.norm.fused(pre2, seg, 6, slope=0.1, resid=skip.contiguous(), stats=st2)
         return out.view(nq, 6, self.out_dim)
 
 
@@ -334,9 +347,9 @@ class UnaryBlock(nn.Module):
         self._w_cache = _Bf16Cache()
 
     def forward(self, x, seg=None):
-        y, _ = linear_bf16(_act(x).contiguous(), self._w_cache.get(self.mlp.weight), self.mlp.bias)
         seg = _seg(seg, x.shape[0], x.device)
-        stats = K.groupnorm_stats(y, self.norm.num_groups, seg, 1)
+        y, stats = linear_gn_stats(_act(x).contiguous(), self._w_cache.get(self.mlp.weight), self.mlp.bias,
+                                   self.norm.num_groups, seg, 1)
         _, out = K.groupnorm_apply(y, stats, self.norm.norm.weight, self.norm.norm.bias, self.norm.num_groups, seg, 1,
                                    slope=0.1 if self.leaky_relu is not None else 1.0, eps=self.norm.norm.eps)
         return out

@@ -77,3 +77,38 @@ def bmm_bf16(a, b, alpha=1.0, out_f32=True, out_bf16=False):
         _lib.i64(m), _lib.i64(n), _lib.ptr(None), _lib.f32(alpha), 0, _lib.ptr(of), _lib.ptr(ob), _lib.i64(n),
         _lib.i64(m * n), _lib.stream_ptr()), "gemm_bf16")
     return of, ob
+
+
+def _gn_fusable(n, groups):
+    """Mirrors the check in se3et_gemm_bf16_gnstats (csrc/gemm.cu)."""
+    bn = next((b for b in (256, 128, 64, 32, 16) if n % b == 0), 0)
+    if not bn or n % groups:
+        return False
+    cpg, chunk = n // groups, min(bn, 32)
+    return ((cpg & (cpg - 1)) == 0 and cpg <= chunk or cpg % chunk == 0) and bn // cpg <= 64
+
+
+def linear_gn_stats(a, w, bias, groups, seg_off, rows_per_point):
+    """fp32 y = a @ w.T (+ bias) together with the GroupNorm statistics of y (double (nseg, groups, 2)), accumulated
+    in the GEMM epilogue.  Falls back to the separate statistics kernel for channel/group shapes the epilogue does
+    not cover (still the CUDA path)."""
+    from . import e2pn_ops
+    m, k = a.shape
+    n = w.shape[0]
+    if not _gn_fusable(n, groups) or m == 0:
+        y, _ = linear_bf16(a, w, bias)
+        return y, e2pn_ops.groupnorm_stats(y, groups, seg_off, rows_per_point)
+    _lib.require_cuda(a, w, bias, seg_off)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.shape[1] == w.shape[1]
+    assert a.stride(1) == 1 and w.stride(1) == 1 and seg_off.dtype == torch.int64
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == n
+    nseg = seg_off.numel() - 1
+    y = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    stats = torch.empty((nseg, groups, 2), dtype=torch.float64, device=a.device)
+    _lib.check(_lib.lib().se3et_gemm_bf16_gnstats(
+        _lib.ptr(a), _lib.i64(a.stride(0) if m > 1 else k), _lib.ptr(w), _lib.i64(w.stride(0) if n > 1 else k),
+        _lib.i64(m), _lib.i64(n), _lib.i64(k), _lib.ptr(bias), _lib.ptr(y), _lib.i64(n), _lib.ptr(stats),
+        _lib.ptr(seg_off), _lib.i64(nseg), _lib.i64(groups), _lib.i64(rows_per_point), _lib.stream_ptr()),
+        "gemm_bf16_gnstats")
+    return y, stats

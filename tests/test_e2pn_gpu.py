@@ -58,7 +58,7 @@ def test_tables_match_kernel_and_reference(gold):
     assert tuple(conv.kidx_rot.shape) == (15, 6, 6) and tuple(conv.ridx_rot.shape) == (15, 6, 6)
 
 
-@pytest.mark.parametrize("cin,cout", [(8, 16), (1, 16), (32, 32), (64, 128)])
+@pytest.mark.parametrize("cin,cout", [(8, 16), (1, 16), (16, 32), (32, 32), (64, 128), (128, 64)])
 def test_kpconv_matches_oracle(pyramid, cin, cout):
     t = oe.octahedral_tables()
     p1 = torch.from_numpy(pyramid["points"][1])
@@ -106,6 +106,66 @@ def test_groupnorm_pairs_do_not_mix():
     of, ob = K.groupnorm_apply(yd, stats, gamma.to(DEV), beta.to(DEV), G, seg, 6, slope=0.1, out_f32=True)
     assert torch.allclose(of.cpu().view_as(want), want, rtol=1e-4, atol=1e-4)
     assert torch.allclose(ob.float().cpu().view_as(want), want, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("n_out,groups,k", [(32, 32, 64), (64, 32, 40), (128, 32, 96), (256, 32, 128), (512, 32, 64),
+                                             (1024, 32, 64), (16, 4, 24), (48, 16, 32), (64, 4, 32)])
+def test_gemm_epilogue_statistics_match_separate_pass(n_out, groups, k):
+    """se3et_gemm_bf16_gnstats: the per-pair GroupNorm sums accumulated in the tcgen05 epilogue equal the ones the
+    stand-alone statistics kernel computes from the stored fp32 output (pairs end inside GEMM tiles on purpose;
+    one pair is empty)."""
+    from se3et_b200.ops.gemm import linear_bf16, linear_gn_stats
+    g = torch.Generator().manual_seed(n_out + k)
+    pts = [211, 0, 390, 64, 5]  # points per pair; x6 rows each -> boundaries at rows 1266, 3606, 3990 (not /128)
+    seg = torch.tensor(np.concatenate([[0], np.cumsum(pts)]), dtype=torch.int64, device=DEV)
+    rows = 6 * sum(pts)
+    a = (torch.randn(rows, k, generator=g) + 0.3).to(torch.bfloat16).to(DEV)
+    w = (torch.randn(n_out, k, generator=g) / k ** 0.5).to(torch.bfloat16).to(DEV)
+    bias = torch.randn(n_out, generator=g).to(DEV)
+    y, stats = linear_gn_stats(a, w, bias, groups, seg, 6)
+    y_ref, _ = linear_bf16(a, w, bias)
+    assert torch.equal(y, y_ref)
+    want = K.groupnorm_stats(y_ref, groups, seg, 6)
+    assert torch.allclose(stats, want, rtol=1e-5, atol=1e-3)
+    yd = y.double().view(sum(pts), 6, groups, n_out // groups)
+    for i in (0, 2, 4):
+        blk = yd[int(seg[i]):int(seg[i + 1])]
+        assert torch.allclose(stats[i, :, 0], blk.sum(dim=(0, 1, 3)), rtol=1e-5, atol=1e-3)
+        assert torch.allclose(stats[i, :, 1], (blk * blk).sum(dim=(0, 1, 3)), rtol=1e-5, atol=1e-3)
+    assert float(stats[1].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("c,G,rpp", [(32, 32, 6), (128, 32, 6), (1024, 32, 6), (256, 32, 1), (48, 16, 6), (2048, 32, 6)])
+def test_groupnorm_apply_two_operands_and_residual(c, G, rpp):
+    """act(GN_a(ya) + GN_b(yb)) and act(GN_a(ya) + resid) against torch, several pairs of different sizes."""
+    g = torch.Generator().manual_seed(c + rpp)
+    pts = [37, 101, 0, 64]
+    seg = torch.tensor(np.concatenate([[0], np.cumsum(pts)]), dtype=torch.int64, device=DEV)
+    rows = rpp * sum(pts)
+    ya = torch.randn(rows, c, generator=g) * 1.7 + 0.4
+    yb = torch.randn(rows, c, generator=g) * 0.6 - 1.0
+    resid = torch.randn(rows, c, generator=g).to(torch.bfloat16)
+    ga, ba, gb, bb = (torch.randn(c, generator=g) for _ in range(4))
+
+    def ref_norm(y, gamma, beta):
+        out = []
+        for i in range(len(pts)):
+            blk = y[rpp * int(seg[i]):rpp * int(seg[i + 1])]
+            if blk.numel():
+                out.append(oe.group_norm_epn(blk.view(-1, rpp, c), G, gamma, beta).reshape(-1, c))
+        return torch.cat(out)
+
+    yad, ybd = ya.to(DEV), yb.to(DEV)
+    sa, sb = K.groupnorm_stats(yad, G, seg, rpp), K.groupnorm_stats(ybd, G, seg, rpp)
+    of, _ = K.groupnorm_apply(yad, sa, ga.to(DEV), ba.to(DEV), G, seg, rpp, slope=0.1, yb=ybd, stats_b=sb,
+                              gamma_b=gb.to(DEV), beta_b=bb.to(DEV), out_f32=True, out_bf16=False)
+    want = torch.nn.functional.leaky_relu(ref_norm(ya, ga, ba) + ref_norm(yb, gb, bb), 0.1)
+    assert torch.allclose(of.cpu(), want, rtol=1e-4, atol=2e-4)
+    of, ob = K.groupnorm_apply(yad, sa, ga.to(DEV), ba.to(DEV), G, seg, rpp, slope=1.0, resid=resid.to(DEV),
+                               out_f32=True, out_bf16=True)
+    want = ref_norm(ya, ga, ba) + resid.float()
+    assert torch.allclose(of.cpu(), want, rtol=1e-4, atol=2e-4)
+    assert torch.allclose(ob.float().cpu(), want, rtol=1e-2, atol=2e-2)
 
 
 def test_pooling_ops_match_oracle(pyramid):
