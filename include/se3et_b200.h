@@ -149,6 +149,26 @@ int se3et_kpconv_gather(const float* q_pts, const float* s_pts, const int64_t* n
                         int64_t h, const void* x_bf16, int64_t cin, const float* kernel_points_15x3, float kp_extent,
                         void* out_bf16, int64_t kpad, se3et_stream_t stream);
 
+/* kpconv_fused -- the whole KPConvInterSO3.forward (blocks_epn.py:454-546, 334-390) in one kernel:
+ *   out[(p, r)][d] = sum_{k, a, c} ( sum_n w[p][n][k] x[idx[p][n]][a][c] ) * W[kidx[k][r]][ridx[a][r]][c][d]
+ * The gathered operand is built per 16-point tile in shared memory (mma.sync on the 16-row basis of the
+ * octahedral index tables) and contracted by tcgen05 tensor cores with fp32 accumulation in TMEM; it never
+ * touches global memory.
+ *   x_bf16  [ns, 6, cin] bf16;  out_f32 [nq * 6, cout] fp32 (pre-norm, as KPConvInterSO3 returns it)
+ *   w_bf16  [cout, 36 * cin] bf16, K-major, K index = (chunk * 36 + kc * 6 + a') * 16 + c for input channel
+ *           chunk * 16 + c of weights[kc][a'][.][d]  (se3et_b200/modules/e2pn.py:KPConvInterSO3._w_fused)
+ *   stats   optional double [nseg, groups, 2]: GroupNorm sums of the output per pair (zeroed by the call)
+ * Requires cin % 16 == 0, cout % 16 == 0, h <= 48 (h <= 40 when cout % 128 == 0); otherwise
+ * SE3ET_ERR_UNSUPPORTED and the host uses se3et_kpconv_gather + se3et_gemm_bf16(_gnstats). */
+int se3et_kpconv_fused(const float* q_pts, const float* s_pts, const int64_t* neighbors, int64_t nq, int64_t ns,
+                       int64_t h, const void* x_bf16, int64_t cin, const void* w_bf16, int64_t cout,
+                       const float* kernel_points_15x3, float kp_extent, float* out_f32, double* stats,
+                       const int64_t* seg_offsets, int64_t nseg, int64_t groups, se3et_stream_t stream);
+
+/* Diagnostics: {registers, static smem bytes, max threads per block, local bytes, max dynamic smem} of the fused
+ * kernel instantiation for output tile width bn (16, 32, 64 or 128). */
+int se3et_kpconv_fused_attrs(int bn, int* out5);
+
 /* GroupNormEPN / kpconv GroupNorm (blocks_epn.py:684-701, kpconv/modules.py:33-50): statistics per
  * (segment, group) over rows_per_point * points * channels_per_group values.  stats: double [nseg, groups, 2]. */
 int se3et_groupnorm_stats(const float* y, int64_t rows, int64_t channels, int64_t groups, const int64_t* seg_offsets,

@@ -1,0 +1,465 @@
+// Fused KPConvInterSO3.forward (blocks_epn.py:454-546 with feat_gather_by_perm :334-390): neighbour gather, kernel
+// point influence, rotate-by-permute and the (kernel points x anchors x Cin) -> Cout contraction in ONE kernel; the
+// gathered operand A' (kpconv_tables.cuh) lives only in shared memory.
+//
+// Persistent CTA, tile = 16 query points = 96 operand rows (p, r) of a UMMA M = 128 tile:
+//   warps 0-7  producers, 2 points each.  Per point: the 16 x H basis weight matrix W16 (bf16 A fragments kept in
+//              registers for the whole tile).  Per (point, 16-channel chunk, input anchor): cp.async gather of the
+//              neighbour rows x[idx[n]][a][chunk] (32 B sectors, 4-stage ring per warp), mma.sync m16n8k16
+//              W16 . X, and every accumulator element is stored once (twice .. six times for its (r, kc) copies) as
+//              bf16 into the 128-byte-swizzled K-major operand tile the tensor core reads.
+//   warp 8     tcgen05.mma issuer: per chunk 9 K-blocks of 64 (36 (kc, a') slots x 16 channels) against the weight
+//              K-blocks, fp32 accumulation in TMEM across all chunks of the tile.
+//   warp 9     TMA producer of the weight K-blocks (3-stage mbarrier ring).
+//   warps 0-3  epilogue after their production: tcgen05.ld, fp32 rows to global memory, GroupNorm statistics.
+// The operand tile is single-buffered (9 x 12 KB): the MMA of chunk i and the production of chunk i + 1 alternate,
+// while gathers and the next tile's weights run ahead.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "gn_epilogue.cuh"
+#include "kpconv_mma.cuh"
+#include "tc.cuh"
+
+namespace se3et {
+
+using namespace kpm;
+
+constexpr int kFPts = 16;                     // points per tile
+constexpr int kFRows = kFPts * kA;            // 96 operand rows
+constexpr int kFProdWarps = 8;                // 2 points each
+constexpr int kFThreads = (kFProdWarps + 2) * 32;
+constexpr int kFKBlocks = 9;                  // 36 slots x 16 channels = 576 = 9 x 64
+constexpr int kFKBlockBytes = kFRows * 128;   // 12288, a multiple of the 1024-byte swizzle period
+constexpr int kFStages = 4;                   // gather ring per warp, item = (point, chunk, anchor)
+constexpr int kFXRow = 48;                    // bytes per gathered row: 16 channels bf16 + 16 pad (conflict-free ldmatrix)
+constexpr int kFWStages = 3;
+constexpr int kFKS = 3;                       // neighbour k-steps of 16 (H <= 48)
+constexpr int kFW16Row = (kFKS * 16 + 8) * 2; // 112 bytes
+
+__constant__ int8_t c_f_basis_target[16][6] = {
+#define SE3ET_BT(row) {(int8_t)basis_target(row, 0), (int8_t)basis_target(row, 1), (int8_t)basis_target(row, 2), \
+                       (int8_t)basis_target(row, 3), (int8_t)basis_target(row, 4), (int8_t)basis_target(row, 5)}
+    SE3ET_BT(0), SE3ET_BT(1), SE3ET_BT(2), SE3ET_BT(3), SE3ET_BT(4), SE3ET_BT(5), SE3ET_BT(6), SE3ET_BT(7),
+    SE3ET_BT(8), SE3ET_BT(9), SE3ET_BT(10), SE3ET_BT(11), SE3ET_BT(12), SE3ET_BT(13), SE3ET_BT(14), SE3ET_BT(15)
+#undef SE3ET_BT
+};
+__constant__ uint32_t c_f_ridx_cols[6] = {ridx_col_packed(0), ridx_col_packed(1), ridx_col_packed(2),
+                                          ridx_col_packed(3), ridx_col_packed(4), ridx_col_packed(5)};
+
+struct FusedArgs {
+  const float* q_pts;
+  const float* s_pts;
+  const int64_t* idx;
+  const __nv_bfloat16* x;
+  const float* kernel_points;
+  float* out;                 // fp32 [nq * 6, cout]
+  int64_t nq, ns;
+  int H, HR;                  // neighbour columns, rounded up to 8
+  int cin, cout;
+  float inv_extent;
+  // GroupNorm statistics of the output (optional)
+  double* gn_stats;
+  const int64_t* gn_seg_off;
+  int gn_nseg, gn_cpg, gn_groups;
+};
+
+template <int BN>
+struct FusedSmem {
+  static constexpr int kAOff = 0;
+  static constexpr int kABytes = kFKBlocks * kFKBlockBytes;          // 110592
+  static constexpr int kWOff = kAOff + kABytes;                       // the last K-block's unused rows 96..127 alias
+  static constexpr int kWStage = (BN * 128 + 1023) / 1024 * 1024;     // the first 4 KB of this region (never read back)
+  static constexpr int kWBytes = kFWStages * kWStage < 4096 ? 4096 : kFWStages * kWStage;
+  static constexpr int kBarOff = kWOff + kWBytes;                     // 10 mbarriers + tmem pointer
+  static constexpr int kZeroOff = kBarOff + 128;                      // 16 zero bytes
+  static constexpr int kGnOff = kZeroOff + 16;                        // 4 warps x 128 floats
+  static constexpr int kXOff = kGnOff + 4 * 128 * 4;                  // gather rings
+  static int total(int hr) { return kXOff + kFProdWarps * kFStages * hr * kFXRow + 1024; }
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kFThreads, 1)
+kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
+  using S = FusedSmem<BN>;
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a_tile = smem + S::kAOff;
+  uint8_t* w_tile = smem + S::kWOff;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
+  uint64_t* a_empty = a_full + 1;
+  uint64_t* w_full = a_full + 2;
+  uint64_t* w_empty = w_full + kFWStages;
+  uint64_t* tmem_full = w_empty + kFWStages;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  uint8_t* zero16 = smem + S::kZeroOff;
+  float* gn_acc = reinterpret_cast<float*>(smem + S::kGnOff);
+  __shared__ float sh_kp[48];
+  __shared__ int8_t sh_target[16][6];
+  __shared__ uint32_t sh_ridx[6];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * BN;
+  const int64_t ntiles = (args.nq + kFPts - 1) / kFPts;
+  const int nchunks = args.cin / kChunk;
+  const int xstage = args.HR * kFXRow;
+
+  if (threadIdx.x < 45) sh_kp[threadIdx.x] = args.kernel_points[threadIdx.x];
+  if (threadIdx.x < 96) sh_target[threadIdx.x / 6][threadIdx.x % 6] = c_f_basis_target[threadIdx.x / 6][threadIdx.x % 6];
+  if (threadIdx.x < 6) sh_ridx[threadIdx.x] = c_f_ridx_cols[threadIdx.x];
+  if (threadIdx.x < 4) reinterpret_cast<uint32_t*>(zero16)[threadIdx.x] = 0u;
+  if (threadIdx.x == 0) {
+    tc::tma_prefetch_desc(&tma_w);
+    tc::mbar_init(a_full, kFProdWarps);
+    tc::mbar_init(a_empty, 1);
+    for (int s = 0; s < kFWStages; ++s) {
+      tc::mbar_init(&w_full[s], 1);
+      tc::mbar_init(&w_empty[s], 1);
+    }
+    tc::mbar_init(tmem_full, 1);
+    tc::mbar_init(tmem_empty, 4);
+    tc::mbar_fence_init();
+  }
+  if (warp < kFProdWarps) {
+    // gather rows H..HR-1 are never written: zero the whole ring once
+    uint8_t* xs = smem + S::kXOff + warp * kFStages * xstage;
+    for (int i = lane; i < kFStages * xstage / 16; i += 32) reinterpret_cast<uint4*>(xs)[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (warp == kFProdWarps) tc::tmem_alloc<kTmemCols>(tmem_ptr);
+  tc::tcgen05_fence_before_sync();
+  __syncthreads();
+  tc::tcgen05_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp < kFProdWarps) {
+    // =========================================== producers ===================================================
+    uint8_t* xs = smem + S::kXOff + warp * kFStages * xstage;
+    const LaneTargets T = make_lane_targets(lane, sh_target, sh_ridx);
+    const int q = lane & 3;
+    const int row_elems = kA * args.cin;
+    const int H = args.H, HR = args.HR;
+    // ldmatrix row of this lane inside a k-step and its 16-byte half
+    const int ld_row = (lane & 7) + ((lane >> 3) & 1) * 8, ld_half = lane >> 4;
+    uint32_t gc = 0;       // chunks produced so far (all tiles): parity of the operand-tile barriers
+    uint32_t titer = 0;    // tiles done by this CTA
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++titer) {
+      // ---- per-tile setup: neighbours and basis weights of my two points ------------------------------------
+      int jreg[2][2];
+      uint32_t afrag[2][kFKS][4];
+#pragma unroll
+      for (int pt = 0; pt < 2; ++pt) {
+        const int64_t p = tile * kFPts + 2 * warp + pt;
+        const bool pvalid = p < args.nq;
+        const int64_t pc = pvalid ? p : 0;
+        const float qx = args.q_pts[3 * pc], qy = args.q_pts[3 * pc + 1], qz = args.q_pts[3 * pc + 2];
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int n = it * 32 + lane;
+          int64_t j = (pvalid && n < H) ? args.idx[pc * H + n] : -1;
+          const bool valid = j >= 0 && j < args.ns;
+          if (!valid) j = 0;
+          jreg[pt][it] = valid ? (int)j : -1;
+          if (n < kFKS * 16) {
+            float row[16];
+            basis_weights(args.s_pts[3 * j] - qx, args.s_pts[3 * j + 1] - qy, args.s_pts[3 * j + 2] - qz, sh_kp,
+                          args.inv_extent, valid, row);
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+              *reinterpret_cast<__nv_bfloat16*>(xs + r * kFW16Row + n * 2) = __float2bfloat16(row[r]);
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int ks = 0; ks < kFKS; ++ks)
+          ldmatrix_x4(afrag[pt][ks], smem_addr(xs + ld_row * kFW16Row + (ks * 16 + ld_half * 8) * 2));
+        __syncwarp();
+      }
+      // the W16 scratch aliased gather stage 0 (rows >= H must read as zero again)
+      for (int i = lane; i < 16 * kFW16Row / 16; i += 32) reinterpret_cast<uint4*>(xs)[i] = make_uint4(0, 0, 0, 0);
+      __syncwarp();
+
+      // ---- gather ring ---------------------------------------------------------------------------------------
+      auto issue = [&](int chunk, int pt, int a, int stage) {
+        uint8_t* dst = xs + stage * xstage;
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          const int i = lane + 32 * u;  // piece: neighbour n = i / 2, 16-byte half i % 2
+          const int n = i >> 1;
+          const int jn = __shfl_sync(0xffffffffu, u < 2 ? jreg[pt][0] : jreg[pt][1], n & 31);
+          if (n < H) {
+            const __nv_bfloat16* src = args.x + ((int64_t)(jn < 0 ? 0 : jn) * kA + a) * args.cin + chunk * kChunk +
+                                       (i & 1) * 8;
+            cp_async_16(smem_addr(dst + n * kFXRow + (i & 1) * 16), src, jn < 0 ? 0 : 16);
+          }
+        }
+      };
+      // items of a chunk: e = pt * 6 + a; the ring runs 3 items ahead
+#pragma unroll
+      for (int e = 0; e < 3; ++e) {
+        issue(0, e / 6, e % 6, e % kFStages);
+        cp_async_commit();
+      }
+      for (int chunk = 0; chunk < nchunks; ++chunk) {
+#pragma unroll
+        for (int e = 0; e < 12; ++e) {
+          const int pt = e / 6, a = e % 6;
+          {  // prefetch item e + 3 (possibly of the next chunk)
+            const int e2 = (e + 3) % 12;
+            const int chunk2 = chunk + (e + 3) / 12;
+            if (chunk2 < nchunks) issue(chunk2, e2 / 6, e2 % 6, (e + 3) % kFStages);
+            cp_async_commit();
+          }
+          cp_async_wait<3>();
+          __syncwarp();
+          if (e == 0) {
+            tc::mbar_wait(a_empty, (gc & 1) ^ 1);  // the MMA of the previous chunk has consumed the operand tile
+          }
+          const uint8_t* xsb = xs + (e % kFStages) * xstage;
+          float d[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+          for (int ks = 0; ks < kFKS; ++ks) {
+            const int n = ks * 16 + ld_row;
+            uint32_t b[4];
+            ldmatrix_x4_trans(b, n < HR ? smem_addr(xsb + n * kFXRow + ld_half * 16) : smem_addr(zero16));
+            mma_16816(d[0], afrag[pt][ks], b[0], b[1]);
+            mma_16816(d[1], afrag[pt][ks], b[2], b[3]);
+          }
+          // accumulator rows g / g + 8 = basis rows; each is copied to its (r, kc) targets:
+          // operand row m = (2 warp + pt) * 6 + r, slot j = kc * 6 + ridx[a][r], K-block j / 4, 16-byte chunk
+          // (j % 4) * 2 + nt, swizzled by (m % 8)
+          const int mbase = (2 * warp + pt) * kA;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+              const uint32_t ap = (T.ridx[h][t] >> (3 * a)) & 7u;
+              const uint32_t j = T.kc[h][t] * kA + ap;
+              const uint32_t m = mbase + T.r[h][t];
+              uint8_t* rowp = a_tile + (j >> 2) * kFKBlockBytes + m * 128 + q * 4;
+              const uint32_t c0 = (j & 3) * 2;
+              *reinterpret_cast<uint32_t*>(rowp + (((c0) ^ (m & 7)) << 4)) = pack2(d[0][2 * h], d[0][2 * h + 1]);
+              *reinterpret_cast<uint32_t*>(rowp + (((c0 + 1) ^ (m & 7)) << 4)) = pack2(d[1][2 * h], d[1][2 * h + 1]);
+            }
+          }
+          if (T.centre) {
+#pragma unroll
+            for (int r = 2; r < kA; ++r) {
+              const uint32_t j = 5 * kA + ridx_tab(a, r);
+              const uint32_t m = mbase + r;
+              uint8_t* rowp = a_tile + (j >> 2) * kFKBlockBytes + m * 128 + q * 4;
+              const uint32_t c0 = (j & 3) * 2;
+              *reinterpret_cast<uint32_t*>(rowp + (((c0) ^ (m & 7)) << 4)) = pack2(d[0][2], d[0][3]);
+              *reinterpret_cast<uint32_t*>(rowp + (((c0 + 1) ^ (m & 7)) << 4)) = pack2(d[1][2], d[1][3]);
+            }
+          }
+          __syncwarp();  // every lane is done with this ring stage and its stores are issued
+          if (e == 11) {
+            tc::fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(a_full);
+            ++gc;
+          }
+        }
+      }
+      cp_async_wait<0>();
+      __syncwarp();
+
+      // ---- epilogue (warps 0-3 own TMEM lanes 32 w .. 32 w + 31 = operand rows) ------------------------------
+      if (warp < 4) {
+        tc::mbar_wait(tmem_full, titer & 1);
+        tc::tcgen05_fence_after_sync();
+        const int m = warp * 32 + lane;
+        const int64_t grow = tile * kFRows + m;
+        const bool row_ok = m < kFRows && grow < args.nq * kA;
+        float* warp_acc = gn_acc + warp * 128;
+        bool gn_uniform = false;
+        int gn_seg = 0;
+        double* gn_row_stats = nullptr;
+        if (args.gn_stats) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) warp_acc[lane * 4 + i] = 0.f;
+          const int64_t p_first = tile * kFPts;
+          const int64_t p_last = min(p_first + kFPts, args.nq) - 1;
+          gn_seg = segment_of(args.gn_seg_off, args.gn_nseg, p_first);
+          gn_uniform = segment_of(args.gn_seg_off, args.gn_nseg, p_last) == gn_seg;
+          if (!gn_uniform && row_ok)
+            gn_row_stats = args.gn_stats +
+                           (int64_t)segment_of(args.gn_seg_off, args.gn_nseg, grow / kA) * args.gn_groups * 2;
+          __syncwarp();
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t rr[32];
+          tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(BN >= 32 ? c0 : 0), rr);
+          tc::tmem_ld_wait();
+          constexpr int kCols = BN >= 32 ? 32 : BN;
+          float v[kCols];
+#pragma unroll
+          for (int jj = 0; jj < kCols; ++jj) v[jj] = __uint_as_float(rr[jj]);
+          if (args.gn_stats) {
+            const int cpg = args.gn_cpg;
+            const int g_glob = (n0 + c0) / cpg, g_loc = g_glob - n0 / cpg;
+            gn_accumulate_chunk<kCols>(cpg, v, row_ok, gn_uniform, lane, warp_acc, g_loc, gn_row_stats, g_glob);
+          }
+          if (row_ok) {
+            float4* dst = reinterpret_cast<float4*>(args.out + grow * args.cout + n0 + c0);
+#pragma unroll
+            for (int jj = 0; jj < kCols / 4; ++jj)
+              dst[jj] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+          }
+        }
+        tc::tcgen05_fence_before_sync();
+        if (args.gn_stats) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (gn_uniform) {
+            const int e = warp * 32 + lane;
+            const int ngr2 = 2 * ((n0 + BN - 1) / args.gn_cpg - n0 / args.gn_cpg + 1);
+            for (int i = e; i < ngr2; i += 128) {
+              const float t = gn_acc[i] + gn_acc[128 + i] + gn_acc[256 + i] + gn_acc[384 + i];
+              atomicAdd(args.gn_stats + ((int64_t)gn_seg * args.gn_groups + n0 / args.gn_cpg) * 2 + i, (double)t);
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");  // accumulators are re-zeroed by the next tile
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tmem_empty);
+      }
+    }
+  } else if (warp == kFProdWarps) {
+    // =========================================== MMA issuer ==================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::umma_idesc_bf16(128, BN);
+      uint32_t gc = 0, wkb = 0, titer = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++titer) {
+        tc::mbar_wait(tmem_empty, (titer & 1) ^ 1);  // the epilogue has drained the previous tile's accumulators
+        tc::tcgen05_fence_after_sync();
+        for (int chunk = 0; chunk < nchunks; ++chunk, ++gc) {
+          tc::mbar_wait(a_full, gc & 1);
+          tc::tcgen05_fence_after_sync();
+          for (int kb = 0; kb < kFKBlocks; ++kb, ++wkb) {
+            const int s = wkb % kFWStages;
+            tc::mbar_wait(&w_full[s], (wkb / kFWStages) & 1);
+            tc::tcgen05_fence_after_sync();
+            const uint64_t a_desc = tc::umma_desc_sw128(tc::smem_u32(a_tile + kb * kFKBlockBytes));
+            const uint64_t b_desc = tc::umma_desc_sw128(tc::smem_u32(w_tile + s * S::kWStage));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc::umma_bf16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                            (chunk | kb | k) != 0);
+            tc::umma_commit(&w_empty[s]);
+          }
+          tc::umma_commit(a_empty);
+        }
+        tc::umma_commit(tmem_full);
+      }
+    }
+  } else {
+    // =========================================== weight TMA ==================================================
+    if (lane == 0) {
+      uint32_t wkb = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int chunk = 0; chunk < nchunks; ++chunk) {
+          for (int kb = 0; kb < kFKBlocks; ++kb, ++wkb) {
+            const int s = wkb % kFWStages;
+            tc::mbar_wait(&w_empty[s], ((wkb / kFWStages) & 1) ^ 1);
+            tc::mbar_arrive_expect_tx(&w_full[s], BN * 128);
+            tc::tma_load_2d(w_tile + s * S::kWStage, &tma_w, &w_full[s], (chunk * kFKBlocks + kb) * 64, n0);
+          }
+        }
+      }
+    }
+  }
+  tc::tcgen05_fence_before_sync();
+  __syncthreads();
+  if (warp == kFProdWarps) tc::tmem_dealloc<kTmemCols>(tmem_base);
+}
+
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);  // gemm.cu
+
+template <int BN>
+static int launch_fused(const CUtensorMap& tw, const FusedArgs& args, cudaStream_t st) {
+  using S = FusedSmem<BN>;
+  const int smem = S::total(args.HR);
+  if (smem > 227 * 1024) return SE3ET_ERR_UNSUPPORTED;
+  static int configured = 0;
+  if (configured < smem) {
+    SE3ET_CUDA_CHECK(cudaFuncSetAttribute(kpconv_fused_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  const int64_t ntiles = ceil_div(args.nq, kFPts);
+  dim3 grid((unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs), (unsigned)(args.cout / BN));
+  kpconv_fused_kernel<BN><<<grid, kFThreads, smem, st>>>(tw, args);
+  SE3ET_LAUNCH_CHECK();
+  return SE3ET_OK;
+}
+
+}  // namespace se3et
+
+using namespace se3et;
+
+extern "C" int se3et_kpconv_fused(const float* q_pts, const float* s_pts, const int64_t* neighbors, int64_t nq,
+                                  int64_t ns, int64_t h, const void* x_bf16, int64_t cin, const void* w_bf16,
+                                  int64_t cout, const float* kernel_points_15x3, float kp_extent, float* out_f32,
+                                  double* stats, const int64_t* seg_offsets, int64_t nseg, int64_t groups,
+                                  se3et_stream_t stream) {
+  if (nq < 0 || ns <= 0 || h <= 0 || cin <= 0 || cout <= 0 || !(kp_extent > 0.f)) return SE3ET_ERR_ARG;
+  if (h > kFKS * 16 || cin % kChunk != 0 || cout % 16 != 0) return SE3ET_ERR_UNSUPPORTED;
+  int bn = 0;
+  for (int c : {128, 64, 32, 16})
+    if (cout % c == 0) { bn = c; break; }
+  if (!q_pts || !s_pts || !neighbors || !x_bf16 || !w_bf16 || !kernel_points_15x3 || !out_f32) return SE3ET_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  FusedArgs a;
+  a.q_pts = q_pts; a.s_pts = s_pts; a.idx = neighbors; a.x = static_cast<const __nv_bfloat16*>(x_bf16);
+  a.kernel_points = kernel_points_15x3; a.out = out_f32; a.nq = nq; a.ns = ns; a.H = (int)h;
+  a.HR = ((int)h + 7) / 8 * 8;
+  if (a.HR < 16) a.HR = 16;  // the per-warp ring doubles as the W16 scratch (16 x 112 bytes)
+  a.cin = (int)cin; a.cout = (int)cout; a.inv_extent = 1.f / kp_extent;
+  a.gn_stats = nullptr; a.gn_seg_off = nullptr; a.gn_nseg = 0; a.gn_cpg = 1; a.gn_groups = 0;
+  if (stats) {
+    if (!seg_offsets || nseg <= 0 || groups <= 0 || cout % groups) return SE3ET_ERR_ARG;
+    const int64_t cpg = cout / groups;
+    const int chunk = bn >= 32 ? 32 : bn;
+    const bool pow2 = (cpg & (cpg - 1)) == 0;
+    if (!((pow2 && cpg <= chunk) || cpg % chunk == 0) || bn / cpg > 64) return SE3ET_ERR_UNSUPPORTED;
+    SE3ET_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * nseg * groups, st));
+    a.gn_stats = stats; a.gn_seg_off = seg_offsets; a.gn_nseg = (int)nseg; a.gn_cpg = (int)cpg; a.gn_groups = (int)groups;
+  }
+  if (nq == 0) return SE3ET_OK;
+  CUtensorMap tw;
+  int rc = make_tmap_bf16_2d(&tw, w_bf16, cout, 36 * cin, 36 * cin, bn);
+  if (rc) return rc;
+  switch (bn) {
+    case 128: return launch_fused<128>(tw, a, st);
+    case 64: return launch_fused<64>(tw, a, st);
+    case 32: return launch_fused<32>(tw, a, st);
+    default: return launch_fused<16>(tw, a, st);
+  }
+}
+
+// Diagnostics: attributes of the fused kernel instantiation for tile width bn (registers, static smem, max threads).
+extern "C" int se3et_kpconv_fused_attrs(int bn, int* out5) {
+  cudaFuncAttributes at;
+  cudaError_t e;
+  switch (bn) {
+    case 128: e = cudaFuncGetAttributes(&at, kpconv_fused_kernel<128>); break;
+    case 64: e = cudaFuncGetAttributes(&at, kpconv_fused_kernel<64>); break;
+    case 32: e = cudaFuncGetAttributes(&at, kpconv_fused_kernel<32>); break;
+    default: e = cudaFuncGetAttributes(&at, kpconv_fused_kernel<16>); break;
+  }
+  if (e != cudaSuccess) { set_last_error("cudaFuncGetAttributes", e); return SE3ET_ERR_CUDA; }
+  out5[0] = at.numRegs; out5[1] = (int)at.sharedSizeBytes; out5[2] = at.maxThreadsPerBlock;
+  out5[3] = (int)at.localSizeBytes; out5[4] = at.maxDynamicSharedSizeBytes;
+  if (bn == 32) {  // occupancy probe for the common configuration (HR = 40)
+    const int smem = FusedSmem<32>::total(40);
+    cudaFuncSetAttribute(kpconv_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int nb = -1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kpconv_fused_kernel<32>, kFThreads, smem);
+    out5[3] = nb;
+    out5[4] = smem;
+    if (e != cudaSuccess) { set_last_error("occupancy", e); return SE3ET_ERR_CUDA; }
+  }
+  return SE3ET_OK;
+}

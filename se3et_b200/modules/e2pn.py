@@ -21,6 +21,19 @@ from ..ops.gemm import linear_bf16, linear_gn_stats
 from . import octahedral
 
 
+# switches for A/B measurements and tests (the defaults are the product path)
+_GFLAGS = {'fused_kpconv': True}
+
+
+def _gn_fusable_fused(cout, groups):
+    """GroupNorm shapes the fused KPConv epilogue covers (same rule as the GEMM epilogue, tile width <= 128)."""
+    if cout % groups:
+        return False
+    bn = next(b for b in (128, 64, 32, 16) if cout % b == 0)
+    cpg, chunk = cout // groups, min(bn, 32)
+    return ((cpg & (cpg - 1)) == 0 and cpg <= chunk or cpg % chunk == 0) and bn // cpg <= 64
+
+
 def _act(x):
     return x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
 
@@ -112,6 +125,7 @@ class KPConvInterSO3(nn.Module):
                                  requires_grad=True)
         self.reset_parameters()
         self._w_cache = _Bf16Cache()
+        self._wf_cache = _Bf16Cache()
         self._tables_checked = False
 
     def reset_parameters(self):
@@ -136,9 +150,24 @@ class KPConvInterSO3(nn.Module):
             return flat
         return self._w_cache.get(self.weights, tr)
 
+    def _w_fused(self):
+        """(Cout, 36*Cin) bf16 for the fused kernel: K index = (chunk*36 + kc*6 + a')*16 + c, input channel chunk*16+c."""
+        def tr(w):
+            cin, cout = self.in_channels, self.out_channels
+            return w.reshape(36, cin // 16, 16, cout).permute(3, 1, 0, 2).reshape(cout, 36 * cin)
+        return self._wf_cache.get(self.weights, tr)
+
+    def _fused_ok(self, neighb_inds):
+        return _GFLAGS['fused_kpconv'] and neighb_inds.shape[0] > 0 and K.kpconv_fused_supported(
+            self.in_channels, self.out_channels, neighb_inds.shape[1])
+
     def forward(self, q_pts, s_pts, neighb_inds, x):
         """-> fp32 (Nq, A, Cout), pre-norm (blocks_epn.py:454-546)."""
         self._check_tables()
+        if self._fused_ok(neighb_inds):
+            y, _ = K.kpconv_fused(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), self._w_fused(),
+                                  self.kernel_points, self.KP_extent)
+            return y.view(-1, self.kanchor, self.out_channels)
         a = K.kpconv_gather(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), self.kernel_points,
                             self.KP_extent)
         y, _ = linear_bf16(a, self._w_flat())
@@ -147,6 +176,9 @@ class KPConvInterSO3(nn.Module):
     def forward_stats(self, q_pts, s_pts, neighb_inds, x, groups, seg):
         """forward() plus the per-pair GroupNorm statistics of its output (accumulated in the GEMM epilogue)."""
         self._check_tables()
+        if self._fused_ok(neighb_inds) and _gn_fusable_fused(self.out_channels, groups):
+            return K.kpconv_fused(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), self._w_fused(),
+                                  self.kernel_points, self.KP_extent, gn=(groups, seg))
         a = K.kpconv_gather(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), self.kernel_points,
                             self.KP_extent)
         return linear_gn_stats(a, self._w_flat(), None, groups, seg, self.kanchor)

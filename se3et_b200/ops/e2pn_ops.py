@@ -114,3 +114,39 @@ def upsample_concat(x_bf16, up_idx, y_bf16):
         _lib.ptr(x_bf16), _lib.i64(x_bf16.shape[0]), _lib.i64(c1), _lib.ptr(up_idx), _lib.i64(up_idx.stride(0)),
         _lib.ptr(y_bf16), _lib.i64(c2), _lib.i64(n), _lib.ptr(out), _lib.stream_ptr()), "upsample_concat")
     return out
+
+
+def kpconv_fused_supported(cin, cout, h):
+    """Shapes the fused kernel covers (mirrors se3et_kpconv_fused in csrc/kpconv_fused.cu)."""
+    if cin % 16 or cout % 16 or h > 48:
+        return False
+    return h <= 40 or cout % 128 != 0
+
+
+def kpconv_fused(q_pts, s_pts, neighbors, x_bf16, w_fused, kernel_points, kp_extent, gn=None):
+    """KPConvInterSO3.forward in one kernel. x (Ns, 6, Cin) bf16, w_fused (Cout, 36*Cin) bf16 in the fused K order.
+    gn = (groups, seg_off) additionally returns the per-pair GroupNorm statistics (double (nseg, groups, 2)).
+    -> (fp32 (Nq*6, Cout), stats or None)."""
+    _lib.require_cuda(q_pts, s_pts, neighbors, x_bf16, w_fused, kernel_points)
+    assert x_bf16.dtype == torch.bfloat16 and x_bf16.is_contiguous() and x_bf16.dim() == 3 and x_bf16.shape[1] == 6
+    assert w_fused.dtype == torch.bfloat16 and w_fused.is_contiguous()
+    assert neighbors.dtype == torch.int64 and neighbors.is_contiguous()
+    assert q_pts.dtype == torch.float32 and s_pts.dtype == torch.float32 and q_pts.is_contiguous() and s_pts.is_contiguous()
+    assert kernel_points.dtype == torch.float32 and kernel_points.is_contiguous() and kernel_points.shape == (15, 3)
+    nq, h = neighbors.shape
+    ns, _, cin = x_bf16.shape
+    cout = w_fused.shape[0]
+    assert w_fused.shape[1] == 36 * cin and s_pts.shape[0] == ns and q_pts.shape[0] == nq
+    out = torch.empty((nq * 6, cout), dtype=torch.float32, device=x_bf16.device)
+    stats, seg_off, groups, nseg = None, None, 0, 0
+    if gn is not None:
+        groups, seg_off = gn
+        assert seg_off.dtype == torch.int64
+        nseg = seg_off.numel() - 1
+        stats = torch.empty((nseg, groups, 2), dtype=torch.float64, device=x_bf16.device)
+    _lib.check(_lib.lib().se3et_kpconv_fused(
+        _lib.ptr(q_pts), _lib.ptr(s_pts), _lib.ptr(neighbors), _lib.i64(nq), _lib.i64(ns), _lib.i64(h),
+        _lib.ptr(x_bf16), _lib.i64(cin), _lib.ptr(w_fused), _lib.i64(cout), _lib.ptr(kernel_points),
+        _lib.f32(kp_extent), _lib.ptr(out), _lib.ptr(stats), _lib.ptr(seg_off), _lib.i64(nseg), _lib.i64(groups),
+        _lib.stream_ptr()), "kpconv_fused")
+    return out, stats

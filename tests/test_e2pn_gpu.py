@@ -81,6 +81,40 @@ def test_kpconv_matches_oracle(pyramid, cin, cout):
         assert rel_err(got, want) < 5e-3
 
 
+@pytest.mark.parametrize("cin,cout,G", [(16, 16, 16), (32, 32, 32), (32, 64, 16), (64, 128, 32), (128, 256, 32),
+                                        (48, 80, 5)])
+def test_fused_kpconv_equals_gather_plus_gemm(pyramid, cin, cout, G):
+    """The one-kernel KPConv (operand tile in shared memory, tcgen05 contraction, GroupNorm statistics in the
+    epilogue) against the two-kernel path (global operand + GEMM) on the same inputs: level-0 self convolution
+    (more tiles than SMs, ragged last tile) and the strided level-0 -> level-1 one, two pairs for the statistics."""
+    p0 = torch.from_numpy(pyramid["points"][0]).to(DEV)
+    p1 = torch.from_numpy(pyramid["points"][1]).to(DEV)
+    for q, s, nb in ((p0, p0, pyramid["neighbors"][0]), (p1, p0, pyramid["subsampling"][0])):
+        nb = torch.from_numpy(nb).to(DEV)
+        conv = M.KPConvInterSO3(15, 6, cin, cout, 0.05, 0.0625, non_sep_conv=True, rot_by_permute=True,
+                                quotient_factor=4)
+        with torch.no_grad():
+            conv.weights.copy_(helpers.seeded_tensor("conv.weights", (6, 6, cin, cout)))
+        conv = conv.to(DEV)
+        x = helpers.seeded_tensor("conv.input", (s.shape[0], 6, cin)).to(DEV)
+        nq = q.shape[0]
+        seg = torch.tensor([0, nq // 3 + 5, nq], dtype=torch.int64, device=DEV)
+        assert conv._fused_ok(nb)
+        y_f, st_f = conv.forward_stats(q, s, nb, x, G, seg)
+        M._GFLAGS['fused_kpconv'] = False
+        try:
+            y_u, st_u = conv.forward_stats(q, s, nb, x, G, seg)
+        finally:
+            M._GFLAGS['fused_kpconv'] = True
+        # both round the influence weights and the gathered operand to bf16; they differ only in accumulation order
+        assert rel_err(y_f, y_u) < 2e-3, rel_err(y_f, y_u)
+        assert torch.allclose(y_f, y_u, rtol=2e-2, atol=2e-3 * y_u.abs().max().item())
+        want = K.groupnorm_stats(y_f, G, seg, 6)
+        assert torch.allclose(st_f, want, rtol=1e-5, atol=1e-3)
+        y_plain = conv(q, s, nb, x).reshape(-1, cout)
+        assert torch.equal(y_plain, y_f)
+
+
 def test_kpconv_matches_reference_fixture(gold, pyramid):
     p1 = torch.from_numpy(pyramid["points"][1]).to(DEV)
     nb1 = torch.from_numpy(pyramid["neighbors"][1]).to(DEV)
@@ -244,6 +278,7 @@ def test_backbone_batched_pairs_equal_single_pairs(gold, pyramid):
         na = a.shape[0]
         assert o.shape[0] == na + b.shape[0]
         ea, eb = rel_err(o[:na], a), rel_err(o[na:], b)
-        # GroupNorm statistics are accumulated in fp64, so they do not depend on how rows are split over CTAs;
-        # what is left is fp64 summation-order noise (1e-16) that can flip a bf16 rounding once in a blue moon
-        assert ea < 2e-3 and eb < 2e-3, (lvl, ea, eb)
+        # GroupNorm statistics are accumulated per GEMM tile (fp32 partials, fp64 across tiles): the second pair's
+        # rows fall into differently aligned tiles when it is stacked behind another pair, so its statistics differ
+        # at the 1e-7 level and a few bf16 roundings flip and propagate through the layers
+        assert ea < 1e-2 and eb < 1e-2, (lvl, ea, eb)
