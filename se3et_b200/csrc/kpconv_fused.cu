@@ -33,7 +33,7 @@ constexpr int kFKBlocks = 9;                  // 36 slots x 16 channels = 576 = 
 constexpr int kFKBlockBytes = kFRows * 128;   // 12288, a multiple of the 1024-byte swizzle period
 constexpr int kFStages = 4;                   // gather ring per warp, item = (point, chunk, anchor)
 constexpr int kFXRow = 48;                    // bytes per gathered row: 16 channels bf16 + 16 pad (conflict-free ldmatrix)
-constexpr int kFWStages = 3;
+constexpr int kFWMaxStages = 18;             // weight K-block ring: as many stages as fit (two chunks at most)
 constexpr int kFKS = 3;                       // neighbour k-steps of 16 (H <= 48)
 constexpr int kFW16Row = (kFKS * 16 + 8) * 2; // 112 bytes
 
@@ -57,6 +57,7 @@ struct FusedArgs {
   int64_t nq, ns;
   int H, HR;                  // neighbour columns, rounded up to 8
   int cin, cout;
+  int wstages;                // weight ring stages (<= kFWMaxStages)
   float inv_extent;
   // GroupNorm statistics of the output (optional)
   double* gn_stats;
@@ -67,15 +68,20 @@ struct FusedArgs {
 template <int BN>
 struct FusedSmem {
   static constexpr int kAOff = 0;
-  static constexpr int kABytes = kFKBlocks * kFKBlockBytes;          // 110592
-  static constexpr int kWOff = kAOff + kABytes;                       // the last K-block's unused rows 96..127 alias
-  static constexpr int kWStage = (BN * 128 + 1023) / 1024 * 1024;     // the first 4 KB of this region (never read back)
-  static constexpr int kWBytes = kFWStages * kWStage < 4096 ? 4096 : kFWStages * kWStage;
-  static constexpr int kBarOff = kWOff + kWBytes;                     // 10 mbarriers + tmem pointer
-  static constexpr int kZeroOff = kBarOff + 128;                      // 16 zero bytes
+  static constexpr int kABytes = kFKBlocks * kFKBlockBytes;          // 110592; the last K-block's unused rows
+                                                                      // 96..127 alias the first 4 KB after it
+  static constexpr int kBarOff = kAOff + kABytes + 4096;              // mbarriers + tmem pointer (512 B)
+  static constexpr int kZeroOff = kBarOff + 512;                      // 16 zero bytes
   static constexpr int kGnOff = kZeroOff + 16;                        // 4 warps x 128 floats
-  static constexpr int kXOff = kGnOff + 4 * 128 * 4;                  // gather rings
-  static int total(int hr) { return kXOff + kFProdWarps * kFStages * hr * kFXRow + 1024; }
+  static constexpr int kXOff = kGnOff + 4 * 128 * 4;                  // gather rings [warps][stages][HR][48]
+  static constexpr int kWStage = (BN * 128 + 1023) / 1024 * 1024;
+  __host__ __device__ static int x_bytes(int hr) { return kFProdWarps * kFStages * hr * kFXRow; }
+  __host__ __device__ static int w_off(int hr) { return (kXOff + x_bytes(hr) + 1023) / 1024 * 1024; }
+  static int total(int hr, int wstages) { return w_off(hr) + wstages * kWStage + 1024; }
+  static int max_wstages(int hr) {
+    const int n = (227 * 1024 - 1024 - w_off(hr)) / kWStage;
+    return n > kFWMaxStages ? kFWMaxStages : n;
+  }
 };
 
 template <int BN>
@@ -86,14 +92,15 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_tile = smem + S::kAOff;
-  uint8_t* w_tile = smem + S::kWOff;
+  uint8_t* w_tile = smem + S::w_off(args.HR);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
   uint64_t* a_empty = a_full + 1;
-  uint64_t* w_full = a_full + 2;
-  uint64_t* w_empty = w_full + kFWStages;
-  uint64_t* tmem_full = w_empty + kFWStages;
-  uint64_t* tmem_empty = tmem_full + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  uint64_t* tmem_full = a_full + 2;
+  uint64_t* tmem_empty = a_full + 3;
+  uint64_t* w_full = a_full + 4;
+  uint64_t* w_empty = w_full + kFWMaxStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_empty + kFWMaxStages);
+  const int wstages = args.wstages;
   uint8_t* zero16 = smem + S::kZeroOff;
   float* gn_acc = reinterpret_cast<float*>(smem + S::kGnOff);
   __shared__ float sh_kp[48];
@@ -114,7 +121,7 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
     tc::tma_prefetch_desc(&tma_w);
     tc::mbar_init(a_full, kFProdWarps);
     tc::mbar_init(a_empty, 1);
-    for (int s = 0; s < kFWStages; ++s) {
+    for (int s = 0; s < wstages; ++s) {
       tc::mbar_init(&w_full[s], 1);
       tc::mbar_init(&w_empty[s], 1);
     }
@@ -136,71 +143,109 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
   if (warp < kFProdWarps) {
     // =========================================== producers ===================================================
     uint8_t* xs = smem + S::kXOff + warp * kFStages * xstage;
+    const uint32_t xs_s = smem_addr(xs);
+    const uint32_t a_tile_s = smem_addr(a_tile);
+    const uint32_t zero_s = smem_addr(zero16);
     const LaneTargets T = make_lane_targets(lane, sh_target, sh_ridx);
     const int q = lane & 3;
-    const int row_elems = kA * args.cin;
     const int H = args.H, HR = args.HR;
+    const int cin = args.cin;
     // ldmatrix row of this lane inside a k-step and its 16-byte half
     const int ld_row = (lane & 7) + ((lane >> 3) & 1) * 8, ld_half = lane >> 4;
-    uint32_t gc = 0;       // chunks produced so far (all tiles): parity of the operand-tile barriers
-    uint32_t titer = 0;    // tiles done by this CTA
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++titer) {
-      // ---- per-tile setup: neighbours and basis weights of my two points ------------------------------------
-      int jreg[2][2];
-      uint32_t afrag[2][kFKS][4];
+    // this lane's three gather pieces of an item: neighbour n = i / 2, 16-byte half i % 2, i = lane + 32 u
+    uint32_t gdst[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int i = lane + 32 * u;
+      gdst[u] = xs_s + (i >> 1) * kFXRow + (i & 1) * 16;
+    }
+    // per-tile state (registers): A fragments of the two points' basis weights, gather source pointers
+    uint32_t afrag[2][kFKS][4];
+    const __nv_bfloat16* gsrc[2][3];
+    uint32_t gvalid = 0;  // bit pt * 3 + u: the piece reads a real neighbour (else zero fill)
+
+    auto setup = [&](int64_t tile) {
+      float qp[2][3];
+      bool pvalid[2];
 #pragma unroll
       for (int pt = 0; pt < 2; ++pt) {
         const int64_t p = tile * kFPts + 2 * warp + pt;
-        const bool pvalid = p < args.nq;
-        const int64_t pc = pvalid ? p : 0;
-        const float qx = args.q_pts[3 * pc], qy = args.q_pts[3 * pc + 1], qz = args.q_pts[3 * pc + 2];
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
-          const int n = it * 32 + lane;
-          int64_t j = (pvalid && n < H) ? args.idx[pc * H + n] : -1;
-          const bool valid = j >= 0 && j < args.ns;
-          if (!valid) j = 0;
-          jreg[pt][it] = valid ? (int)j : -1;
-          if (n < kFKS * 16) {
-            float row[16];
-            basis_weights(args.s_pts[3 * j] - qx, args.s_pts[3 * j + 1] - qy, args.s_pts[3 * j + 2] - qz, sh_kp,
-                          args.inv_extent, valid, row);
-#pragma unroll
-            for (int r = 0; r < 16; ++r)
-              *reinterpret_cast<__nv_bfloat16*>(xs + r * kFW16Row + n * 2) = __float2bfloat16(row[r]);
-          }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int ks = 0; ks < kFKS; ++ks)
-          ldmatrix_x4(afrag[pt][ks], smem_addr(xs + ld_row * kFW16Row + (ks * 16 + ld_half * 8) * 2));
-        __syncwarp();
+        pvalid[pt] = p < args.nq;
+        const int64_t pc = pvalid[pt] ? p : 0;
+        qp[pt][0] = args.q_pts[3 * pc]; qp[pt][1] = args.q_pts[3 * pc + 1]; qp[pt][2] = args.q_pts[3 * pc + 2];
       }
-      // the W16 scratch aliased gather stage 0 (rows >= H must read as zero again)
-      for (int i = lane; i < 16 * kFW16Row / 16; i += 32) reinterpret_cast<uint4*>(xs)[i] = make_uint4(0, 0, 0, 0);
-      __syncwarp();
-
-      // ---- gather ring ---------------------------------------------------------------------------------------
-      auto issue = [&](int chunk, int pt, int a, int stage) {
-        uint8_t* dst = xs + stage * xstage;
+      gvalid = 0;
+#pragma unroll
+      for (int pt = 0; pt < 2; ++pt) {
+        const int64_t pc = pvalid[pt] ? tile * kFPts + 2 * warp + pt : 0;
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
-          const int i = lane + 32 * u;  // piece: neighbour n = i / 2, 16-byte half i % 2
-          const int n = i >> 1;
-          const int jn = __shfl_sync(0xffffffffu, u < 2 ? jreg[pt][0] : jreg[pt][1], n & 31);
-          if (n < H) {
-            const __nv_bfloat16* src = args.x + ((int64_t)(jn < 0 ? 0 : jn) * kA + a) * args.cin + chunk * kChunk +
-                                       (i & 1) * 8;
-            cp_async_16(smem_addr(dst + n * kFXRow + (i & 1) * 16), src, jn < 0 ? 0 : 16);
-          }
+          const int i = lane + 32 * u, n = i >> 1;
+          int64_t j = (pvalid[pt] && n < H) ? args.idx[pc * H + n] : -1;
+          const bool valid = j >= 0 && j < args.ns;
+          gsrc[pt][u] = args.x + (valid ? j : 0) * (int64_t)(kA * cin) + (i & 1) * 8;
+          gvalid |= (valid ? 1u : 0u) << (pt * 3 + u);
         }
-      };
-      // items of a chunk: e = pt * 6 + a; the ring runs 3 items ahead
+      }
+      // W16 scratch for both points aliases the head of the gather ring: [pt][16][kFW16Row]
+      for (int i = lane; i < 2 * 16 * kFW16Row / 16; i += 32) reinterpret_cast<uint4*>(xs)[i] = make_uint4(0, 0, 0, 0);
+      __syncwarp();
+      // the 2 H (point, neighbour) pairs spread over the lanes: slot i = lane + 32 it
+#pragma unroll
+      for (int it = 0; it < 3; ++it) {
+        const int i = lane + 32 * it;
+        const int pt = i >= H ? 1 : 0, n = i - pt * H;
+        const bool active = i < 2 * H && (pt ? pvalid[1] : pvalid[0]);
+        const int64_t pc = active ? tile * kFPts + 2 * warp + pt : 0;
+        int64_t j = active ? args.idx[pc * H + n] : -1;
+        const bool valid = j >= 0 && j < args.ns;
+        if (!valid) j = 0;
+        const float dx = args.s_pts[3 * j] - (pt ? qp[1][0] : qp[0][0]);
+        const float dy = args.s_pts[3 * j + 1] - (pt ? qp[1][1] : qp[0][1]);
+        const float dz = args.s_pts[3 * j + 2] - (pt ? qp[1][2] : qp[0][2]);
+        if (valid) {  // shadow / padding neighbours keep their zero weights
+          float row[16];
+          basis_weights(dx, dy, dz, sh_kp, args.inv_extent, true, row);
+          uint8_t* dst = xs + pt * 16 * kFW16Row + n * 2;
+#pragma unroll
+          for (int r = 0; r < 16; ++r) *reinterpret_cast<__nv_bfloat16*>(dst + r * kFW16Row) = __float2bfloat16(row[r]);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int pt = 0; pt < 2; ++pt)
+#pragma unroll
+        for (int ks = 0; ks < kFKS; ++ks)
+          ldmatrix_x4(afrag[pt][ks], xs_s + pt * 16 * kFW16Row + ld_row * kFW16Row + (ks * 16 + ld_half * 8) * 2);
+      __syncwarp();
+      // gather rows >= H must read as zero again
+      for (int i = lane; i < 2 * 16 * kFW16Row / 16; i += 32) reinterpret_cast<uint4*>(xs)[i] = make_uint4(0, 0, 0, 0);
+      __syncwarp();
+    };
+
+    auto issue = [&](int chunk, int pt, int a, int stage) {
+      const int off = a * cin + chunk * kChunk;
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        if (lane + 32 * u < 2 * H)
+          cp_async_16(gdst[u] + stage * xstage, gsrc[pt][u] + off, (gvalid >> (pt * 3 + u)) & 1u ? 16 : 0);
+      }
+    };
+    auto prologue = [&]() {
 #pragma unroll
       for (int e = 0; e < 3; ++e) {
         issue(0, e / 6, e % 6, e % kFStages);
         cp_async_commit();
       }
+    };
+
+    uint32_t gc = 0;       // chunks produced so far (all tiles): parity of the operand-tile barriers
+    uint32_t titer = 0;    // tiles done by this CTA
+    if ((int64_t)blockIdx.x < ntiles) {
+      setup(blockIdx.x);
+      prologue();
+    }
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++titer) {
       for (int chunk = 0; chunk < nchunks; ++chunk) {
 #pragma unroll
         for (int e = 0; e < 12; ++e) {
@@ -216,20 +261,20 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
           if (e == 0) {
             tc::mbar_wait(a_empty, (gc & 1) ^ 1);  // the MMA of the previous chunk has consumed the operand tile
           }
-          const uint8_t* xsb = xs + (e % kFStages) * xstage;
+          const uint32_t xsb = xs_s + (e % kFStages) * xstage;
           float d[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
           for (int ks = 0; ks < kFKS; ++ks) {
             const int n = ks * 16 + ld_row;
             uint32_t b[4];
-            ldmatrix_x4_trans(b, n < HR ? smem_addr(xsb + n * kFXRow + ld_half * 16) : smem_addr(zero16));
+            ldmatrix_x4_trans(b, n < HR ? xsb + n * kFXRow + ld_half * 16 : zero_s);
             mma_16816(d[0], afrag[pt][ks], b[0], b[1]);
             mma_16816(d[1], afrag[pt][ks], b[2], b[3]);
           }
           // accumulator rows g / g + 8 = basis rows; each is copied to its (r, kc) targets:
           // operand row m = (2 warp + pt) * 6 + r, slot j = kc * 6 + ridx[a][r], K-block j / 4, 16-byte chunk
           // (j % 4) * 2 + nt, swizzled by (m % 8)
-          const int mbase = (2 * warp + pt) * kA;
+          const uint32_t mbase = (2 * warp + pt) * kA;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -237,10 +282,10 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
               const uint32_t ap = (T.ridx[h][t] >> (3 * a)) & 7u;
               const uint32_t j = T.kc[h][t] * kA + ap;
               const uint32_t m = mbase + T.r[h][t];
-              uint8_t* rowp = a_tile + (j >> 2) * kFKBlockBytes + m * 128 + q * 4;
-              const uint32_t c0 = (j & 3) * 2;
-              *reinterpret_cast<uint32_t*>(rowp + (((c0) ^ (m & 7)) << 4)) = pack2(d[0][2 * h], d[0][2 * h + 1]);
-              *reinterpret_cast<uint32_t*>(rowp + (((c0 + 1) ^ (m & 7)) << 4)) = pack2(d[1][2 * h], d[1][2 * h + 1]);
+              const uint32_t addr = a_tile_s + (j >> 2) * kFKBlockBytes + m * 128 + q * 4 +
+                                    ((((j & 3) * 2) ^ (m & 7)) << 4);
+              st_shared_b32(addr, pack2(d[0][2 * h], d[0][2 * h + 1]));
+              st_shared_b32(addr ^ 16u, pack2(d[1][2 * h], d[1][2 * h + 1]));
             }
           }
           if (T.centre) {
@@ -248,10 +293,10 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
             for (int r = 2; r < kA; ++r) {
               const uint32_t j = 5 * kA + ridx_tab(a, r);
               const uint32_t m = mbase + r;
-              uint8_t* rowp = a_tile + (j >> 2) * kFKBlockBytes + m * 128 + q * 4;
-              const uint32_t c0 = (j & 3) * 2;
-              *reinterpret_cast<uint32_t*>(rowp + (((c0) ^ (m & 7)) << 4)) = pack2(d[0][2], d[0][3]);
-              *reinterpret_cast<uint32_t*>(rowp + (((c0 + 1) ^ (m & 7)) << 4)) = pack2(d[1][2], d[1][3]);
+              const uint32_t addr = a_tile_s + (j >> 2) * kFKBlockBytes + m * 128 + q * 4 +
+                                    ((((j & 3) * 2) ^ (m & 7)) << 4);
+              st_shared_b32(addr, pack2(d[0][2], d[0][3]));
+              st_shared_b32(addr ^ 16u, pack2(d[1][2], d[1][3]));
             }
           }
           __syncwarp();  // every lane is done with this ring stage and its stores are issued
@@ -265,6 +310,11 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
       }
       cp_async_wait<0>();
       __syncwarp();
+      // the next tile's weights and first gathers run under this tile's last MMA and epilogue
+      if (tile + gridDim.x < ntiles) {
+        setup(tile + gridDim.x);
+        prologue();
+      }
 
       // ---- epilogue (warps 0-3 own TMEM lanes 32 w .. 32 w + 31 = operand rows) ------------------------------
       if (warp < 4) {
@@ -331,24 +381,24 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
     // =========================================== MMA issuer ==================================================
     if (lane == 0) {
       constexpr uint32_t idesc = tc::umma_idesc_bf16(128, BN);
-      uint32_t gc = 0, wkb = 0, titer = 0;
+      uint32_t gc = 0, titer = 0, ws = 0, wphase = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++titer) {
         tc::mbar_wait(tmem_empty, (titer & 1) ^ 1);  // the epilogue has drained the previous tile's accumulators
         tc::tcgen05_fence_after_sync();
         for (int chunk = 0; chunk < nchunks; ++chunk, ++gc) {
           tc::mbar_wait(a_full, gc & 1);
           tc::tcgen05_fence_after_sync();
-          for (int kb = 0; kb < kFKBlocks; ++kb, ++wkb) {
-            const int s = wkb % kFWStages;
-            tc::mbar_wait(&w_full[s], (wkb / kFWStages) & 1);
+          for (int kb = 0; kb < kFKBlocks; ++kb) {
+            tc::mbar_wait(&w_full[ws], wphase);
             tc::tcgen05_fence_after_sync();
             const uint64_t a_desc = tc::umma_desc_sw128(tc::smem_u32(a_tile + kb * kFKBlockBytes));
-            const uint64_t b_desc = tc::umma_desc_sw128(tc::smem_u32(w_tile + s * S::kWStage));
+            const uint64_t b_desc = tc::umma_desc_sw128(tc::smem_u32(w_tile + ws * S::kWStage));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               tc::umma_bf16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
                             (chunk | kb | k) != 0);
-            tc::umma_commit(&w_empty[s]);
+            tc::umma_commit(&w_empty[ws]);
+            if (++ws == (uint32_t)wstages) { ws = 0; wphase ^= 1; }
           }
           tc::umma_commit(a_empty);
         }
@@ -358,14 +408,14 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
   } else {
     // =========================================== weight TMA ==================================================
     if (lane == 0) {
-      uint32_t wkb = 0;
+      uint32_t ws = 0, wphase = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int chunk = 0; chunk < nchunks; ++chunk) {
-          for (int kb = 0; kb < kFKBlocks; ++kb, ++wkb) {
-            const int s = wkb % kFWStages;
-            tc::mbar_wait(&w_empty[s], ((wkb / kFWStages) & 1) ^ 1);
-            tc::mbar_arrive_expect_tx(&w_full[s], BN * 128);
-            tc::tma_load_2d(w_tile + s * S::kWStage, &tma_w, &w_full[s], (chunk * kFKBlocks + kb) * 64, n0);
+          for (int kb = 0; kb < kFKBlocks; ++kb) {
+            tc::mbar_wait(&w_empty[ws], wphase ^ 1);
+            tc::mbar_arrive_expect_tx(&w_full[ws], BN * 128);
+            tc::tma_load_2d(w_tile + ws * S::kWStage, &tma_w, &w_full[ws], (chunk * kFKBlocks + kb) * 64, n0);
+            if (++ws == (uint32_t)wstages) { ws = 0; wphase ^= 1; }
           }
         }
       }
@@ -379,10 +429,11 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);  // gemm.cu
 
 template <int BN>
-static int launch_fused(const CUtensorMap& tw, const FusedArgs& args, cudaStream_t st) {
+static int launch_fused(const CUtensorMap& tw, FusedArgs args, cudaStream_t st) {
   using S = FusedSmem<BN>;
-  const int smem = S::total(args.HR);
-  if (smem > 227 * 1024) return SE3ET_ERR_UNSUPPORTED;
+  args.wstages = S::max_wstages(args.HR);
+  if (args.wstages < 2) return SE3ET_ERR_UNSUPPORTED;
+  const int smem = S::total(args.HR, args.wstages);
   static int configured = 0;
   if (configured < smem) {
     SE3ET_CUDA_CHECK(cudaFuncSetAttribute(kpconv_fused_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -453,7 +504,7 @@ extern "C" int se3et_kpconv_fused_attrs(int bn, int* out5) {
   out5[0] = at.numRegs; out5[1] = (int)at.sharedSizeBytes; out5[2] = at.maxThreadsPerBlock;
   out5[3] = (int)at.localSizeBytes; out5[4] = at.maxDynamicSharedSizeBytes;
   if (bn == 32) {  // occupancy probe for the common configuration (HR = 40)
-    const int smem = FusedSmem<32>::total(40);
+    const int smem = FusedSmem<32>::total(40, FusedSmem<32>::max_wstages(40));
     cudaFuncSetAttribute(kpconv_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int nb = -1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kpconv_fused_kernel<32>, kFThreads, smem);
