@@ -110,10 +110,23 @@ int se3et_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, int6
  * (row r belongs to point r / rows_per_point) and the channels of group g.  stats is zeroed by the call.
  * replaces: the Linear / KPConv contraction followed by the statistics pass of GroupNormEPN
  *   (blocks_epn.py:658-663, 697-701) without re-reading the activations.
- * Returns SE3ET_ERR_UNSUPPORTED when N / groups is neither a power of two <= 32 nor a multiple of 32
+ * out_f32 may be NULL (statistics only).
+ * Returns SE3ET_ERR_UNSUPPORTED when N / groups is neither a power of two <= 16 nor a multiple of 16
  * (the host then uses se3et_groupnorm_stats). */
 int se3et_gemm_bf16_gnstats(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int64_t n, int64_t k,
                             const float* bias, float* out_f32, int64_t ldc, double* stats,
+                            const int64_t* seg_offsets, int64_t nseg, int64_t groups, int64_t rows_per_point,
+                            se3et_stream_t stream);
+
+/* Second pass of a Linear + GroupNorm (+ residual) (+ LeakyReLU) block: recomputes the GEMM and applies
+ *   out_bf16 = LeakyReLU_slope( (A B^T + bias - mean) * rstd * gamma + beta [+ resid] )
+ * in the epilogue, mean / rstd per (pair, group) from `stats` (as produced by se3et_gemm_bf16_gnstats with
+ * out_f32 = NULL, which then only accumulates).  The pre-norm activations never reach global memory:
+ * UnaryBlockEPN and the residual tail of ResnetBottleneckBlockEPN (blocks_epn.py:639-665, 833-852).
+ * resid_bf16 (optional) has the output's shape and pitch.  slope = 1 disables the activation. */
+int se3et_gemm_bf16_gnapply(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int64_t n, int64_t k,
+                            const float* bias, const double* stats, const float* gamma, const float* beta, float eps,
+                            float leaky_slope, const void* resid_bf16, void* out_bf16, int64_t ldc,
                             const int64_t* seg_offsets, int64_t nseg, int64_t groups, int64_t rows_per_point,
                             se3et_stream_t stream);
 

@@ -18,8 +18,9 @@ namespace se3et {
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;  // 64 bf16 = 128 bytes = one swizzle atom
-constexpr int kGemmStages = 4;
+constexpr int kGemmMaxStages = 4;
 constexpr int kGemmThreads = 192;
+constexpr int kEpCols = 16;  // epilogue chunk: columns per tcgen05.ld
 
 struct GemmEpilogue {
   float* out_f32;            // nullable, [M, ldc]
@@ -31,13 +32,21 @@ struct GemmEpilogue {
   int act;                   // 0 none, 1 ReLU
   int transposed;            // 1: out_f32[c_off + col * ldc + row] (row-contiguous columns), fp32 only
   int n_valid;               // transposed mode: only columns < n_valid are stored
-  // optional fused GroupNorm statistics of the stored fp32 values (se3et_gemm_bf16_gnstats):
-  double* gn_stats = nullptr; // [nseg, groups, 2] {sum, sum of squares}, zeroed by the host before the launch
-  const int64_t* gn_seg_off = nullptr; // [nseg + 1] point offsets of the pairs
+  // GroupNorm over (pair, channel group); a row r belongs to point r / gn_rpp, pairs are gn_seg_off ranges of points
+  const int64_t* gn_seg_off = nullptr;
   int gn_nseg = 0;
-  int gn_cpg = 1;                // channels per group: a power of two <= 32, or a multiple of 32
+  int gn_cpg = 1;            // channels per group: a power of two <= 16, or a multiple of 16
   int gn_groups = 0;
-  int gn_rpp = 1;                // rows per point (6 for equivariant features)
+  int gn_rpp = 1;            // rows per point (6 for equivariant features)
+  // (a) accumulate the statistics of the fp32 values (se3et_gemm_bf16_gnstats): [nseg, groups, 2] {sum, sum sq}
+  double* gn_stats = nullptr;
+  // (b) apply: out_bf16 = LeakyReLU_slope((v - mean) * rstd * gamma + beta [+ resid])   (se3et_gemm_bf16_gnapply)
+  const double* norm_stats = nullptr;
+  const float* norm_gamma = nullptr;
+  const float* norm_beta = nullptr;
+  const __nv_bfloat16* norm_resid = nullptr;  // nullable, [M, ldc]
+  float norm_eps = 1e-5f;
+  float norm_slope = 1.f;
 };
 
 struct GemmShape {
@@ -45,6 +54,7 @@ struct GemmShape {
   int64_t a_batch_rows;      // rows between batches in the flattened A map
   int64_t b_batch_rows;      // rows between batches in the flattened B map (0 = shared B)
   const int64_t* groups;     // optional device table, 6 int64 per blockIdx.z: {a_row0, b_row0, m_rows, c_off, ldc, -}
+  int stages;                // smem ring depth, 1..kGemmMaxStages (fewer stages -> more CTAs per SM for short K)
 };
 
 template <int BN>
@@ -52,24 +62,31 @@ struct GemmSmem {
   static constexpr int kABytes = kGemmBM * 128;
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = kGemmStages * kStageBytes;
-  static constexpr int kGnOffset = kBarOffset + 128;      // 4 epilogue warps x 64 groups x {sum, sumsq} floats
-  static constexpr int kTotal = kGnOffset + 4 * 64 * 2 * 4 + 1024;  // + barriers + GN scratch + alignment slack
+  static constexpr int kTail = 128 + 4 * 64 * 2 * 4 + 64 * 8;  // barriers, GN accumulators, (mean, rstd) table
+  static constexpr int kCBytes = kGemmBM * BN * 2;             // bf16 output tile staged for coalesced stores
+  __host__ __device__ static int bar_offset(int stages) { return stages * kStageBytes; }
+  // tail: 128 B barriers | 2 KB GN accumulators | 512 B (mean, rstd) | 2 KB per-column (scale, shift) | pad
+  __host__ __device__ static int c_offset(int stages) { return stages * kStageBytes + 5120; }
+  static int total(int stages, bool c_tile) { return stages * kStageBytes + 5120 + (c_tile ? kCBytes : 0) + 1024; }
 };
 
-
 template <int BN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, (BN <= 128 ? 3 : 2))
 gemm_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, GemmShape shape,
                 GemmEpilogue ep) {
   using S = GemmSmem<BN>;
   constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
-  uint64_t* empty_bar = full_bar + kGemmStages;
-  uint64_t* tmem_full_bar = empty_bar + kGemmStages;
+  const int stages = shape.stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::bar_offset(stages));
+  uint64_t* empty_bar = full_bar + kGemmMaxStages;
+  uint64_t* tmem_full_bar = empty_bar + kGemmMaxStages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* gn_acc = reinterpret_cast<float*>(smem + S::bar_offset(stages) + 128);  // [4 warps][64 groups][2]
+  float2* gn_tab = reinterpret_cast<float2*>(gn_acc + 4 * 128);                  // [64 groups] {mean, rstd}
+  float2* col_tab = reinterpret_cast<float2*>(gn_tab + 64);                       // [BN] apply mode: {scale, shift}
+  uint8_t* c_tile = smem + S::c_offset(stages);  // apply mode only: [128 rows][BN bf16], 16-byte chunks swizzled
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kGemmBM, n0 = blockIdx.y * BN, z = blockIdx.z;
@@ -90,7 +107,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&tma_a);
     tc::tma_prefetch_desc(&tma_b);
-    for (int s = 0; s < kGemmStages; ++s) {
+    for (int s = 0; s < stages; ++s) {
       tc::mbar_init(&full_bar[s], 1);
       tc::mbar_init(&empty_bar[s], 1);
     }
@@ -107,22 +124,23 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     if (lane == 0) {
       const int a_row = (int)a_row0 + m0;
       const int b_row = (int)b_row0 + n0;
+      int s = 0;
+      uint32_t phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kGemmStages;
-        const uint32_t phase = (kb / kGemmStages) & 1;
         tc::mbar_wait(&empty_bar[s], phase ^ 1);
         tc::mbar_arrive_expect_tx(&full_bar[s], S::kStageBytes);
         uint8_t* a_dst = smem + s * S::kStageBytes;
         tc::tma_load_2d(a_dst, &tma_a, &full_bar[s], kb * kGemmBK, a_row);
         tc::tma_load_2d(a_dst + S::kABytes, &tma_b, &full_bar[s], kb * kGemmBK, b_row);
+        if (++s == stages) { s = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = tc::umma_idesc_bf16(kGemmBM, BN);
+      int s = 0;
+      uint32_t phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % kGemmStages;
-        const uint32_t phase = (kb / kGemmStages) & 1;
         tc::mbar_wait(&full_bar[s], phase);
         tc::tcgen05_fence_after_sync();
         const uint32_t a_addr = tc::smem_u32(smem + s * S::kStageBytes);
@@ -134,72 +152,151 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
           tc::umma_bf16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
         }
         tc::umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+        if (++s == stages) { s = 0; phase ^= 1; }
       }
       tc::umma_commit(tmem_full_bar);
     }
   } else {
     // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
-    const int lane_base = (warp & 3) * 32;
+    const int ew = warp & 3;
+    const int lane_base = ew * 32;
     const int row = m0 + lane_base + lane;
-    tc::mbar_wait(tmem_full_bar, 0);
-    tc::tcgen05_fence_after_sync();
     const bool row_ok = row < m_rows;
     const int64_t c_off = c_base + (int64_t)row * ldc + n0;
-    // fused GroupNorm statistics: per-warp accumulators in smem, one set of fp64 atomics per tile
-    float* gn_acc = reinterpret_cast<float*>(smem + S::kGnOffset);
-    float* warp_acc = gn_acc + (warp & 3) * 128;
+    const bool use_gn = ep.gn_stats != nullptr || ep.norm_stats != nullptr;
+    float* warp_acc = gn_acc + ew * 128;
     bool gn_uniform = false;
-    int gn_seg = 0;
+    int gn_seg = 0, row_seg = 0;
     double* gn_row_stats = nullptr;
-    if (ep.gn_stats) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) warp_acc[lane * 4 + i] = 0.f;
+    const int cpg = ep.gn_cpg;
+    const int g_tile0 = n0 / cpg;
+    // ---- before the accumulators are ready: pair lookup, statistics table of this tile (overlaps the main loop)
+    if (use_gn) {
       const int last = min(m0 + kGemmBM, m_rows) - 1;
       gn_seg = segment_of(ep.gn_seg_off, ep.gn_nseg, m0 / ep.gn_rpp);
       gn_uniform = segment_of(ep.gn_seg_off, ep.gn_nseg, last / ep.gn_rpp) == gn_seg;
-      if (!gn_uniform && row_ok)
-        gn_row_stats = ep.gn_stats +
-                       (int64_t)segment_of(ep.gn_seg_off, ep.gn_nseg, row / ep.gn_rpp) * ep.gn_groups * 2;
+      row_seg = gn_uniform ? gn_seg : segment_of(ep.gn_seg_off, ep.gn_nseg, (row_ok ? row : last) / ep.gn_rpp);
+      if (ep.gn_stats) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) warp_acc[lane * 4 + i] = 0.f;
+        if (!gn_uniform && row_ok) gn_row_stats = ep.gn_stats + (int64_t)row_seg * ep.gn_groups * 2;
+      }
+      if (ep.norm_stats && gn_uniform) {
+        // per-column affine map of this tile: x_norm = acc * scale + shift (bias, mean, rstd, gamma, beta folded)
+        const int e = ew * 32 + lane;
+        const double cnt = (double)(ep.gn_seg_off[gn_seg + 1] - ep.gn_seg_off[gn_seg]) * ep.gn_rpp * cpg;
+        for (int cc = e; cc < BN; cc += 128) {
+          const int c = n0 + cc;
+          const double* st = ep.norm_stats + ((int64_t)gn_seg * ep.gn_groups + c / cpg) * 2;
+          const double mean = st[0] / cnt;
+          const double var = st[1] / cnt - mean * mean;
+          const float sc = rsqrtf((float)fmax(var, 0.0) + ep.norm_eps) * ep.norm_gamma[c];
+          const float b = ep.bias ? ep.bias[c] : 0.f;
+          col_tab[cc] = make_float2(sc, ep.norm_beta[c] + (b - (float)mean) * sc);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+      }
       __syncwarp();
     }
+    // apply mode: the output tile is staged in shared memory so that global loads (residual) and stores are
+    // row-contiguous.  chunk (row, j) of 16 bytes lives at row * BN * 2 + ((j ^ (row & 7)) << 4).
+    constexpr int kRowChunks = BN / 8;  // 16-byte chunks per tile row
+    constexpr int kSwz = kRowChunks >= 8 ? 7 : kRowChunks - 1;  // swizzle stays inside the row
+    const int et = ew * 32 + lane;      // epilogue thread 0..127
+    if (ep.norm_stats && ep.norm_resid) {
+      for (int i = et; i < kGemmBM * kRowChunks; i += 128) {
+        const int rr = i / kRowChunks, j = i - rr * kRowChunks;
+        if (m0 + rr < m_rows) {
+          const uint32_t dst = tc::smem_u32(c_tile) + rr * (BN * 2) + ((j ^ (rr & kSwz)) << 4);
+          const __nv_bfloat16* src = ep.norm_resid + c_base + (int64_t)(m0 + rr) * ldc + n0 + j * 8;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    tc::mbar_wait(tmem_full_bar, 0);
+    tc::tcgen05_fence_after_sync();
+    if (ep.norm_stats && ep.norm_resid) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      if (BN >= 32) {
-        tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0, r);
-      } else {
-        // BN == 16: only 16 valid columns were written; load 32 (allocated) and ignore the rest
-        tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)lane_base << 16), r);
+    for (int c0 = 0; c0 < BN; c0 += kEpCols) {
+      uint32_t r[kEpCols];
+      tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0, r);
+      // residual row segment of the apply mode (this thread's own row of the staged tile)
+      uint4 res[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+      const int trow = lane_base + lane;
+      uint8_t* crow = c_tile + trow * (BN * 2);
+      const int cj = c0 / 8;
+      if (ep.norm_stats && ep.norm_resid) {
+        res[0] = *reinterpret_cast<const uint4*>(crow + (((cj) ^ (trow & kSwz)) << 4));
+        res[1] = *reinterpret_cast<const uint4*>(crow + (((cj + 1) ^ (trow & kSwz)) << 4));
       }
       tc::tmem_ld_wait();
-      constexpr int kCols = BN >= 32 ? 32 : BN;
-      float v[kCols];
+      float v[kEpCols];
 #pragma unroll
-      for (int j = 0; j < kCols; ++j) {
+      for (int j = 0; j < kEpCols; ++j) {
         float x = __uint_as_float(r[j]) * ep.alpha;
         if (ep.bias) x += __ldg(ep.bias + n0 + c0 + j);
         if (ep.act == 1) x = fmaxf(x, 0.f);
         v[j] = x;
       }
       if (ep.gn_stats) {
-        const int cpg = ep.gn_cpg;
-        const int g_glob = (n0 + c0) / cpg, g_loc = g_glob - n0 / cpg;
-gn_accumulate_chunk<kCols>(cpg, v, row_ok, gn_uniform, lane, warp_acc, g_loc, gn_row_stats, g_glob);
+        const int g_glob = (n0 + c0) / cpg, g_loc = g_glob - g_tile0;
+        gn_accumulate_chunk<kEpCols>(cpg, v, row_ok, gn_uniform, lane, warp_acc, g_loc, gn_row_stats, g_glob);
+      }
+      if (ep.norm_stats) {
+        const uint32_t rw[8] = {res[0].x, res[0].y, res[0].z, res[0].w, res[1].x, res[1].y, res[1].z, res[1].w};
+#pragma unroll
+        for (int j = 0; j < kEpCols; ++j) {
+          float x;
+          if (gn_uniform) {
+            const float2 t = col_tab[c0 + j];
+            x = fmaf(__uint_as_float(r[j]), t.x, t.y);
+          } else {  // tile straddles a pair boundary: per-row statistics straight from global memory
+            const int c = n0 + c0 + j;
+            const double cnt = (double)(ep.gn_seg_off[row_seg + 1] - ep.gn_seg_off[row_seg]) * ep.gn_rpp * cpg;
+            const double* st = ep.norm_stats + ((int64_t)row_seg * ep.gn_groups + c / cpg) * 2;
+            const double mean = st[0] / cnt;
+            const double var = st[1] / cnt - mean * mean;
+            const float sc = rsqrtf((float)fmax(var, 0.0) + ep.norm_eps) * __ldg(ep.norm_gamma + c);
+            x = (v[j] - (float)mean) * sc + __ldg(ep.norm_beta + c);
+          }
+          const uint32_t w = rw[j >> 1];
+          x += (j & 1) ? __uint_as_float(w & 0xffff0000u) : __uint_as_float(w << 16);
+          v[j] = fmaxf(x, x * ep.norm_slope);  // LeakyReLU for slope <= 1
+        }
+        // result back into the staged tile (same chunks the residual came from)
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * jj], v[8 * jj + 1]);
+          __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * jj + 2], v[8 * jj + 3]);
+          __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * jj + 4], v[8 * jj + 5]);
+          __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * jj + 6], v[8 * jj + 7]);
+          uint4 u;
+          u.x = *reinterpret_cast<uint32_t*>(&p0);
+          u.y = *reinterpret_cast<uint32_t*>(&p1);
+          u.z = *reinterpret_cast<uint32_t*>(&p2);
+          u.w = *reinterpret_cast<uint32_t*>(&p3);
+          *reinterpret_cast<uint4*>(crow + (((cj + jj) ^ (trow & kSwz)) << 4)) = u;
+        }
+        continue;
       }
       if (row_ok && ep.transposed) {
 #pragma unroll
-        for (int j = 0; j < kCols; ++j)
+        for (int j = 0; j < kEpCols; ++j)
           if (n0 + c0 + j < ep.n_valid) ep.out_f32[c_base + (int64_t)(n0 + c0 + j) * ldc + row] = v[j];
       } else if (row_ok) {
         if (ep.out_f32) {
           float4* dst = reinterpret_cast<float4*>(ep.out_f32 + c_off + c0);
 #pragma unroll
-          for (int j = 0; j < kCols / 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < kEpCols / 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         if (ep.out_bf16) {
           uint4* dst = reinterpret_cast<uint4*>(ep.out_bf16 + c_off + c0);
 #pragma unroll
-          for (int j = 0; j < kCols / 8; ++j) {
+          for (int j = 0; j < kEpCols / 8; ++j) {
             __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
             __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
             __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
@@ -214,14 +311,24 @@ gn_accumulate_chunk<kCols>(cpg, v, row_ok, gn_uniform, lane, warp_acc, g_loc, gn
         }
       }
     }
+    if (ep.norm_stats) {
+      // staged tile -> global memory, row-contiguous 16-byte stores
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = et; i < kGemmBM * kRowChunks; i += 128) {
+        const int rr = i / kRowChunks, j = i - rr * kRowChunks;
+        if (m0 + rr < m_rows)
+          *reinterpret_cast<uint4*>(ep.out_bf16 + c_base + (int64_t)(m0 + rr) * ldc + n0 + j * 8) =
+              *reinterpret_cast<const uint4*>(c_tile + rr * (BN * 2) + ((j ^ (rr & kSwz)) << 4));
+      }
+    }
     if (ep.gn_stats) {
       asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
       if (gn_uniform) {
-        const int e = (warp & 3) * 32 + lane;
-        const int ngr2 = 2 * ((n0 + BN - 1) / ep.gn_cpg - n0 / ep.gn_cpg + 1);
+        const int e = ew * 32 + lane;
+        const int ngr2 = 2 * ((n0 + BN - 1) / cpg - g_tile0 + 1);
         for (int i = e; i < ngr2; i += 128) {
           const float t = gn_acc[i] + gn_acc[128 + i] + gn_acc[256 + i] + gn_acc[384 + i];
-          atomicAdd(ep.gn_stats + ((int64_t)gn_seg * ep.gn_groups + n0 / ep.gn_cpg) * 2 + i, (double)t);
+          atomicAdd(ep.gn_stats + ((int64_t)gn_seg * ep.gn_groups + g_tile0) * 2 + i, (double)t);
         }
       }
     }
@@ -265,16 +372,21 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t 
 }
 
 template <int BN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& shape, const GemmEpilogue& ep,
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmShape shape, const GemmEpilogue& ep,
                        int batch, cudaStream_t st) {
   using S = GemmSmem<BN>;
-  static bool configured = false;
-  if (!configured) {
-    SE3ET_CUDA_CHECK(cudaFuncSetAttribute(gemm_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    configured = true;
+  const int num_kb = (shape.K + kGemmBK - 1) / kGemmBK;
+  const bool c_tile = ep.norm_stats != nullptr;
+  shape.stages = num_kb < kGemmMaxStages ? num_kb : kGemmMaxStages;
+  while (shape.stages > 1 && S::total(shape.stages, c_tile) > 227 * 1024) --shape.stages;
+  const int smem = S::total(shape.stages, c_tile);
+  static int configured = 0;
+  if (configured < smem) {
+    SE3ET_CUDA_CHECK(cudaFuncSetAttribute(gemm_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
   }
   dim3 grid((unsigned)ceil_div(shape.M, kGemmBM), (unsigned)(shape.N / BN), (unsigned)batch);
-  gemm_tma_kernel<BN><<<grid, kGemmThreads, S::kTotal, st>>>(ta, tb, shape, ep);
+  gemm_tma_kernel<BN><<<grid, kGemmThreads, smem, st>>>(ta, tb, shape, ep);
   SE3ET_LAUNCH_CHECK();
   return SE3ET_OK;
 }
@@ -291,8 +403,9 @@ int gemm_bf16(const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b, int64
               int64_t b_rows_total, const GemmEpilogue& ep, cudaStream_t st) {
   if (M <= 0 || batch <= 0) return SE3ET_OK;
   if (N <= 0 || K <= 0 || !a || !b) return SE3ET_ERR_ARG;
-  const int bn = pick_bn(N);
+  int bn = pick_bn(N);
   if (!bn) return SE3ET_ERR_UNSUPPORTED;
+  if (ep.norm_stats && bn > 128) bn = 128;  // apply mode stages its output tile: 3 CTAs per SM
   if (ep.transposed && (!ep.out_f32 || ep.out_bf16)) return SE3ET_ERR_ARG;
   if (!ep.transposed && ep.out_f32 &&
       ((reinterpret_cast<uintptr_t>(ep.out_f32) & 15) || (ep.ldc % 4) || (ep.c_batch_stride % 4) || groups))
@@ -309,7 +422,7 @@ int gemm_bf16(const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b, int64
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tb, b, b_rows, K, ldb, bn);
   if (rc) return rc;
-  GemmShape shape{M, N, K, a_batch_rows, b_batch_rows, groups};
+  GemmShape shape{M, N, K, a_batch_rows, b_batch_rows, groups, kGemmMaxStages};
   switch (bn) {
     case 256: return launch_gemm<256>(ta, tb, shape, ep, batch, st);
     case 128: return launch_gemm<128>(ta, tb, shape, ep, batch, st);
@@ -367,20 +480,24 @@ extern "C" int se3et_gemm_bf16(const void* a, int64_t lda, const void* b, int64_
                    (int)k, (int)batch, a_batch_rows, b_batch_rows, nullptr, 0, 0, ep, static_cast<cudaStream_t>(stream));
 }
 
+// shapes the GroupNorm epilogues cover: groups inside 16-column chunks (cpg | 16) or chunks inside groups (16 | cpg),
+// at most 64 groups per output tile
+static bool gn_epilogue_ok(int64_t n, int64_t groups, int bn) {
+  if (groups <= 0 || n % groups) return false;
+  const int64_t cpg = n / groups;
+  const bool pow2 = (cpg & (cpg - 1)) == 0;
+  return ((pow2 && cpg <= kEpCols) || cpg % kEpCols == 0) && bn / cpg <= 64;
+}
+
 extern "C" int se3et_gemm_bf16_gnstats(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int64_t n,
                                        int64_t k, const float* bias, float* out_f32, int64_t ldc, double* stats,
                                        const int64_t* seg_offsets, int64_t nseg, int64_t groups,
                                        int64_t rows_per_point, se3et_stream_t stream) {
   if (m < 0 || n <= 0 || k <= 0 || m > INT32_MAX || n > INT32_MAX || k > INT32_MAX) return SE3ET_ERR_ARG;
-  if (!out_f32 || !stats || !seg_offsets || nseg <= 0 || groups <= 0 || n % groups || rows_per_point <= 0)
-    return SE3ET_ERR_ARG;
+  if (!stats || !seg_offsets || nseg <= 0 || groups <= 0 || n % groups || rows_per_point <= 0) return SE3ET_ERR_ARG;
   const int bn = pick_bn((int)n);
   if (!bn) return SE3ET_ERR_UNSUPPORTED;
-  const int64_t cpg = n / groups;
-  const int chunk = bn >= 32 ? 32 : bn;
-  const bool pow2 = (cpg & (cpg - 1)) == 0;
-  // the epilogue reduces groups inside 32-column chunks: cpg | chunk, or chunk | cpg; <= 64 groups per tile
-  if (!((pow2 && cpg <= chunk) || cpg % chunk == 0) || bn / cpg > 64) return SE3ET_ERR_UNSUPPORTED;
+  if (!gn_epilogue_ok(n, groups, bn)) return SE3ET_ERR_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SE3ET_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * nseg * groups, st));
   if (m == 0) return SE3ET_OK;
@@ -388,7 +505,7 @@ extern "C" int se3et_gemm_bf16_gnstats(const void* a, int64_t lda, const void* b
   ep.out_f32 = out_f32;
   ep.out_bf16 = nullptr;
   ep.bias = bias;
-  ep.ldc = ldc;
+  ep.ldc = out_f32 ? ldc : n;
   ep.c_batch_stride = 0;
   ep.alpha = 1.f;
   ep.act = 0;
@@ -397,9 +514,50 @@ extern "C" int se3et_gemm_bf16_gnstats(const void* a, int64_t lda, const void* b
   ep.gn_stats = stats;
   ep.gn_seg_off = seg_offsets;
   ep.gn_nseg = (int)nseg;
-  ep.gn_cpg = (int)cpg;
+  ep.gn_cpg = (int)(n / groups);
   ep.gn_groups = (int)groups;
   ep.gn_rpp = (int)rows_per_point;
   return gemm_bf16(static_cast<const __nv_bfloat16*>(a), lda, static_cast<const __nv_bfloat16*>(b), ldb, (int)m, (int)n,
                    (int)k, 1, 0, 0, nullptr, 0, 0, ep, st);
+}
+
+extern "C" int se3et_gemm_bf16_gnapply(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int64_t n,
+                                       int64_t k, const float* bias, const double* stats, const float* gamma,
+                                       const float* beta, float eps, float leaky_slope, const void* resid_bf16,
+                                       void* out_bf16, int64_t ldc, const int64_t* seg_offsets, int64_t nseg,
+                                       int64_t groups, int64_t rows_per_point, se3et_stream_t stream) {
+  if (m < 0 || n <= 0 || k <= 0 || m > INT32_MAX || n > INT32_MAX || k > INT32_MAX) return SE3ET_ERR_ARG;
+  if (!stats || !gamma || !beta || !out_bf16 || !seg_offsets || nseg <= 0 || groups <= 0 || n % groups ||
+      rows_per_point <= 0)
+    return SE3ET_ERR_ARG;
+  int bn = pick_bn((int)n);
+  if (!bn) return SE3ET_ERR_UNSUPPORTED;
+  if (bn > 128) bn = 128;
+  if (!gn_epilogue_ok(n, groups, bn)) return SE3ET_ERR_UNSUPPORTED;
+  if (resid_bf16 && (reinterpret_cast<uintptr_t>(resid_bf16) & 15)) return SE3ET_ERR_ARG;
+  if (leaky_slope > 1.f) return SE3ET_ERR_ARG;
+  if (m == 0) return SE3ET_OK;
+  GemmEpilogue ep;
+  ep.out_f32 = nullptr;
+  ep.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16);
+  ep.bias = bias;
+  ep.ldc = ldc;
+  ep.c_batch_stride = 0;
+  ep.alpha = 1.f;
+  ep.act = 0;
+  ep.transposed = 0;
+  ep.n_valid = (int)n;
+  ep.gn_seg_off = seg_offsets;
+  ep.gn_nseg = (int)nseg;
+  ep.gn_cpg = (int)(n / groups);
+  ep.gn_groups = (int)groups;
+  ep.gn_rpp = (int)rows_per_point;
+  ep.norm_stats = stats;
+  ep.norm_gamma = gamma;
+  ep.norm_beta = beta;
+  ep.norm_resid = static_cast<const __nv_bfloat16*>(resid_bf16);
+  ep.norm_eps = eps;
+  ep.norm_slope = leaky_slope;
+  return gemm_bf16(static_cast<const __nv_bfloat16*>(a), lda, static_cast<const __nv_bfloat16*>(b), ldb, (int)m, (int)n,
+                   (int)k, 1, 0, 0, nullptr, 0, 0, ep, static_cast<cudaStream_t>(stream));
 }

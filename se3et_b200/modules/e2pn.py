@@ -17,12 +17,12 @@ from torch.nn.parameter import Parameter
 
 from .. import _lib
 from ..ops import e2pn_ops as K
-from ..ops.gemm import linear_bf16, linear_gn_stats
+from ..ops.gemm import _gn_fusable, linear_bf16, linear_gn_apply, linear_gn_stats
 from . import octahedral
 
 
 # switches for A/B measurements and tests (the defaults are the product path)
-_GFLAGS = {'fused_kpconv': True}
+_GFLAGS = {'fused_kpconv': True, 'two_pass_unary': True}
 
 
 def _gn_fusable_fused(cout, groups):
@@ -200,17 +200,32 @@ class UnaryBlockEPN(nn.Module):
         self.leaky_relu = nn.LeakyReLU(0.1)
         self._w_cache = _Bf16Cache()
 
-    def pre_norm(self, x, seg, rows_per_point):
-        """fp32 (N*A, Cout) Linear output and its per-pair GroupNorm statistics."""
+    def pre_norm(self, x, seg, rows_per_point, store=True):
+        """fp32 (N*A, Cout) Linear output (None when store=False) and its per-pair GroupNorm statistics."""
         x2 = _act(x).reshape(-1, self.in_dim)
         return linear_gn_stats(x2, self._w_cache.get(self.mlp.weight), self.mlp.bias, self.norm.num_groups, seg,
-                               rows_per_point)
+                               rows_per_point, store=store)
+
+    def two_pass_ok(self):
+        return _GFLAGS['two_pass_unary'] and _gn_fusable(self.out_dim, self.norm.num_groups)
+
+    def apply(self, x, stats, seg, rows_per_point, slope, resid=None):
+        """Second pass: the Linear recomputed with GroupNorm (+ resid) (+ LeakyReLU) in the GEMM epilogue -> bf16."""
+        x2 = _act(x).reshape(-1, self.in_dim)
+        return linear_gn_apply(x2, self._w_cache.get(self.mlp.weight), self.mlp.bias, stats, self.norm.norm.weight,
+                               self.norm.norm.bias, self.norm.norm.eps, slope, self.norm.num_groups, seg,
+                               rows_per_point, resid=resid)
 
     def forward(self, x, batch=None, seg=None):
         n, a = x.shape[0], x.shape[1]
         seg = _seg(seg, n, x.device)
+        slope = 1.0 if self.no_relu else 0.1
+        if self.two_pass_ok() and n > 0:
+            x = _act(x).contiguous()
+            _, stats = self.pre_norm(x, seg, a, store=False)
+            return self.apply(x, stats, seg, a, slope).view(n, a, self.out_dim)
         y, stats = self.pre_norm(x, seg, a)
-        _, out = self.norm.fused(y, seg, a, slope=1.0 if self.no_relu else 0.1, stats=stats)
+        _, out = self.norm.fused(y, seg, a, slope=slope, stats=stats)
         return out.view(n, a, self.out_dim)
 
 
@@ -313,10 +328,22 @@ class ResnetBottleneckBlockEPN(nn.Module):
             y = x
         f, _ = self.interso3.fused(y, q_pts, s_pts, neighb_inds, seg, out_f32=True)
         _, y = self.norm.fused(f, seg, 6, slope=0.1)
-        pre2, st2 = self.unary2.pre_norm(y.view(nq, 6, -1), seg, 6)
         if 'strided' in self.block_name:
             skip = K.maxpool_nbr(skip, neighb_inds.contiguous(), seg if sub_width is not None else None, sub_width)
-        if isinstance(self.skip_conv, UnaryBlockEPN):
+        has_skip_conv = isinstance(self.skip_conv, UnaryBlockEPN)
+        if nq > 0 and self.unary2.two_pass_ok() and (not has_skip_conv or self.skip_conv.two_pass_ok()):
+            # statistics passes, then the Linear(s) recomputed with normalisation + residual + LeakyReLU in the
+            # GEMM epilogue: the (N, A, out_dim) pre-norm tensors never reach global memory
+            y3 = y.view(nq, 6, -1)
+            _, st2 = self.unary2.pre_norm(y3, seg, 6, store=False)
+            if has_skip_conv:
+                _, st_s = self.skip_conv.pre_norm(skip, seg, 6, store=False)
+                resid = self.skip_conv.apply(skip, st_s, seg, 6, 1.0)
+            else:
+                resid = skip.contiguous().view(nq * 6, self.out_dim)
+            return self.unary2.apply(y3, st2, seg, 6, 0.1, resid=resid).view(nq, 6, self.out_dim)
+        pre2, st2 = self.unary2.pre_norm(y.view(nq, 6, -1), seg, 6)
+        if has_skip_conv:
             pre_s, st_s = self.skip_conv.pre_norm(skip, seg, 6)
             _, out = self.unary2.norm.fused(pre2, seg, 6, slope=0.1, other=(pre_s, self.skip_conv.norm, st_s),
                                             stats=st2)
@@ -380,8 +407,13 @@ class UnaryBlock(nn.Module):
 
     def forward(self, x, seg=None):
         seg = _seg(seg, x.shape[0], x.device)
-        y, stats = linear_gn_stats(_act(x).contiguous(), self._w_cache.get(self.mlp.weight), self.mlp.bias,
-                                   self.norm.num_groups, seg, 1)
+        slope = 0.1 if self.leaky_relu is not None else 1.0
+        xb, w = _act(x).contiguous(), self._w_cache.get(self.mlp.weight)
+        if _GFLAGS['two_pass_unary'] and _gn_fusable(self.out_channels, self.norm.num_groups) and x.shape[0] > 0:
+            _, stats = linear_gn_stats(xb, w, self.mlp.bias, self.norm.num_groups, seg, 1, store=False)
+            return linear_gn_apply(xb, w, self.mlp.bias, stats, self.norm.norm.weight, self.norm.norm.bias,
+                                   self.norm.norm.eps, slope, self.norm.num_groups, seg, 1)
+        y, stats = linear_gn_stats(xb, w, self.mlp.bias, self.norm.num_groups, seg, 1)
         _, out = K.groupnorm_apply(y, stats, self.norm.norm.weight, self.norm.norm.bias, self.norm.num_groups, seg, 1,
                                    slope=0.1 if self.leaky_relu is not None else 1.0, eps=self.norm.norm.eps)
         return out

@@ -80,31 +80,36 @@ def bmm_bf16(a, b, alpha=1.0, out_f32=True, out_bf16=False):
 
 
 def _gn_fusable(n, groups):
-    """Mirrors the check in se3et_gemm_bf16_gnstats (csrc/gemm.cu)."""
+    """Mirrors gn_epilogue_ok in csrc/gemm.cu."""
     bn = next((b for b in (256, 128, 64, 32, 16) if n % b == 0), 0)
-    if not bn or n % groups:
+    if not bn or groups <= 0 or n % groups:
         return False
-    cpg, chunk = n // groups, min(bn, 32)
-    return ((cpg & (cpg - 1)) == 0 and cpg <= chunk or cpg % chunk == 0) and bn // cpg <= 64
+    cpg = n // groups
+    return ((cpg & (cpg - 1)) == 0 and cpg <= 16 or cpg % 16 == 0) and bn // cpg <= 64
 
 
-def linear_gn_stats(a, w, bias, groups, seg_off, rows_per_point):
-    """fp32 y = a @ w.T (+ bias) together with the GroupNorm statistics of y (double (nseg, groups, 2)), accumulated
-    in the GEMM epilogue.  Falls back to the separate statistics kernel for channel/group shapes the epilogue does
-    not cover (still the CUDA path)."""
+def _check_ab(a, w, bias):
+    _lib.require_cuda(a, w, bias)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and a.shape[1] == w.shape[1]
+    assert a.stride(1) == 1 and w.stride(1) == 1
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == w.shape[0]
+
+
+def linear_gn_stats(a, w, bias, groups, seg_off, rows_per_point, store=True):
+    """GroupNorm statistics (double (nseg, groups, 2)) of y = a @ w.T (+ bias), accumulated in the GEMM epilogue;
+    store=True also writes y as fp32.  -> (y or None, stats).  Falls back to GEMM + the separate statistics kernel
+    for channel/group shapes the epilogue does not cover (still the CUDA path)."""
     from . import e2pn_ops
     m, k = a.shape
     n = w.shape[0]
     if not _gn_fusable(n, groups) or m == 0:
         y, _ = linear_bf16(a, w, bias)
         return y, e2pn_ops.groupnorm_stats(y, groups, seg_off, rows_per_point)
-    _lib.require_cuda(a, w, bias, seg_off)
-    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.shape[1] == w.shape[1]
-    assert a.stride(1) == 1 and w.stride(1) == 1 and seg_off.dtype == torch.int64
-    if bias is not None:
-        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() == n
+    _check_ab(a, w, bias)
+    assert seg_off.dtype == torch.int64
     nseg = seg_off.numel() - 1
-    y = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    y = torch.empty((m, n), dtype=torch.float32, device=a.device) if store else None
     stats = torch.empty((nseg, groups, 2), dtype=torch.float64, device=a.device)
     _lib.check(_lib.lib().se3et_gemm_bf16_gnstats(
         _lib.ptr(a), _lib.i64(a.stride(0) if m > 1 else k), _lib.ptr(w), _lib.i64(w.stride(0) if n > 1 else k),
@@ -112,3 +117,24 @@ def linear_gn_stats(a, w, bias, groups, seg_off, rows_per_point):
         _lib.ptr(seg_off), _lib.i64(nseg), _lib.i64(groups), _lib.i64(rows_per_point), _lib.stream_ptr()),
         "gemm_bf16_gnstats")
     return y, stats
+
+
+def linear_gn_apply(a, w, bias, stats, gamma, beta, eps, slope, groups, seg_off, rows_per_point, resid=None):
+    """bf16 LeakyReLU_slope(GroupNorm(a @ w.T + bias) [+ resid]) with the normalisation applied in the GEMM epilogue
+    (second pass after linear_gn_stats(..., store=False)).  Requires _gn_fusable(n, groups)."""
+    _check_ab(a, w, bias)
+    m, k = a.shape
+    n = w.shape[0]
+    assert _gn_fusable(n, groups) and seg_off.dtype == torch.int64 and stats.dtype == torch.float64
+    out = torch.empty((m, n), dtype=torch.bfloat16, device=a.device)
+    if m == 0:
+        return out
+    if resid is not None:
+        assert resid.dtype == torch.bfloat16 and resid.is_contiguous() and resid.numel() == m * n
+    nseg = seg_off.numel() - 1
+    _lib.check(_lib.lib().se3et_gemm_bf16_gnapply(
+        _lib.ptr(a), _lib.i64(a.stride(0) if m > 1 else k), _lib.ptr(w), _lib.i64(w.stride(0) if n > 1 else k),
+        _lib.i64(m), _lib.i64(n), _lib.i64(k), _lib.ptr(bias), _lib.ptr(stats), _lib.ptr(gamma), _lib.ptr(beta),
+        _lib.f32(eps), _lib.f32(slope), _lib.ptr(resid), _lib.ptr(out), _lib.i64(n), _lib.ptr(seg_off),
+        _lib.i64(nseg), _lib.i64(groups), _lib.i64(rows_per_point), _lib.stream_ptr()), "gemm_bf16_gnapply")
+    return out

@@ -169,6 +169,38 @@ def test_gemm_epilogue_statistics_match_separate_pass(n_out, groups, k):
     assert float(stats[1].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("n_out,groups,k,rpp", [(32, 32, 64, 6), (128, 32, 32, 6), (256, 32, 128, 6), (1024, 32, 256, 6),
+                                                 (64, 4, 40, 1), (16, 4, 24, 6)])
+def test_gemm_groupnorm_apply_epilogue(n_out, groups, k, rpp):
+    """se3et_gemm_bf16_gnapply (statistics pass + recomputed GEMM with GroupNorm / residual / LeakyReLU in the
+    epilogue) against Linear -> per-pair GroupNorm -> add -> LeakyReLU in torch fp32."""
+    from se3et_b200.ops.gemm import linear_gn_apply, linear_gn_stats
+    g = torch.Generator().manual_seed(n_out + k)
+    pts = [150, 0, 333, 41]  # pair boundaries fall inside GEMM tiles
+    seg = torch.tensor(np.concatenate([[0], np.cumsum(pts)]), dtype=torch.int64, device=DEV)
+    rows = rpp * sum(pts)
+    a = (torch.randn(rows, k, generator=g) + 0.3).to(torch.bfloat16)
+    w = (torch.randn(n_out, k, generator=g) / k ** 0.5).to(torch.bfloat16)
+    bias, gamma, beta = (torch.randn(n_out, generator=g) for _ in range(3))
+    resid = torch.randn(rows, n_out, generator=g).to(torch.bfloat16)
+    y = a.float() @ w.float().t() + bias
+    want = []
+    for i in range(len(pts)):
+        blk = y[rpp * int(seg[i]):rpp * int(seg[i + 1])]
+        if blk.numel():
+            want.append(oe.group_norm_epn(blk.view(-1, rpp, n_out), groups, gamma, beta).reshape(-1, n_out))
+    want = torch.cat(want)
+    ad, wd = a.to(DEV), w.to(DEV)
+    none, stats = linear_gn_stats(ad, wd, bias.to(DEV), groups, seg, rpp, store=False)
+    assert none is None
+    for slope, res in ((0.1, resid), (1.0, None)):
+        got = linear_gn_apply(ad, wd, bias.to(DEV), stats, gamma.to(DEV), beta.to(DEV), 1e-5, slope, groups, seg, rpp,
+                              resid=None if res is None else res.to(DEV))
+        ref = want + (0 if res is None else res.float())
+        ref = torch.nn.functional.leaky_relu(ref, slope) if slope != 1.0 else ref
+        assert torch.allclose(got.float().cpu(), ref, rtol=2e-2, atol=2e-2), (got.float().cpu() - ref).abs().max()
+
+
 @pytest.mark.parametrize("c,G,rpp", [(32, 32, 6), (128, 32, 6), (1024, 32, 6), (256, 32, 1), (48, 16, 6), (2048, 32, 6)])
 def test_groupnorm_apply_two_operands_and_residual(c, G, rpp):
     """act(GN_a(ya) + GN_b(yb)) and act(GN_a(ya) + resid) against torch, several pairs of different sizes."""
