@@ -55,6 +55,7 @@ struct GemmShape {
   int64_t b_batch_rows;      // rows between batches in the flattened B map (0 = shared B)
   const int64_t* groups;     // optional device table, 6 int64 per blockIdx.z: {a_row0, b_row0, m_rows, c_off, ldc, -}
   int stages;                // smem ring depth, 1..kGemmMaxStages (fewer stages -> more CTAs per SM for short K)
+  int tiles_per_cta;         // consecutive 128-row tiles one CTA walks (loads / MMA / epilogue overlap across tiles)
 };
 
 template <int BN>
@@ -71,7 +72,7 @@ struct GemmSmem {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(kGemmThreads, (BN <= 128 ? 3 : 2))
+__global__ void __launch_bounds__(kGemmThreads, (BN <= 128 ? 2 : 1))
 gemm_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, GemmShape shape,
                 GemmEpilogue ep) {
   using S = GemmSmem<BN>;
@@ -81,15 +82,17 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   const int stages = shape.stages;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::bar_offset(stages));
   uint64_t* empty_bar = full_bar + kGemmMaxStages;
-  uint64_t* tmem_full_bar = empty_bar + kGemmMaxStages;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + kGemmMaxStages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;            // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   float* gn_acc = reinterpret_cast<float*>(smem + S::bar_offset(stages) + 128);  // [4 warps][64 groups][2]
   float2* gn_tab = reinterpret_cast<float2*>(gn_acc + 4 * 128);                  // [64 groups] {mean, rstd}
   float2* col_tab = reinterpret_cast<float2*>(gn_tab + 64);                       // [BN] apply mode: {scale, shift}
   uint8_t* c_tile = smem + S::c_offset(stages);  // apply mode only: [128 rows][BN bf16], 16-byte chunks swizzled
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kGemmBM, n0 = blockIdx.y * BN, z = blockIdx.z;
+  const int n0 = blockIdx.y * BN, z = blockIdx.z;
+  const int tile0 = blockIdx.x * shape.tiles_per_cta;
   const int num_kb = (shape.K + kGemmBK - 1) / kGemmBK;
   int64_t a_row0 = (int64_t)z * shape.a_batch_rows, b_row0 = (int64_t)z * shape.b_batch_rows;
   int m_rows = shape.M;
@@ -101,8 +104,13 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     m_rows = (int)shape.groups[6 * z + 2];
     c_base = shape.groups[6 * z + 3];
     ldc = shape.groups[6 * z + 4];
-    if (m0 >= m_rows) return;  // uniform for the whole CTA, before any barrier / TMEM allocation
+    if (tile0 * kGemmBM >= m_rows) return;  // uniform for the whole CTA, before any barrier / TMEM allocation
   }
+  // tiles this CTA owns: [tile0, tile0 + ntiles)
+  const int ntiles = min(shape.tiles_per_cta, (m_rows - tile0 * kGemmBM + kGemmBM - 1) / kGemmBM);
+  // two accumulator buffers when they fit TMEM next to a co-resident CTA (epilogue of tile t under the MMA of t + 1)
+  constexpr int kAccBufs = BN <= 128 ? 2 : 1;
+  constexpr uint32_t kTmemAlloc = kTmemCols * kAccBufs;
 
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&tma_a);
@@ -111,10 +119,13 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       tc::mbar_init(&full_bar[s], 1);
       tc::mbar_init(&empty_bar[s], 1);
     }
-    tc::mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(&tmem_full_bar[b], 1);
+      tc::mbar_init(&tmem_empty_bar[b], 4);
+    }
     tc::mbar_fence_init();
   }
-  if (warp == 1) tc::tmem_alloc<kTmemCols>(tmem_ptr);
+  if (warp == 1) tc::tmem_alloc<kTmemAlloc>(tmem_ptr);
   tc::tcgen05_fence_before_sync();
   __syncthreads();
   tc::tcgen05_fence_after_sync();
@@ -122,17 +133,19 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      const int a_row = (int)a_row0 + m0;
       const int b_row = (int)b_row0 + n0;
       int s = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        tc::mbar_wait(&empty_bar[s], phase ^ 1);
-        tc::mbar_arrive_expect_tx(&full_bar[s], S::kStageBytes);
-        uint8_t* a_dst = smem + s * S::kStageBytes;
-        tc::tma_load_2d(a_dst, &tma_a, &full_bar[s], kb * kGemmBK, a_row);
-        tc::tma_load_2d(a_dst + S::kABytes, &tma_b, &full_bar[s], kb * kGemmBK, b_row);
-        if (++s == stages) { s = 0; phase ^= 1; }
+      for (int t = 0; t < ntiles; ++t) {
+        const int a_row = (int)a_row0 + (tile0 + t) * kGemmBM;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          tc::mbar_wait(&empty_bar[s], phase ^ 1);
+          tc::mbar_arrive_expect_tx(&full_bar[s], S::kStageBytes);
+          uint8_t* a_dst = smem + s * S::kStageBytes;
+          tc::tma_load_2d(a_dst, &tma_a, &full_bar[s], kb * kGemmBK, a_row);
+          tc::tma_load_2d(a_dst + S::kABytes, &tma_b, &full_bar[s], kb * kGemmBK, b_row);
+          if (++s == stages) { s = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -140,202 +153,221 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       constexpr uint32_t idesc = tc::umma_idesc_bf16(kGemmBM, BN);
       int s = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        tc::mbar_wait(&full_bar[s], phase);
+      for (int t = 0; t < ntiles; ++t) {
+        const int buf = t % kAccBufs;
+        const uint32_t use = (uint32_t)(t / kAccBufs);
+        tc::mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);  // the epilogue has drained this accumulator buffer
         tc::tcgen05_fence_after_sync();
-        const uint32_t a_addr = tc::smem_u32(smem + s * S::kStageBytes);
-        const uint64_t a_desc = tc::umma_desc_sw128(a_addr);
-        const uint64_t b_desc = tc::umma_desc_sw128(a_addr + S::kABytes);
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * kTmemCols);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          tc::mbar_wait(&full_bar[s], phase);
+          tc::tcgen05_fence_after_sync();
+          const uint32_t a_addr = tc::smem_u32(smem + s * S::kStageBytes);
+          const uint64_t a_desc = tc::umma_desc_sw128(a_addr);
+          const uint64_t b_desc = tc::umma_desc_sw128(a_addr + S::kABytes);
 #pragma unroll
-        for (int k = 0; k < kGemmBK / 16; ++k) {
-          // +32 bytes per UMMA_K step inside the 128-byte swizzle atom (encoded >> 4)
-          tc::umma_bf16(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          for (int k = 0; k < kGemmBK / 16; ++k) {
+            // +32 bytes per UMMA_K step inside the 128-byte swizzle atom (encoded >> 4)
+            tc::umma_bf16(tmem_acc, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
+          tc::umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+          if (++s == stages) { s = 0; phase ^= 1; }
         }
-        tc::umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
-        if (++s == stages) { s = 0; phase ^= 1; }
+        tc::umma_commit(&tmem_full_bar[buf]);
       }
-      tc::umma_commit(tmem_full_bar);
     }
   } else {
     // epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32)
     const int ew = warp & 3;
     const int lane_base = ew * 32;
-    const int row = m0 + lane_base + lane;
-    const bool row_ok = row < m_rows;
-    const int64_t c_off = c_base + (int64_t)row * ldc + n0;
+    const int et = ew * 32 + lane;      // epilogue thread 0..127
     const bool use_gn = ep.gn_stats != nullptr || ep.norm_stats != nullptr;
     float* warp_acc = gn_acc + ew * 128;
-    bool gn_uniform = false;
-    int gn_seg = 0, row_seg = 0;
-    double* gn_row_stats = nullptr;
     const int cpg = ep.gn_cpg;
     const int g_tile0 = n0 / cpg;
-    // ---- before the accumulators are ready: pair lookup, statistics table of this tile (overlaps the main loop)
-    if (use_gn) {
-      const int last = min(m0 + kGemmBM, m_rows) - 1;
-      gn_seg = segment_of(ep.gn_seg_off, ep.gn_nseg, m0 / ep.gn_rpp);
-      gn_uniform = segment_of(ep.gn_seg_off, ep.gn_nseg, last / ep.gn_rpp) == gn_seg;
-      row_seg = gn_uniform ? gn_seg : segment_of(ep.gn_seg_off, ep.gn_nseg, (row_ok ? row : last) / ep.gn_rpp);
-      if (ep.gn_stats) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) warp_acc[lane * 4 + i] = 0.f;
-        if (!gn_uniform && row_ok) gn_row_stats = ep.gn_stats + (int64_t)row_seg * ep.gn_groups * 2;
-      }
-      if (ep.norm_stats && gn_uniform) {
-        // per-column affine map of this tile: x_norm = acc * scale + shift (bias, mean, rstd, gamma, beta folded)
-        const int e = ew * 32 + lane;
-        const double cnt = (double)(ep.gn_seg_off[gn_seg + 1] - ep.gn_seg_off[gn_seg]) * ep.gn_rpp * cpg;
-        for (int cc = e; cc < BN; cc += 128) {
-          const int c = n0 + cc;
-          const double* st = ep.norm_stats + ((int64_t)gn_seg * ep.gn_groups + c / cpg) * 2;
-          const double mean = st[0] / cnt;
-          const double var = st[1] / cnt - mean * mean;
-          const float sc = rsqrtf((float)fmax(var, 0.0) + ep.norm_eps) * ep.norm_gamma[c];
-          const float b = ep.bias ? ep.bias[c] : 0.f;
-          col_tab[cc] = make_float2(sc, ep.norm_beta[c] + (b - (float)mean) * sc);
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
-      }
-      __syncwarp();
-    }
-    // apply mode: the output tile is staged in shared memory so that global loads (residual) and stores are
-    // row-contiguous.  chunk (row, j) of 16 bytes lives at row * BN * 2 + ((j ^ (row & 7)) << 4).
     constexpr int kRowChunks = BN / 8;  // 16-byte chunks per tile row
     constexpr int kSwz = kRowChunks >= 8 ? 7 : kRowChunks - 1;  // swizzle stays inside the row
-    const int et = ew * 32 + lane;      // epilogue thread 0..127
-    if (ep.norm_stats && ep.norm_resid) {
-      for (int i = et; i < kGemmBM * kRowChunks; i += 128) {
-        const int rr = i / kRowChunks, j = i - rr * kRowChunks;
-        if (m0 + rr < m_rows) {
-          const uint32_t dst = tc::smem_u32(c_tile) + rr * (BN * 2) + ((j ^ (rr & kSwz)) << 4);
-          const __nv_bfloat16* src = ep.norm_resid + c_base + (int64_t)(m0 + rr) * ldc + n0 + j * 8;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    for (int t = 0; t < ntiles; ++t) {
+      const int m0 = (tile0 + t) * kGemmBM;
+      const int buf = t % kAccBufs;
+      const uint32_t use = (uint32_t)(t / kAccBufs);
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * kTmemCols);
+      const int row = m0 + lane_base + lane;
+      const bool row_ok = row < m_rows;
+      const int64_t c_off = c_base + (int64_t)row * ldc + n0;
+      bool gn_uniform = false;
+      int gn_seg = 0, row_seg = 0;
+      double* gn_row_stats = nullptr;
+      // ---- before the accumulators are ready: pair lookup, per-column table of this tile, residual prefetch
+      if (use_gn) {
+        const int last = min(m0 + kGemmBM, m_rows) - 1;
+        gn_seg = segment_of(ep.gn_seg_off, ep.gn_nseg, m0 / ep.gn_rpp);
+        gn_uniform = segment_of(ep.gn_seg_off, ep.gn_nseg, last / ep.gn_rpp) == gn_seg;
+        row_seg = gn_uniform ? gn_seg : segment_of(ep.gn_seg_off, ep.gn_nseg, (row_ok ? row : last) / ep.gn_rpp);
+        if (ep.gn_stats) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) warp_acc[lane * 4 + i] = 0.f;
+          if (!gn_uniform && row_ok) gn_row_stats = ep.gn_stats + (int64_t)row_seg * ep.gn_groups * 2;
         }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    tc::mbar_wait(tmem_full_bar, 0);
-    tc::tcgen05_fence_after_sync();
-    if (ep.norm_stats && ep.norm_resid) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += kEpCols) {
-      uint32_t r[kEpCols];
-      tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0, r);
-      // residual row segment of the apply mode (this thread's own row of the staged tile)
-      uint4 res[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-      const int trow = lane_base + lane;
-      uint8_t* crow = c_tile + trow * (BN * 2);
-      const int cj = c0 / 8;
-      if (ep.norm_stats && ep.norm_resid) {
-        res[0] = *reinterpret_cast<const uint4*>(crow + (((cj) ^ (trow & kSwz)) << 4));
-        res[1] = *reinterpret_cast<const uint4*>(crow + (((cj + 1) ^ (trow & kSwz)) << 4));
-      }
-      tc::tmem_ld_wait();
-      float v[kEpCols];
-#pragma unroll
-      for (int j = 0; j < kEpCols; ++j) {
-        float x = __uint_as_float(r[j]) * ep.alpha;
-        if (ep.bias) x += __ldg(ep.bias + n0 + c0 + j);
-        if (ep.act == 1) x = fmaxf(x, 0.f);
-        v[j] = x;
-      }
-      if (ep.gn_stats) {
-        const int g_glob = (n0 + c0) / cpg, g_loc = g_glob - g_tile0;
-        gn_accumulate_chunk<kEpCols>(cpg, v, row_ok, gn_uniform, lane, warp_acc, g_loc, gn_row_stats, g_glob);
-      }
-      if (ep.norm_stats) {
-        const uint32_t rw[8] = {res[0].x, res[0].y, res[0].z, res[0].w, res[1].x, res[1].y, res[1].z, res[1].w};
-#pragma unroll
-        for (int j = 0; j < kEpCols; ++j) {
-          float x;
-          if (gn_uniform) {
-            const float2 t = col_tab[c0 + j];
-            x = fmaf(__uint_as_float(r[j]), t.x, t.y);
-          } else {  // tile straddles a pair boundary: per-row statistics straight from global memory
-            const int c = n0 + c0 + j;
-            const double cnt = (double)(ep.gn_seg_off[row_seg + 1] - ep.gn_seg_off[row_seg]) * ep.gn_rpp * cpg;
-            const double* st = ep.norm_stats + ((int64_t)row_seg * ep.gn_groups + c / cpg) * 2;
+        if (ep.norm_stats && gn_uniform) {
+          // per-column affine map of this tile: x_norm = acc * scale + shift (bias, mean, rstd, gamma, beta folded)
+          const double cnt = (double)(ep.gn_seg_off[gn_seg + 1] - ep.gn_seg_off[gn_seg]) * ep.gn_rpp * cpg;
+          for (int cc = et; cc < BN; cc += 128) {
+            const int c = n0 + cc;
+            const double* st = ep.norm_stats + ((int64_t)gn_seg * ep.gn_groups + c / cpg) * 2;
             const double mean = st[0] / cnt;
             const double var = st[1] / cnt - mean * mean;
-            const float sc = rsqrtf((float)fmax(var, 0.0) + ep.norm_eps) * __ldg(ep.norm_gamma + c);
-            x = (v[j] - (float)mean) * sc + __ldg(ep.norm_beta + c);
+            const float sc = rsqrtf((float)fmax(var, 0.0) + ep.norm_eps) * ep.norm_gamma[c];
+            const float b = ep.bias ? ep.bias[c] : 0.f;
+            col_tab[cc] = make_float2(sc, ep.norm_beta[c] + (b - (float)mean) * sc);
           }
-          const uint32_t w = rw[j >> 1];
-          x += (j & 1) ? __uint_as_float(w & 0xffff0000u) : __uint_as_float(w << 16);
-          v[j] = fmaxf(x, x * ep.norm_slope);  // LeakyReLU for slope <= 1
         }
-        // result back into the staged tile (same chunks the residual came from)
-#pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * jj], v[8 * jj + 1]);
-          __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * jj + 2], v[8 * jj + 3]);
-          __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * jj + 4], v[8 * jj + 5]);
-          __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * jj + 6], v[8 * jj + 7]);
-          uint4 u;
-          u.x = *reinterpret_cast<uint32_t*>(&p0);
-          u.y = *reinterpret_cast<uint32_t*>(&p1);
-          u.z = *reinterpret_cast<uint32_t*>(&p2);
-          u.w = *reinterpret_cast<uint32_t*>(&p3);
-          *reinterpret_cast<uint4*>(crow + (((cj + jj) ^ (trow & kSwz)) << 4)) = u;
-        }
-        continue;
+        __syncwarp();
       }
-      if (row_ok && ep.transposed) {
-#pragma unroll
-        for (int j = 0; j < kEpCols; ++j)
-          if (n0 + c0 + j < ep.n_valid) ep.out_f32[c_base + (int64_t)(n0 + c0 + j) * ldc + row] = v[j];
-      } else if (row_ok) {
-        if (ep.out_f32) {
-          float4* dst = reinterpret_cast<float4*>(ep.out_f32 + c_off + c0);
-#pragma unroll
-          for (int j = 0; j < kEpCols / 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      // apply mode: the output tile is staged in shared memory so that global loads (residual) and stores are
+      // row-contiguous.  chunk (row, j) of 16 bytes lives at row * BN * 2 + ((j ^ (row & kSwz)) << 4).
+      if (ep.norm_stats && ep.norm_resid) {
+        for (int i = et; i < kGemmBM * kRowChunks; i += 128) {
+          const int rr = i / kRowChunks, j = i - rr * kRowChunks;
+          if (m0 + rr < m_rows) {
+            const uint32_t dst = tc::smem_u32(c_tile) + rr * (BN * 2) + ((j ^ (rr & kSwz)) << 4);
+            const __nv_bfloat16* src = ep.norm_resid + c_base + (int64_t)(m0 + rr) * ldc + n0 + j * 8;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+          }
         }
-        if (ep.out_bf16) {
-          uint4* dst = reinterpret_cast<uint4*>(ep.out_bf16 + c_off + c0);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      tc::mbar_wait(&tmem_full_bar[buf], use & 1);
+      tc::tcgen05_fence_after_sync();
+      if (ep.norm_stats) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // residual tile and column table visible to the 4 warps
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += kEpCols) {
+        uint32_t r[kEpCols];
+        tc::tmem_ld_32x32b_x16(tmem_acc + ((uint32_t)lane_base << 16) + (uint32_t)c0, r);
+        // residual row segment of the apply mode (this thread's own row of the staged tile)
+        uint4 res[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        const int trow = lane_base + lane;
+        uint8_t* crow = c_tile + trow * (BN * 2);
+        const int cj = c0 / 8;
+        if (ep.norm_stats && ep.norm_resid) {
+          res[0] = *reinterpret_cast<const uint4*>(crow + (((cj) ^ (trow & kSwz)) << 4));
+          res[1] = *reinterpret_cast<const uint4*>(crow + (((cj + 1) ^ (trow & kSwz)) << 4));
+        }
+        tc::tmem_ld_wait();
+        if (ep.norm_stats) {
+          const uint32_t rw[8] = {res[0].x, res[0].y, res[0].z, res[0].w, res[1].x, res[1].y, res[1].z, res[1].w};
+          float v[kEpCols];
 #pragma unroll
-          for (int j = 0; j < kEpCols / 8; ++j) {
-            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
-            __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
-            __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+          for (int j = 0; j < kEpCols; ++j) {
+            float x;
+            if (gn_uniform) {
+              const float2 tb = col_tab[c0 + j];
+              x = fmaf(__uint_as_float(r[j]), tb.x, tb.y);
+            } else {  // tile straddles a pair boundary: per-row statistics straight from global memory
+              const int c = n0 + c0 + j;
+              const double cnt = (double)(ep.gn_seg_off[row_seg + 1] - ep.gn_seg_off[row_seg]) * ep.gn_rpp * cpg;
+              const double* st = ep.norm_stats + ((int64_t)row_seg * ep.gn_groups + c / cpg) * 2;
+              const double mean = st[0] / cnt;
+              const double var = st[1] / cnt - mean * mean;
+              const float sc = rsqrtf((float)fmax(var, 0.0) + ep.norm_eps) * __ldg(ep.norm_gamma + c);
+              const float b = ep.bias ? __ldg(ep.bias + c) : 0.f;
+              x = (__uint_as_float(r[j]) + b - (float)mean) * sc + __ldg(ep.norm_beta + c);
+            }
+            const uint32_t w = rw[j >> 1];
+            x += (j & 1) ? __uint_as_float(w & 0xffff0000u) : __uint_as_float(w << 16);
+            v[j] = fmaxf(x, x * ep.norm_slope);  // LeakyReLU for slope <= 1
+          }
+          // result back into the staged tile (same chunks the residual came from)
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * jj], v[8 * jj + 1]);
+            __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * jj + 2], v[8 * jj + 3]);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * jj + 4], v[8 * jj + 5]);
+            __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * jj + 6], v[8 * jj + 7]);
             uint4 u;
             u.x = *reinterpret_cast<uint32_t*>(&p0);
             u.y = *reinterpret_cast<uint32_t*>(&p1);
             u.z = *reinterpret_cast<uint32_t*>(&p2);
             u.w = *reinterpret_cast<uint32_t*>(&p3);
-            dst[j] = u;
+            *reinterpret_cast<uint4*>(crow + (((cj + jj) ^ (trow & kSwz)) << 4)) = u;
+          }
+          continue;
+        }
+        float v[kEpCols];
+#pragma unroll
+        for (int j = 0; j < kEpCols; ++j) {
+          float x = __uint_as_float(r[j]) * ep.alpha;
+          if (ep.bias) x += __ldg(ep.bias + n0 + c0 + j);
+          if (ep.act == 1) x = fmaxf(x, 0.f);
+          v[j] = x;
+        }
+        if (ep.gn_stats) {
+          const int g_glob = (n0 + c0) / cpg, g_loc = g_glob - g_tile0;
+          gn_accumulate_chunk<kEpCols>(cpg, v, row_ok, gn_uniform, lane, warp_acc, g_loc, gn_row_stats, g_glob);
+        }
+        if (row_ok && ep.transposed) {
+#pragma unroll
+          for (int j = 0; j < kEpCols; ++j)
+            if (n0 + c0 + j < ep.n_valid) ep.out_f32[c_base + (int64_t)(n0 + c0 + j) * ldc + row] = v[j];
+        } else if (row_ok) {
+          if (ep.out_f32) {
+            float4* dst = reinterpret_cast<float4*>(ep.out_f32 + c_off + c0);
+#pragma unroll
+            for (int j = 0; j < kEpCols / 4; ++j)
+              dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (ep.out_bf16) {
+            uint4* dst = reinterpret_cast<uint4*>(ep.out_bf16 + c_off + c0);
+#pragma unroll
+            for (int j = 0; j < kEpCols / 8; ++j) {
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]);
+              __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]);
+              __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+              uint4 u;
+              u.x = *reinterpret_cast<uint32_t*>(&p0);
+              u.y = *reinterpret_cast<uint32_t*>(&p1);
+              u.z = *reinterpret_cast<uint32_t*>(&p2);
+              u.w = *reinterpret_cast<uint32_t*>(&p3);
+              dst[j] = u;
+            }
           }
         }
       }
-    }
-    if (ep.norm_stats) {
-      // staged tile -> global memory, row-contiguous 16-byte stores
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = et; i < kGemmBM * kRowChunks; i += 128) {
-        const int rr = i / kRowChunks, j = i - rr * kRowChunks;
-        if (m0 + rr < m_rows)
-          *reinterpret_cast<uint4*>(ep.out_bf16 + c_base + (int64_t)(m0 + rr) * ldc + n0 + j * 8) =
-              *reinterpret_cast<const uint4*>(c_tile + rr * (BN * 2) + ((j ^ (rr & kSwz)) << 4));
-      }
-    }
-    if (ep.gn_stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
-      if (gn_uniform) {
-        const int e = ew * 32 + lane;
-        const int ngr2 = 2 * ((n0 + BN - 1) / cpg - g_tile0 + 1);
-        for (int i = e; i < ngr2; i += 128) {
-          const float t = gn_acc[i] + gn_acc[128 + i] + gn_acc[256 + i] + gn_acc[384 + i];
-          atomicAdd(ep.gn_stats + ((int64_t)gn_seg * ep.gn_groups + g_tile0) * 2 + i, (double)t);
+      // the accumulator buffer may be overwritten by the MMA of tile t + kAccBufs
+      tc::tcgen05_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[buf]);
+      if (ep.norm_stats) {
+        // staged tile -> global memory, row-contiguous 16-byte stores
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = et; i < kGemmBM * kRowChunks; i += 128) {
+          const int rr = i / kRowChunks, j = i - rr * kRowChunks;
+          if (m0 + rr < m_rows)
+            *reinterpret_cast<uint4*>(ep.out_bf16 + c_base + (int64_t)(m0 + rr) * ldc + n0 + j * 8) =
+                *reinterpret_cast<const uint4*>(c_tile + rr * (BN * 2) + ((j ^ (rr & kSwz)) << 4));
         }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // before the next tile's residual lands in the staging tile
+      }
+      if (ep.gn_stats) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+        if (gn_uniform) {
+          const int ngr2 = 2 * ((n0 + BN - 1) / cpg - g_tile0 + 1);
+          for (int i = et; i < ngr2; i += 128) {
+            const float tt = gn_acc[i] + gn_acc[128 + i] + gn_acc[256 + i] + gn_acc[384 + i];
+            atomicAdd(ep.gn_stats + ((int64_t)gn_seg * ep.gn_groups + g_tile0) * 2 + i, (double)tt);
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // accumulators are re-zeroed by the next tile
       }
     }
   }
   tc::tcgen05_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc<kTmemCols>(tmem_base);
+  if (warp == 1) tc::tmem_dealloc<kTmemAlloc>(tmem_base);
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -377,15 +409,24 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmShape s
   using S = GemmSmem<BN>;
   const int num_kb = (shape.K + kGemmBK - 1) / kGemmBK;
   const bool c_tile = ep.norm_stats != nullptr;
-  shape.stages = num_kb < kGemmMaxStages ? num_kb : kGemmMaxStages;
-  while (shape.stages > 1 && S::total(shape.stages, c_tile) > 227 * 1024) --shape.stages;
+  // ring depth: as deep as two co-resident CTAs per SM allow (the ring runs ahead across the CTA's tiles, so it is
+  // useful even when K is a single block), at least 2
+  shape.stages = kGemmMaxStages;
+  while (shape.stages > 2 && S::total(shape.stages, c_tile) > 113 * 1024) --shape.stages;
   const int smem = S::total(shape.stages, c_tile);
   static int configured = 0;
   if (configured < smem) {
     SE3ET_CUDA_CHECK(cudaFuncSetAttribute(gemm_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  dim3 grid((unsigned)ceil_div(shape.M, kGemmBM), (unsigned)(shape.N / BN), (unsigned)batch);
+  // strip of consecutive row tiles per CTA: enough CTAs for ~4 waves of 2 per SM, at most 16 tiles each
+  const int64_t m_tiles = ceil_div(shape.M, kGemmBM);
+  const int64_t n_tiles = shape.N / BN;
+  int64_t tpc = (m_tiles * n_tiles * batch) / ((int64_t)kNumSMs * 8);
+  tpc = tpc < 1 ? 1 : (tpc > 16 ? 16 : tpc);
+  if (shape.groups) tpc = 1;
+  shape.tiles_per_cta = (int)tpc;
+  dim3 grid((unsigned)ceil_div(m_tiles, tpc), (unsigned)n_tiles, (unsigned)batch);
   gemm_tma_kernel<BN><<<grid, kGemmThreads, smem, st>>>(ta, tb, shape, ep);
   SE3ET_LAUNCH_CHECK();
   return SE3ET_OK;
@@ -422,7 +463,7 @@ int gemm_bf16(const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b, int64
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tb, b, b_rows, K, ldb, bn);
   if (rc) return rc;
-  GemmShape shape{M, N, K, a_batch_rows, b_batch_rows, groups, kGemmMaxStages};
+  GemmShape shape{M, N, K, a_batch_rows, b_batch_rows, groups, kGemmMaxStages, 1};
   switch (bn) {
     case 256: return launch_gemm<256>(ta, tb, shape, ep, batch, st);
     case 128: return launch_gemm<128>(ta, tb, shape, ep, batch, st);
