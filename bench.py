@@ -27,6 +27,13 @@ if ROOT not in sys.path:
 
 METRIC = "3dmatch_shape_pairs_per_sec"
 VARIANT = "se3eti.3dmatch"
+WORKLOADS = {
+    # name: (variant, metric, synthetic generator, description)
+    "3dmatch": ("se3eti.3dmatch", "3dmatch_shape_pairs_per_sec", "make_3dmatch_pair",
+                "~15k pts/cloud, voxel 0.025 m, 4 stages"),
+    "kitti": ("se3eti.kitti", "kitti_shape_pairs_per_sec", "make_kitti_pair",
+              "~30k pts/cloud, voxel 0.3 m, 5 stages"),
+}
 
 
 def load_peaks():
@@ -78,10 +85,61 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def make_pairs(count, first=0):
+def make_pairs(count, first=0, generator="make_3dmatch_pair"):
     from se3et_b200 import synthetic
-    pairs = [synthetic.make_3dmatch_pair(first + i) for i in range(count)]
+    pairs = [getattr(synthetic, generator)(first + i) for i in range(count)]
     return [(p["ref_points"], p["src_points"]) for p in pairs]
+
+
+def algorithmic_work(cfg, n_levels, n_ref_c, n_src_c, limits):
+    """Algorithmic work of one pair per entry point: ('hbm', bytes) or ('tensor', flops), from the
+    layer table of the E2PN backbone (se3et_b200/modules/e2pn.py:E2PN) and the transformer shapes.
+    n_levels = stacked point counts per pyramid level, limits = neighbour columns per level."""
+    d = cfg.backbone.init_dim
+    S = cfg.backbone.num_stages
+    conv_flops = hmma_flops = 0.0
+    gemm_flops = gemm_bytes = 0.0
+    apply_bytes = 0.0
+
+    def unary(rows, k, n, resid):
+        nonlocal gemm_flops, gemm_bytes
+        gemm_flops += 2 * 2.0 * rows * k * n                      # statistics pass + apply pass
+        gemm_bytes += 2 * rows * k * 2 + rows * n * 2 * (2 if resid else 1)
+
+    def block(nq, ns, h, cin, cout, strided):
+        nonlocal conv_flops, hmma_flops, apply_bytes
+        mid = cout // 4
+        if cin != mid:
+            unary(6.0 * ns, cin, mid, False)
+        conv_flops += 2.0 * nq * 6 * 36 * mid * mid              # class-pre-summed contraction (issued on tcgen05)
+        hmma_flops += 2.0 * nq * 6 * mid * 16 * 48               # 16-row basis x 48 padded neighbours (mma.sync)
+        apply_bytes += 2 * nq * 6 * mid * (4 + 4) + nq * 6 * mid * (4 + 2)  # two GroupNorm+LeakyReLU passes
+        if cin != cout:
+            unary(6.0 * nq, cin, cout, False)
+        unary(6.0 * nq, mid, cout, True)
+
+    width = 2 * d
+    block(n_levels[0], n_levels[0], limits[0], d, 2 * d, False)
+    for st in range(2, S + 1):
+        l = st - 1
+        block(n_levels[l], n_levels[l - 1], limits[l - 1], width, width, True)
+        block(n_levels[l], n_levels[l], limits[l], width, 2 * width, False)
+        block(n_levels[l], n_levels[l], limits[l], 2 * width, 2 * width, False)
+        width *= 2
+    c = cfg.geotransformer.hidden_dim
+    nn2 = float(n_ref_c ** 2 + n_src_c ** 2)
+    nself = sum(1 for b in cfg.geotransformer.blocks if b == "self_eq")
+    search_bytes = sum(8.0 * n_levels[i] * limits[i] for i in range(S))
+    search_bytes += sum(8.0 * n_levels[i + 1] * limits[i] + 8.0 * n_levels[i] * limits[i + 1] for i in range(S - 1))
+    return {
+        "se3et_kpconv_fused": ("tensor", conv_flops + hmma_flops),
+        "se3et_gemm_bf16_gnstats": ("hbm", gemm_bytes * 0.5), "se3et_gemm_bf16_gnapply": ("hbm", gemm_bytes * 0.5),
+        "se3et_groupnorm_apply": ("hbm", apply_bytes),
+        "se3et_geo_embed_project": ("tensor", 8.0 * nn2 * c * c),
+        "se3et_radius_neighbors": ("hbm", search_bytes + 24.0 * sum(n_levels)),
+        "se3et_gemm_grouped_bf16": ("tensor", nself * 2.0 * nn2 * c * 6 * cfg.geotransformer.num_heads),
+        "se3et_flash_attention": ("tensor", nself * 4.0 * nn2 * c * 6),
+    }
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -117,12 +175,12 @@ def cpu_forward_factory():
     return run, ("reference-c++ precompute + port forward" if impl == "ref_raw" else "port")
 
 
-def run_cpu(steps, warmup, pairs_per_step=1):
+def run_cpu(steps, warmup, pairs_per_step=1, generator="make_3dmatch_pair"):
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     run, kind_note = cpu_forward_factory()
-    clouds = make_pairs(max(1, pairs_per_step))
+    clouds = make_pairs(max(1, pairs_per_step), generator=generator)
     for _ in range(warmup):
         run(*clouds[0])
     t0 = time.perf_counter()
@@ -140,15 +198,17 @@ def reference_arm(args, rank):
         return
     steps, warmup = max(1, args.steps), min(args.warmup, 1)
     steps = min(steps, 4)  # each step is one full pair through the CPU path (several seconds)
-    value, dt, cores, note, done = run_cpu(steps, warmup)
+    value, dt, cores, note, done = run_cpu(steps, warmup, generator=WORKLOADS[args.workload][2])
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SE3ET-I 3DMatch-shaped inference, 1 synthetic pair per step (bounded sample of the "
-                               "64-pair batch), random-init weights", "variant": VARIANT},
+        "config": {"workload": "SE3ET-I %s-shaped inference, 1 synthetic pair per step (bounded sample of the "
+                               "%d-pair batch; %s), random-init weights" % (args.workload, args.pairs,
+                                                                           WORKLOADS[args.workload][3]),
+                   "variant": VARIANT},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
-                         "sample": "%d synthetic 3DMatch-shaped pair(s): %s, torch threads = %d" % (done, note, cores)},
+                         "sample": "%d synthetic %s-shaped pair(s): %s, torch threads = %d" % (done, args.workload, note, cores)},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -165,7 +225,11 @@ def main():
     ap.add_argument("--pairs-per-launch", type=int, default=16, help="pairs stacked into one launch sequence")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic pairs generated (cycled)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="3dmatch", choices=sorted(WORKLOADS),
+                    help="3dmatch = BASELINE.json configs[1] (the headline); kitti = configs[3]")
     args = ap.parse_args()
+    global VARIANT, METRIC
+    VARIANT, METRIC, generator, shape_note = WORKLOADS[args.workload]
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -190,9 +254,12 @@ def main():
     torch.manual_seed(0)
     model = create_model(cfg).to(dev).eval()
 
-    # synthetic pairs: `distinct` different ones, cycled to `pairs` (pair i of rank r is seed 1000 + (r*pairs+i) % distinct)
-    distinct = make_pairs(min(args.distinct, args.pairs), first=0)
-    clouds = [distinct[(rank * args.pairs + i) % len(distinct)] for i in range(args.pairs)]
+    # the job is world * pairs synthetic pairs per step, sharded round-robin by pair (pair i -> rank i mod world, no
+    # collective on the data path); `distinct` different pairs are generated and cycled
+    from se3et_b200 import sharding
+    distinct = make_pairs(min(args.distinct, args.pairs), first=0, generator=generator)
+    mine = sharding.pairs_for_rank(world * args.pairs, rank, world)
+    clouds = [distinct[i % len(distinct)] for i in mine]
     ppl = max(1, min(args.pairs_per_launch, args.pairs))
     groups = [clouds[i:i + ppl] for i in range(0, len(clouds), ppl)]
     dev_inputs = []
@@ -225,8 +292,10 @@ def main():
     barrier()
 
     # ---- timed region: K steps, CUDA events, per-entry-point events for the roofline
-    timed_names = ["se3et_kpconv_gather", "se3et_gemm_bf16", "se3et_groupnorm_apply", "se3et_groupnorm_stats",
-                   "se3et_radius_neighbors", "se3et_geo_embed_project", "se3et_flash_attention"]
+    timed_names = ["se3et_kpconv_fused", "se3et_kpconv_gather", "se3et_gemm_bf16", "se3et_gemm_bf16_gnstats",
+                   "se3et_gemm_bf16_gnapply", "se3et_gemm_grouped_bf16", "se3et_groupnorm_apply",
+                   "se3et_groupnorm_stats", "se3et_maxpool_nbr", "se3et_radius_neighbors", "se3et_grid_subsample",
+                   "se3et_geo_embed_project", "se3et_flash_attention", "se3et_superpoint_matching"]
     L.enabled = True
     L.reset(timed=timed_names)
     sampler = ClockSampler(local_rank)
@@ -268,16 +337,17 @@ def main():
     if rank == 0:
         peaks = load_peaks()
         # dominant entry point by summed device time inside the timed region
-        dom = max(per_api, key=lambda n: per_api[n][0])
-        dom_ms, dom_calls = per_api[dom]
         pair_units = args.pairs * args.steps  # pairs processed by this rank in the timed region
-        # algorithmic work per pair (DESIGN.md "Kernels"): bytes or flops
-        ALG = {
-            "se3et_radius_neighbors": ("hbm", 27.8e6), "se3et_groupnorm_apply": ("hbm", 0.62e9),
-            "se3et_groupnorm_stats": ("hbm", 0.41e9), "se3et_kpconv_gather": ("hbm", 1.9e9 + 3.4e9 / 2),
-            "se3et_gemm_bf16": ("tensor", (139.3 + 46.5 + 30.0) * 1e9), "se3et_geo_embed_project": ("tensor", 135e9),
-            "se3et_flash_attention": ("tensor", 6.2e9),
-        }
+        # algorithmic work per pair from the layer table and the measured pyramid
+        pts0, lens0 = dev_inputs[0]
+        dd = model.forward_stacked(pts0, lens0)["data_dict"]
+        npair = lens0.shape[0] // 2
+        n_levels = [float(p.shape[0]) / npair for p in dd["points"]]
+        lc = dd["lengths"][-1].cpu().numpy()
+        ALG = algorithmic_work(cfg, n_levels, float(lc[0::2].mean()), float(lc[1::2].mean()), cfg.neighbor_limits)
+        timed = {n: v for n, v in per_api.items() if n in ALG}
+        dom = max(timed, key=lambda n: timed[n][0])
+        dom_ms, dom_calls = per_api[dom]
         bound, per_pair = ALG[dom]
         if bound == "hbm":
             achieved = per_pair * pair_units / (dom_ms / 1e3) / 1e9
@@ -288,19 +358,24 @@ def main():
         roofline = {"kernel": dom, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
                     "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"],
                     "share_of_step": dom_ms / ms, "calls": dom_calls,
-                    "per_entry_point_ms": {n: round(v[0], 3) for n, v in per_api.items()}}
+                    "per_entry_point_ms": {n: round(v[0], 3) for n, v in per_api.items()},
+                    # achieved / measured peak of every entry point with a work model (same formula as `frac`)
+                    "per_entry_point_frac": {
+                        n: round(ALG[n][1] * pair_units / (per_api[n][0] / 1e3) /
+                                 ((peaks["hbm_gbs"] * 1e9) if ALG[n][0] == "hbm" else (peaks["bf16_tflops"] * 1e12)), 4)
+                        for n in timed if per_api[n][0] > 0}}
         cpu = None
         if not args.no_cpu_baseline:
-            v, dt, cores, note, done = run_cpu(2, 1)
+            v, dt, cores, note, done = run_cpu(2, 1, generator=generator)
             cpu = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
-                   "sample": "%d synthetic 3DMatch-shaped pairs of the same workload (%s), torch threads = %d, %.1f s"
+                   "sample": "%d synthetic pairs of the same workload (%s), torch threads = %d, %.1f s"
                              % (done, note, cores, dt)}
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "SE3ET-I 3DMatch-shaped inference, batch of %d synthetic pairs per GPU per step "
-                                   "(~15k pts/cloud, voxel 0.025 m, 4 stages), random-init weights" % args.pairs,
+            "config": {"workload": "SE3ET-I %s-shaped inference, batch of %d synthetic pairs per GPU per step "
+                                   "(%s), random-init weights" % (args.workload, args.pairs, shape_note),
                        "variant": VARIANT, "pairs_per_gpu_per_step": args.pairs, "pairs_per_launch": ppl,
                        "distinct_pairs": len(distinct), "parallelism": "pairs sharded over %d GPU(s), no collective" % world,
                        "l2": "working set per launch (activations of %d stacked pairs, > 1 GB) exceeds the 126 MB L2" % ppl},

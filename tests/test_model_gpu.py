@@ -1,0 +1,92 @@
+"""End-to-end GPU parity of the wired model (se3et_b200/model.py) against the torch-CPU oracle of the whole path
+(oracle/points.py precompute -> oracle/e2pn.py backbone -> oracle/transformer.py transformer + matching), on small
+synthetic pairs so that the oracle finishes in seconds.  bf16 operands: coarse features are compared by cosine
+similarity, correspondences by top-k overlap (end-to-end correspondences are not bit-exact in bf16)."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from oracle import e2pn as oe
+from oracle import points as op
+from oracle import transformer as ot
+from se3et_b200 import synthetic
+from se3et_b200.model import create_model, make_cfg
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def oracle_forward(cfg, sd, ref, src):
+    b, g = cfg.backbone, cfg.geotransformer
+    pts = np.concatenate([ref, src])
+    lens = np.array([len(ref), len(src)])
+    d = op.precompute_data_stack_mode(pts, lens, b.num_stages, b.init_voxel_size, b.init_radius, cfg.neighbor_limits,
+                                      impl="oracle")
+    with torch.no_grad():
+        fl = oe.e2pn_forward(sd, torch.ones(len(pts), 1), d, b.init_sigma, b.group_norm)
+        n = int(d["lengths"][-1][0])
+        pc = torch.from_numpy(d["points"][-1])
+        r, s, _, _ = ot.geometric_transformer(sd, pc[:n], pc[n:], fl[-1][:n], fl[-1][n:], g.blocks, g.hidden_dim,
+                                              g.num_heads, g.sigma_d, g.sigma_a, g.angle_k)
+        r = torch.nn.functional.normalize(r, p=2, dim=1)
+        s = torch.nn.functional.normalize(s, p=2, dim=1)
+        ri, si, sc = ot.superpoint_matching(r, s, torch.ones(len(r), dtype=torch.bool), torch.ones(len(s), dtype=torch.bool),
+                                            cfg.coarse_matching.num_correspondences)
+    return d, fl, r, s, ri, si, sc
+
+
+def build(variant):
+    cfg = make_cfg(variant)
+    torch.manual_seed(0)
+    model = create_model(cfg)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    return cfg, model.to(DEV).eval(), sd
+
+
+def min_cos(a, b):
+    return torch.nn.functional.cosine_similarity(a.float().cpu(), b.float().cpu(), dim=-1).min().item()
+
+
+@pytest.mark.parametrize("variant,crop", [("se3eti2.3dmatch", 0.9), ("se3eti.3dmatch", 0.7)])
+def test_pair_forward_matches_oracle(variant, crop):
+    cfg, model, sd = build(variant)
+    p = synthetic.make_3dmatch_pair(13, crop=crop)
+    d, fl, r, s, ri, si, sc = oracle_forward(cfg, sd, p["ref_points"], p["src_points"])
+    out = model.forward_pairs([(p["ref_points"], p["src_points"])])
+    res = model.forward_stacked(torch.from_numpy(np.concatenate([p["ref_points"], p["src_points"]])).to(DEV),
+                                torch.tensor([len(p["ref_points"]), len(p["src_points"])]))
+    for k in ("points", "neighbors", "subsampling", "upsampling"):
+        for a, b in zip(d[k], res["data_dict"][k]):
+            assert np.array_equal(a, b.cpu().numpy()), k  # the pyramid is bit-exact
+    assert min_cos(res["feats_f"], fl[0]) > 0.99
+    assert min_cos(res["ref_feats_c"], r) > 0.98 and min_cos(res["src_feats_c"], s) > 0.98
+    got = set(zip(out[0][0].tolist(), out[0][1].tolist()))
+    want = set(zip(ri.tolist(), si.tolist()))
+    assert len(got) == len(want)
+    assert len(got & want) >= 0.85 * len(want), len(got & want) / len(want)
+
+
+def test_kitti_shaped_five_stage_forward_matches_oracle():
+    cfg, model, sd = build("se3eti.kitti")
+    p = synthetic.make_kitti_pair(3, target_points=6000)
+    d, fl, r, s, ri, si, sc = oracle_forward(cfg, sd, p["ref_points"], p["src_points"])
+    assert len(d["points"]) == 5
+    res = model.forward_stacked(torch.from_numpy(np.concatenate([p["ref_points"], p["src_points"]])).to(DEV),
+                                torch.tensor([len(p["ref_points"]), len(p["src_points"])]))
+    for k in ("points", "neighbors", "subsampling", "upsampling"):
+        for a, b in zip(d[k], res["data_dict"][k]):
+            assert np.array_equal(a, b.cpu().numpy()), k
+    assert min_cos(res["feats_f"], fl[0]) > 0.99
+    assert min_cos(res["ref_feats_c"], r) > 0.98 and min_cos(res["src_feats_c"], s) > 0.98
+
+
+def test_batched_pairs_equal_single_pairs():
+    cfg, model, _ = build("se3eti2.3dmatch")
+    pairs = [synthetic.make_3dmatch_pair(i, crop=0.9) for i in (3, 5, 13)]
+    clouds = [(p["ref_points"], p["src_points"]) for p in pairs]
+    together = model.forward_pairs(clouds)
+    for c, t in zip(clouds, together):
+        alone = model.forward_pairs([c])[0]
+        a, b = set(zip(alone[0].tolist(), alone[1].tolist())), set(zip(t[0].tolist(), t[1].tolist()))
+        assert len(a & b) >= 0.9 * len(a), len(a & b) / len(a)
