@@ -81,3 +81,44 @@ def test_superpoint_matching_matches_reference(gold):
     assert np.array_equal(ri.numpy()[distinct], gold["spm_ref_idx"][distinct])
     assert np.array_equal(si.numpy()[distinct], gold["spm_src_idx"][distinct])
     assert not (set(ri.tolist()) & {3}) and not (set(si.tolist()) & {0, 7})  # masked superpoints never appear
+
+
+# ---- SE3ET-E block list (cross_a_soft / cross_r_soft / invariant self + cross), fixture from the reference ----------
+BLOCKS_E = ['self_eq', 'cross_a_soft', 'self_eq', 'cross_r_soft', 'self', 'cross']
+
+
+@pytest.fixture(scope="module")
+def gold_e(golden_dir):
+    return np.load(os.path.join(golden_dir, "model_e_small.npz"))
+
+
+def transformer_e_state_dict(gold_e, prefix="transformer."):
+    """Seeded parameters under the reference's own key names (shapes recorded in the fixture)."""
+    sd = {}
+    for item in gold_e["param_shapes"]:
+        name, shape = str(item).split(":")
+        if helpers.is_constant(name) or "anchors" in name:
+            continue
+        shape = tuple(int(v) for v in shape.split(",")) if shape else ()
+        sd[prefix + name] = helpers.seeded_tensor("transformer_e." + name, shape)
+    return sd
+
+
+def test_rotation_permutations_match_reference(gold_e):
+    ours = {tuple(r) for r in ot.octahedral_rotation_perms().tolist()}
+    ref = {tuple(r) for r in gold_e["trace_idx_ori"].tolist()}
+    assert ours == ref and len(ours) == 24
+    from se3et_b200.modules import octahedral
+    assert np.allclose(octahedral.tables()["anchors"], np.transpose(gold_e["anchors_embedding"], (0, 2, 1)), atol=1e-6)
+
+
+@pytest.mark.parametrize("tag,nlev", [("nosh", 0), ("sh", 2)])
+def test_transformer_e_matches_reference(gold, gold_e, tag, nlev):
+    S = helpers.SMALL_CFG
+    rp, sp, rf, sf = coarse_inputs(gold)
+    sd = transformer_e_state_dict(gold_e)
+    anchors = torch.from_numpy(np.transpose(gold_e["anchors_embedding"], (0, 2, 1)).copy()).float()
+    r, s = ot.geometric_transformer_eq(sd, rp, sp, rf, sf, BLOCKS_E, S["hidden_dim"], S["num_heads"], S["sigma_d"],
+                                       S["sigma_a"], S["angle_k"], anchors, n_level_equiv=nlev)
+    assert torch.allclose(r, torch.from_numpy(gold_e["ref_feats_" + tag]), rtol=1e-3, atol=2e-4)
+    assert torch.allclose(s, torch.from_numpy(gold_e["src_feats_" + tag]), rtol=1e-3, atol=2e-4)
