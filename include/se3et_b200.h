@@ -232,6 +232,37 @@ int se3et_flash_attention(const void* q, int64_t q_pt, int64_t q_an, const void*
                           const void* v, int64_t v_pt, int64_t v_an, const float* bias, const int64_t* problems,
                           int64_t num_problems, int64_t max_q, int64_t anchors, int64_t heads, int64_t head_dim,
                           float scale, void* out_bf16, int64_t ldo, se3et_stream_t stream);
+/* ---- SE3ET-E: MultiHeadAttentionEQ in the modes a_soft / r_soft (vanilla_transformer.py:87-870) ----------------
+ * The local scores S[a,e,h,n,m] = q_a . k_e / sqrt(c) are never materialised: the global anchor statistics come
+ * from anchor_pair_stats, the per-(a, e) attentions from se3et_flash_attention (one launch per key anchor e), their
+ * weighted sum over e from anchor_mix.  problems = the attention problem table {q_start, n_q, kv_start, n_kv, -}. */
+
+/* g[p][a][e] = sum_{n,m} f( q_a[n] . k_e[m] * scale ), scale = 1 / (heads * sqrt(head_dim)) (head-mean of the local
+ * scores, vanilla_transformer.py:380-431); positive: 0 'sq', 1 'softplus', 2 'sigmoid', 3 'relu', 4 'abs'.
+ * g is zeroed by the call; channels in {64, 128, 256}. */
+int se3et_anchor_pair_stats(const void* q_bf16, int64_t q_pt, int64_t q_an, const void* k_bf16, int64_t k_pt,
+                            int64_t k_an, const int64_t* problems, int64_t num_problems, int64_t max_q,
+                            int64_t anchors, int64_t channels, float scale, int positive, float* g,
+                            se3et_stream_t stream);
+/* w[p][a][e]: r_soft = 0: g / (n m) normalised over e (a_soft, :466-476); r_soft = 1: rotation weights
+ * attn_r[r] = mean_a g[a][perms[r][a]] normalised over r (:560-575; optional output [p][num_rotations]) folded to
+ * w[a][e] = sum_{r : perms[r][a] == e} attn_r[r].  perms = trace_idx_ori, int32 [num_rotations][anchors]. */
+int se3et_anchor_mix_weights(const float* g, const int64_t* problems, int64_t num_problems, const int32_t* perms,
+                             int64_t num_rotations, int64_t anchors, int r_soft, float* w, float* attn_r,
+                             se3et_stream_t stream);
+/* out[(n, a)][c] = sum_e w[cloud(n)][a][e] * in[e * stride_e + n * stride_n + a * stride_a + c]  (bf16; strides in
+ * elements; cloud_offsets: nclouds + 1 point offsets of the query side).  Serves the sum over key anchors of the
+ * per-(a, e) attention outputs (:812-818) and eq2inv_soft (conditional_transformer.py:209-249). */
+int se3et_anchor_mix(const void* in_bf16, int64_t stride_e, int64_t stride_n, int64_t stride_a, const float* w,
+                     const int64_t* cloud_offsets, int64_t nclouds, int64_t anchors, int64_t channels,
+                     int64_t n_points, void* out_bf16, se3et_stream_t stream);
+/* Equivariant (spherical-harmonics, l = 1) score term of the equivariant self attention (rpe_transformer.py:76-79,
+ * geotransformer.py:57-67): bias[bias_off + ((i A + a) H + h) n + m] += c1 * (anchors[a]^T unit(p_i - p_m)) .
+ * u[((q_start + i) A + a) ldu + 3 h ..], u = q W_eq[:, 1:4] per head.  The l = 0 part is constant along m. */
+int se3et_sh_bias_add(const float* points, const int64_t* problems, int64_t num_problems, int64_t max_n,
+                      const float* u, int64_t ldu, const float* anchors_Ax3x3, int64_t anchors, int64_t heads, float c1,
+                      float* bias, se3et_stream_t stream);
+
 /* LayerNorm(x + resid[row / resid_div]) (rpe_transformer.py:161-163, vanilla_transformer.py:908-911 with the
  * (N, C) -> (A, N, C) residual broadcast, output_layer.py:16-22). x fp32 [rows, channels], resid bf16 or NULL. */
 int se3et_add_layernorm(const float* x, const void* resid_bf16, int64_t resid_div, int64_t rows, int64_t channels,

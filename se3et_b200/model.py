@@ -37,7 +37,12 @@ _VARIANTS = {
     'se3eti.3dmatch': (64, 32, 256, 256, 256, 4, 0.025, 2.5, 0.2, [38, 36, 36, 38]),
     'se3eti2.3dmatch': (32, 16, 128, 128, 128, 4, 0.025, 2.5, 0.2, [38, 36, 36, 38]),
     'se3eti.kitti': (64, 32, 256, 128, 256, 5, 0.3, 4.25, 4.8, [40, 40, 40, 40, 40]),
+    'se3ete.3dmatch': (64, 32, 256, 256, 256, 4, 0.025, 2.5, 0.2, [38, 36, 36, 38]),
+    'se3ete2.3dmatch': (32, 16, 128, 128, 128, 4, 0.025, 2.5, 0.2, [38, 36, 36, 38]),
 }
+_BLOCKS_I = ['self_eq', 'cross', 'self_eq', 'cross', 'self_eq', 'cross']
+# experiments/se3ete.3dmatch/config.py:194
+_BLOCKS_E = ['self_eq', 'cross_a_soft', 'self_eq', 'cross_r_soft', 'self', 'cross', 'self', 'cross', 'self', 'cross']
 
 
 def make_cfg(variant='se3eti.3dmatch'):
@@ -45,6 +50,7 @@ def make_cfg(variant='se3eti.3dmatch'):
         raise NotImplementedError("variant %r: the CUDA path covers %s" % (variant, sorted(_VARIANTS)))
     d, g, bo, hid, to, stages, voxel, base_r, sigma_d, limits = _VARIANTS[variant]
     c = Cfg(variant=variant)
+    is_e = variant.startswith('se3ete')
     c.backbone = Cfg(num_stages=stages, init_voxel_size=voxel, kernel_size=15, base_radius=base_r, base_sigma=2.0,
                      init_radius=base_r * voxel, init_sigma=2.0 * voxel, group_norm=g, input_dim=1, init_dim=d,
                      output_dim=bo)
@@ -54,10 +60,12 @@ def make_cfg(variant='se3eti.3dmatch'):
                 use_batch_norm=True, batch_norm_momentum=0.99, KP_extent=1.0, KP_influence='linear',
                 aggregation_mode='sum')
     c.geotransformer = Cfg(input_dim=d * (16 if stages == 4 else 32), hidden_dim=hid, output_dim=to, num_heads=4,
-                           blocks=['self_eq', 'cross', 'self_eq', 'cross', 'self_eq', 'cross'], sigma_d=sigma_d,
+                           blocks=list(_BLOCKS_E if is_e else _BLOCKS_I), sigma_d=sigma_d,
                            sigma_a=15, angle_k=3, supervise_rotation=False, reduction_a='max', align_mode='0',
-                           alternative_impl=False, n_level_equiv=0, attn_r_positive='softplus',
-                           attn_r_positive_rot_supervise='minus')
+                           alternative_impl=False, n_level_equiv=2 if is_e else 0,
+                           # SE3ET-E's model.py does not pass attn_r_positive*: the module defaults apply
+                           attn_r_positive='sq' if is_e else 'softplus',
+                           attn_r_positive_rot_supervise='sigmoid' if is_e else 'minus')
     c.coarse_matching = Cfg(num_targets=128, overlap_threshold=0.1, num_correspondences=256, dual_normalization=True)
     c.neighbor_limits = list(limits)  # demo.py:52 for 3DMatch; KITTI limits are calibrated per dataset (data.py:212-252)
     return c

@@ -103,3 +103,49 @@ def superpoint_matching(ref_feats, src_feats, ref_masks, src_masks, problems, ma
         int(bool(dual_normalization)), _lib.ptr(e), _lib.ptr(rs), _lib.ptr(cs), _lib.ptr(ri), _lib.ptr(si), _lib.ptr(sc),
         _lib.ptr(cnt), _lib.stream_ptr()), "superpoint_matching")
     return ri, si, sc, cnt, e
+
+
+# ---- SE3ET-E -----------------------------------------------------------------------------------------------------
+POSITIVE = {"sq": 0, "softplus": 1, "sigmoid": 2, "relu": 3, "abs": 4}
+
+
+def anchor_pair_stats(q, q_pt, q_an, k, k_pt, k_an, problems, max_q, anchors, channels, heads, positive):
+    """g (P, A, A) fp32 = sum over point pairs of f(head-mean local score); see se3et_anchor_pair_stats."""
+    g = torch.empty((problems.shape[0], anchors, anchors), dtype=torch.float32, device=q.device)
+    scale = 1.0 / (heads * (channels // heads) ** 0.5)
+    _lib.check(_lib.lib().se3et_anchor_pair_stats(
+        _lib.ptr(q), _lib.i64(q_pt), _lib.i64(q_an), _lib.ptr(k), _lib.i64(k_pt), _lib.i64(k_an), _lib.ptr(problems),
+        _lib.i64(problems.shape[0]), _lib.i64(max_q), _lib.i64(anchors), _lib.i64(channels), _lib.f32(scale),
+        int(POSITIVE[positive]), _lib.ptr(g), _lib.stream_ptr()), "anchor_pair_stats")
+    return g
+
+
+def anchor_mix_weights(g, problems, perms, r_soft):
+    """-> (w (P, A, A) fp32, attn_r (P, R) fp32 or None)."""
+    p, a, _ = g.shape
+    w = torch.empty_like(g)
+    attn_r = torch.empty((p, perms.shape[0]), dtype=torch.float32, device=g.device) if r_soft else None
+    _lib.check(_lib.lib().se3et_anchor_mix_weights(
+        _lib.ptr(g), _lib.ptr(problems), _lib.i64(p), _lib.ptr(perms), _lib.i64(perms.shape[0]), _lib.i64(a),
+        int(bool(r_soft)), _lib.ptr(w), _lib.ptr(attn_r), _lib.stream_ptr()), "anchor_mix_weights")
+    return w, attn_r
+
+
+def anchor_mix(x, stride_e, stride_n, stride_a, w, cloud_off, anchors, channels, n_points):
+    """out (n_points * A, C) bf16 = sum_e w[cloud(n)][a][e] * x[e * stride_e + n * stride_n + a * stride_a + :]."""
+    out = torch.empty((n_points * anchors, channels), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.lib().se3et_anchor_mix(
+        _lib.ptr(x), _lib.i64(stride_e), _lib.i64(stride_n), _lib.i64(stride_a), _lib.ptr(w), _lib.ptr(cloud_off),
+        _lib.i64(cloud_off.numel() - 1), _lib.i64(anchors), _lib.i64(channels), _lib.i64(n_points), _lib.ptr(out),
+        _lib.stream_ptr()), "anchor_mix")
+    return out
+
+
+def sh_bias_add(points, problems, max_n, u, anchors_mat, heads, c1, bias):
+    """bias += l = 1 spherical-harmonics score term; u fp32 (rows, ldu) with 3 values per head."""
+    a = anchors_mat.shape[0]
+    _lib.check(_lib.lib().se3et_sh_bias_add(
+        _lib.ptr(points), _lib.ptr(problems), _lib.i64(problems.shape[0]), _lib.i64(max_n), _lib.ptr(u),
+        _lib.i64(u.stride(0)), _lib.ptr(anchors_mat), _lib.i64(a), _lib.i64(heads), _lib.f32(c1), _lib.ptr(bias),
+        _lib.stream_ptr()), "sh_bias_add")
+    return bias

@@ -90,3 +90,37 @@ def test_batched_pairs_equal_single_pairs():
         alone = model.forward_pairs([c])[0]
         a, b = set(zip(alone[0].tolist(), alone[1].tolist())), set(zip(t[0].tolist(), t[1].tolist()))
         assert len(a & b) >= 0.9 * len(a), len(a & b) / len(a)
+
+
+def test_se3et_e_forward_matches_oracle():
+    """BASELINE.json configs[2]: SE3ET-E (equivariant + invariant self / cross attention) on a ~5k-point pair."""
+    cfg, model, sd = build("se3ete2.3dmatch")
+    p = synthetic.make_3dmatch_pair(13, crop=1.5)
+    ref, src = p["ref_points"], p["src_points"]
+    b, g = cfg.backbone, cfg.geotransformer
+    pts, lens = np.concatenate([ref, src]), np.array([len(ref), len(src)])
+    d = op.precompute_data_stack_mode(pts, lens, b.num_stages, b.init_voxel_size, b.init_radius, cfg.neighbor_limits,
+                                      impl="oracle")
+    from se3et_b200.modules import octahedral
+    anchors = torch.tensor(octahedral.tables()["anchors"], dtype=torch.float32)
+    with torch.no_grad():
+        fl = oe.e2pn_forward(sd, torch.ones(len(pts), 1), d, b.init_sigma, b.group_norm)
+        n = int(d["lengths"][-1][0])
+        pc = torch.from_numpy(d["points"][-1])
+        r, s = ot.geometric_transformer_eq(sd, pc[:n], pc[n:], fl[-1][:n], fl[-1][n:], g.blocks, g.hidden_dim,
+                                           g.num_heads, g.sigma_d, g.sigma_a, g.angle_k, anchors,
+                                           n_level_equiv=g.n_level_equiv, positive=g.attn_r_positive)
+        r = torch.nn.functional.normalize(r, p=2, dim=1)
+        s = torch.nn.functional.normalize(s, p=2, dim=1)
+        ri, si, _ = ot.superpoint_matching(r, s, torch.ones(len(r), dtype=torch.bool), torch.ones(len(s), dtype=torch.bool),
+                                           cfg.coarse_matching.num_correspondences)
+    res = model.forward_stacked(torch.from_numpy(pts).to(DEV), torch.from_numpy(lens))
+    assert min_cos(res["ref_feats_c"], r) > 0.97 and min_cos(res["src_feats_c"], s) > 0.97
+    out = model.forward_pairs([(ref, src)])[0]
+    got, want = set(zip(out[0].tolist(), out[1].tolist())), set(zip(ri.tolist(), si.tolist()))
+    assert len(got & want) >= 0.8 * len(want), len(got & want) / len(want)
+    # two pairs in one launch sequence use per-pair anchor statistics
+    q = synthetic.make_3dmatch_pair(3, crop=0.9)
+    both = model.forward_pairs([(ref, src), (q["ref_points"], q["src_points"])])
+    again = set(zip(both[0][0].tolist(), both[0][1].tolist()))
+    assert len(again & got) >= 0.9 * len(got)

@@ -197,3 +197,71 @@ def test_superpoint_selection_is_exact_on_its_own_scores():
         assert torch.equal(ri[p, :k], order // m) and torch.equal(si[p, :k], order % m)
         assert torch.allclose(sc[p, :k], score.reshape(-1)[order], rtol=1e-5)
         assert (ri[p, k:] == -1).all()
+
+
+# ---- SE3ET-E block list on the CUDA path --------------------------------------------------------------------------
+BLOCKS_E = ['self_eq', 'cross_a_soft', 'self_eq', 'cross_r_soft', 'self', 'cross']
+
+
+@pytest.fixture(scope="module")
+def gold_e(golden_dir):
+    return np.load(os.path.join(golden_dir, "model_e_small.npz"))
+
+
+def test_anchor_statistics_and_mixing_match_torch():
+    """anchor_pair_stats / anchor_mix_weights / anchor_mix against the dense torch formulation, two problems."""
+    from se3et_b200.ops import transformer_ops as T
+    from oracle import transformer as ot
+    g = torch.Generator().manual_seed(5)
+    a, c, h = 6, 64, 4
+    nq, nk = [37, 70], [50, 21]
+    q = (torch.randn(sum(nq), a, c, generator=g) * 0.5).bfloat16()
+    k = (torch.randn(sum(nk), a, c, generator=g) * 0.5).bfloat16()
+    qo, ko = np.concatenate([[0], np.cumsum(nq)]), np.concatenate([[0], np.cumsum(nk)])
+    problems = torch.tensor([[qo[i], nq[i], ko[i], nk[i], 0] for i in range(2)], dtype=torch.int64, device=DEV)
+    perms = ot.octahedral_rotation_perms()
+    qd, kd = q.to(DEV).view(-1, c), k.to(DEV).view(-1, c)
+    for positive in ("sq", "softplus"):
+        got = T.anchor_pair_stats(qd, a * c, c, kd, a * c, c, problems, max(nq), a, c, h, positive).cpu()
+        for i in range(2):
+            qq, kk = q[qo[i]:qo[i + 1]].float(), k[ko[i]:ko[i + 1]].float()
+            s = torch.einsum("nac,mec->aenm", qq, kk) / (h * (c // h) ** 0.5)
+            want = (s ** 2 if positive == "sq" else torch.nn.functional.softplus(s)).sum((-2, -1))
+            assert torch.allclose(got[i], want, rtol=2e-3, atol=1e-3), positive
+            for r_soft in (False, True):
+                w, attn_r = T.anchor_mix_weights(got.to(DEV), problems, perms.to(torch.int32).to(DEV), r_soft)
+                ww, ar = ot.anchor_mixing_weights(want / (nq[i] * nk[i]), "r_soft" if r_soft else "a_soft", perms)
+                assert torch.allclose(w[i].cpu(), ww, rtol=2e-3, atol=1e-5)
+                if r_soft:
+                    assert torch.allclose(attn_r[i].cpu(), ar, rtol=2e-3, atol=1e-6)
+    w = torch.rand(2, a, a, generator=g)
+    x = torch.randn(a, sum(nq), a, c, generator=g).bfloat16()
+    cloud_off = torch.tensor(qo, dtype=torch.int64, device=DEV)
+    out = T.anchor_mix(x.to(DEV), sum(nq) * a * c, a * c, c, w.to(DEV), cloud_off, a, c, sum(nq)).cpu().float()
+    wn = torch.cat([w[0][None].expand(nq[0], -1, -1), w[1][None].expand(nq[1], -1, -1)])  # (n, a, e)
+    want = torch.einsum("nae,enac->nac", wn, x.float()).reshape(-1, c)
+    assert torch.allclose(out, want, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("tag,nlev", [("nosh", 0), ("sh", 2)])
+def test_transformer_e_matches_oracle_and_reference(gold, gold_e, tag, nlev):
+    """GeometricTransformer with the SE3ET-E schedule (bf16 tensor cores) vs the fp32 oracle and the reference fixture."""
+    from test_oracle_transformer import coarse_inputs, transformer_e_state_dict
+    from oracle import transformer as ot
+    S = helpers.SMALL_CFG
+    rp, sp, rf, sf = coarse_inputs(gold)
+    sd = transformer_e_state_dict(gold_e, prefix="")
+    if nlev == 0:
+        sd = {k: v for k, v in sd.items() if "proj_eq" not in k}
+    tr = MT.GeometricTransformer(16 * S["init_dim"], S["tr_output_dim"], S["hidden_dim"], S["num_heads"], BLOCKS_E,
+                                 S["sigma_d"], S["sigma_a"], S["angle_k"], na=6, n_level_equiv=nlev)
+    missing, unexpected = tr.load_state_dict(sd, strict=False)
+    assert not unexpected and all(("anchors" in k or "trace_idx" in k or "div_term" in k) for k in missing), missing
+    tr = tr.to(DEV).eval()
+    with torch.no_grad():
+        r, s, *_ = tr(rp[None].to(DEV), sp[None].to(DEV), rf[None].to(DEV), sf[None].to(DEV))
+    want_r, want_s = torch.from_numpy(gold_e["ref_feats_" + tag]), torch.from_numpy(gold_e["src_feats_" + tag])
+    cos = torch.nn.functional.cosine_similarity
+    assert cos(r[0].float().cpu(), want_r, dim=-1).min() > 0.99
+    assert cos(s[0].float().cpu(), want_s, dim=-1).min() > 0.99
+    assert rel_err(r[0].float().cpu(), want_r) < 5e-2 and rel_err(s[0].float().cpu(), want_s) < 5e-2
