@@ -3,14 +3,14 @@
 // gathered operand A' (kpconv_tables.cuh) lives only in shared memory.
 //
 // Persistent CTA, tile = 16 query points = 96 operand rows (p, r) of a UMMA M = 128 tile:
-//   warps 0-7  producers, 2 points each.  Per point: the 16 x H basis weight matrix W16 (bf16 A fragments kept in
-//              registers for the whole tile).  Per (point, 16-channel chunk, input anchor): cp.async gather of the
-//              neighbour rows x[idx[n]][a][chunk] (32 B sectors, 4-stage ring per warp), mma.sync m16n8k16
+//   warps 0-15 producers, one point each.  Per point: the 16 x H basis weight matrix W16 (bf16 A fragments kept in
+//              registers for the whole tile).  Per (16-channel chunk, input anchor): cp.async gather of the
+//              neighbour rows x[idx[n]][a][chunk] (32 B sectors, 3-stage ring per warp), mma.sync m16n8k16
 //              W16 . X, and every accumulator element is stored once (twice .. six times for its (r, kc) copies) as
 //              bf16 into the 128-byte-swizzled K-major operand tile the tensor core reads.
-//   warp 8     tcgen05.mma issuer: per chunk 9 K-blocks of 64 (36 (kc, a') slots x 16 channels) against the weight
+//   warp 16    tcgen05.mma issuer: per chunk 9 K-blocks of 64 (36 (kc, a') slots x 16 channels) against the weight
 //              K-blocks, fp32 accumulation in TMEM across all chunks of the tile.
-//   warp 9     TMA producer of the weight K-blocks (3-stage mbarrier ring).
+//   warp 17    TMA producer of the weight K-blocks (3-stage mbarrier ring).
 //   warps 0-3  epilogue after their production: tcgen05.ld, fp32 rows to global memory, GroupNorm statistics.
 // The operand tile is single-buffered (9 x 12 KB): the MMA of chunk i and the production of chunk i + 1 alternate,
 // while gathers and the next tile's weights run ahead.
@@ -27,12 +27,13 @@ using namespace kpm;
 
 constexpr int kFPts = 16;                     // points per tile
 constexpr int kFRows = kFPts * kA;            // 96 operand rows
-constexpr int kFProdWarps = 8;                // 2 points each
+constexpr int kFProdWarps = 16;               // one point each
 constexpr int kFThreads = (kFProdWarps + 2) * 32;
 constexpr int kFKBlocks = 9;                  // 36 slots x 16 channels = 576 = 9 x 64
 constexpr int kFKBlockBytes = kFRows * 128;   // 12288, a multiple of the 1024-byte swizzle period
-constexpr int kFStages = 4;                   // gather ring per warp, item = (point, chunk, anchor)
-constexpr int kFXRow = 48;                    // bytes per gathered row: 16 channels bf16 + 16 pad (conflict-free ldmatrix)
+constexpr int kFStages = 3;                   // gather ring per warp, item = (chunk, anchor)
+constexpr int kFXRow = 32;                    // bytes per gathered row: 16 channels bf16; the two 16-byte halves of row n
+                                              // are swapped when (n / 4) is odd -> conflict-free ldmatrix
 constexpr int kFWMaxStages = 18;             // weight K-block ring: as many stages as fit (two chunks at most)
 constexpr int kFKS = 3;                       // neighbour k-steps of 16 (H <= 48)
 constexpr int kFW16Row = (kFKS * 16 + 8) * 2; // 112 bytes
@@ -157,86 +158,70 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
 #pragma unroll
     for (int u = 0; u < 3; ++u) {
       const int i = lane + 32 * u;
-      gdst[u] = xs_s + (i >> 1) * kFXRow + (i & 1) * 16;
+      const int n = i >> 1;
+      gdst[u] = xs_s + n * kFXRow + (((i & 1) ^ ((n >> 2) & 1)) << 4);
     }
-    // per-tile state (registers): A fragments of the two points' basis weights, gather source pointers
-    uint32_t afrag[2][kFKS][4];
-    const __nv_bfloat16* gsrc[2][3];
-    uint32_t gvalid = 0;  // bit pt * 3 + u: the piece reads a real neighbour (else zero fill)
+    // per-tile state (registers): A fragments of this warp's point's basis weights, gather source pointers
+    uint32_t afrag[kFKS][4];
+    const __nv_bfloat16* gsrc[3];
+    uint32_t gvalid = 0;  // bit u: the piece reads a real neighbour (else zero fill)
 
     auto setup = [&](int64_t tile) {
-      float qp[2][3];
-      bool pvalid[2];
-#pragma unroll
-      for (int pt = 0; pt < 2; ++pt) {
-        const int64_t p = tile * kFPts + 2 * warp + pt;
-        pvalid[pt] = p < args.nq;
-        const int64_t pc = pvalid[pt] ? p : 0;
-        qp[pt][0] = args.q_pts[3 * pc]; qp[pt][1] = args.q_pts[3 * pc + 1]; qp[pt][2] = args.q_pts[3 * pc + 2];
-      }
+      const int64_t p = tile * kFPts + warp;
+      const bool pvalid = p < args.nq;
+      const int64_t pc = pvalid ? p : 0;
+      const float qx = args.q_pts[3 * pc], qy = args.q_pts[3 * pc + 1], qz = args.q_pts[3 * pc + 2];
       gvalid = 0;
 #pragma unroll
-      for (int pt = 0; pt < 2; ++pt) {
-        const int64_t pc = pvalid[pt] ? tile * kFPts + 2 * warp + pt : 0;
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
-          const int i = lane + 32 * u, n = i >> 1;
-          int64_t j = (pvalid[pt] && n < H) ? args.idx[pc * H + n] : -1;
-          const bool valid = j >= 0 && j < args.ns;
-          gsrc[pt][u] = args.x + (valid ? j : 0) * (int64_t)(kA * cin) + (i & 1) * 8;
-          gvalid |= (valid ? 1u : 0u) << (pt * 3 + u);
-        }
-      }
-      // W16 scratch for both points aliases the head of the gather ring: [pt][16][kFW16Row]
-      for (int i = lane; i < 2 * 16 * kFW16Row / 16; i += 32) reinterpret_cast<uint4*>(xs)[i] = make_uint4(0, 0, 0, 0);
-      __syncwarp();
-      // the 2 H (point, neighbour) pairs spread over the lanes: slot i = lane + 32 it
-#pragma unroll
-      for (int it = 0; it < 3; ++it) {
-        const int i = lane + 32 * it;
-        const int pt = i >= H ? 1 : 0, n = i - pt * H;
-        const bool active = i < 2 * H && (pt ? pvalid[1] : pvalid[0]);
-        const int64_t pc = active ? tile * kFPts + 2 * warp + pt : 0;
-        int64_t j = active ? args.idx[pc * H + n] : -1;
+      for (int u = 0; u < 3; ++u) {
+        const int i = lane + 32 * u, n = i >> 1;
+        int64_t j = (pvalid && n < H) ? args.idx[pc * H + n] : -1;
         const bool valid = j >= 0 && j < args.ns;
-        if (!valid) j = 0;
-        const float dx = args.s_pts[3 * j] - (pt ? qp[1][0] : qp[0][0]);
-        const float dy = args.s_pts[3 * j + 1] - (pt ? qp[1][1] : qp[0][1]);
-        const float dz = args.s_pts[3 * j + 2] - (pt ? qp[1][2] : qp[0][2]);
-        if (valid) {  // shadow / padding neighbours keep their zero weights
-          float row[16];
-          basis_weights(dx, dy, dz, sh_kp, args.inv_extent, true, row);
-          uint8_t* dst = xs + pt * 16 * kFW16Row + n * 2;
+        gsrc[u] = args.x + (valid ? j : 0) * (int64_t)(kA * cin) + (i & 1) * 8;
+        gvalid |= (valid ? 1u : 0u) << u;
+      }
+      // W16 scratch aliases the head of the gather ring: [16][kFW16Row]
+      for (int i = lane; i < 16 * kFW16Row / 16; i += 32) reinterpret_cast<uint4*>(xs)[i] = make_uint4(0, 0, 0, 0);
+      __syncwarp();
 #pragma unroll
-          for (int r = 0; r < 16; ++r) *reinterpret_cast<__nv_bfloat16*>(dst + r * kFW16Row) = __float2bfloat16(row[r]);
+      for (int it = 0; it < 2; ++it) {
+        const int n = lane + 32 * it;
+        if (it == 0 || n < H) {
+          int64_t j = (pvalid && n < H) ? args.idx[pc * H + n] : -1;
+          const bool valid = j >= 0 && j < args.ns;
+          if (valid) {  // shadow / padding neighbours keep their zero weights
+            float row[16];
+            basis_weights(args.s_pts[3 * j] - qx, args.s_pts[3 * j + 1] - qy, args.s_pts[3 * j + 2] - qz, sh_kp,
+                          args.inv_extent, true, row);
+            uint8_t* dst = xs + n * 2;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) *reinterpret_cast<__nv_bfloat16*>(dst + r * kFW16Row) = __float2bfloat16(row[r]);
+          }
         }
       }
       __syncwarp();
 #pragma unroll
-      for (int pt = 0; pt < 2; ++pt)
-#pragma unroll
-        for (int ks = 0; ks < kFKS; ++ks)
-          ldmatrix_x4(afrag[pt][ks], xs_s + pt * 16 * kFW16Row + ld_row * kFW16Row + (ks * 16 + ld_half * 8) * 2);
+      for (int ks = 0; ks < kFKS; ++ks)
+        ldmatrix_x4(afrag[ks], xs_s + ld_row * kFW16Row + (ks * 16 + ld_half * 8) * 2);
       __syncwarp();
       // gather rows >= H must read as zero again
-      for (int i = lane; i < 2 * 16 * kFW16Row / 16; i += 32) reinterpret_cast<uint4*>(xs)[i] = make_uint4(0, 0, 0, 0);
+      for (int i = lane; i < 16 * kFW16Row / 16; i += 32) reinterpret_cast<uint4*>(xs)[i] = make_uint4(0, 0, 0, 0);
       __syncwarp();
     };
 
-    auto issue = [&](int chunk, int pt, int a, int stage) {
+    auto issue = [&](int chunk, int a, int stage) {
       const int off = a * cin + chunk * kChunk;
 #pragma unroll
       for (int u = 0; u < 3; ++u) {
-        if (lane + 32 * u < 2 * H)
-          cp_async_16(gdst[u] + stage * xstage, gsrc[pt][u] + off, (gvalid >> (pt * 3 + u)) & 1u ? 16 : 0);
+        if (lane + 32 * u < 2 * H) cp_async_16(gdst[u] + stage * xstage, gsrc[u] + off, (gvalid >> u) & 1u ? 16 : 0);
       }
     };
+    // item (chunk, a) occupies ring stage a % 3 (6 % 3 == 0); the ring runs two items ahead
     auto prologue = [&]() {
-#pragma unroll
-      for (int e = 0; e < 3; ++e) {
-        issue(0, e / 6, e % 6, e % kFStages);
-        cp_async_commit();
-      }
+      issue(0, 0, 0);
+      cp_async_commit();
+      issue(0, 1, 1);
+      cp_async_commit();
     };
 
     uint32_t gc = 0;       // chunks produced so far (all tiles): parity of the operand-tile barriers
@@ -245,36 +230,35 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
       setup(blockIdx.x);
       prologue();
     }
+    const uint32_t mbase = warp * kA;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++titer) {
       for (int chunk = 0; chunk < nchunks; ++chunk) {
 #pragma unroll
-        for (int e = 0; e < 12; ++e) {
-          const int pt = e / 6, a = e % 6;
-          {  // prefetch item e + 3 (possibly of the next chunk)
-            const int e2 = (e + 3) % 12;
-            const int chunk2 = chunk + (e + 3) / 12;
-            if (chunk2 < nchunks) issue(chunk2, e2 / 6, e2 % 6, (e + 3) % kFStages);
+        for (int a = 0; a < kA; ++a) {
+          {  // prefetch the item two ahead (possibly of the next chunk)
+            const int a2 = (a + 2) % kA;
+            const int chunk2 = chunk + (a + 2) / kA;
+            if (chunk2 < nchunks) issue(chunk2, a2, a2 % kFStages);
             cp_async_commit();
           }
-          cp_async_wait<3>();
+          cp_async_wait<2>();
           __syncwarp();
-          if (e == 0) {
+          if (a == 0) {
             tc::mbar_wait(a_empty, (gc & 1) ^ 1);  // the MMA of the previous chunk has consumed the operand tile
           }
-          const uint32_t xsb = xs_s + (e % kFStages) * xstage;
           float d[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+          const uint32_t xsb = xs_s + (a % kFStages) * xstage;
 #pragma unroll
           for (int ks = 0; ks < kFKS; ++ks) {
             const int n = ks * 16 + ld_row;
             uint32_t b[4];
-            ldmatrix_x4_trans(b, n < HR ? xsb + n * kFXRow + ld_half * 16 : zero_s);
-            mma_16816(d[0], afrag[pt][ks], b[0], b[1]);
-            mma_16816(d[1], afrag[pt][ks], b[2], b[3]);
+            ldmatrix_x4_trans(b, n < HR ? xsb + n * kFXRow + ((ld_half ^ ((n >> 2) & 1)) << 4) : zero_s);
+            mma_16816(d[0], afrag[ks], b[0], b[1]);
+            mma_16816(d[1], afrag[ks], b[2], b[3]);
           }
           // accumulator rows g / g + 8 = basis rows; each is copied to its (r, kc) targets:
-          // operand row m = (2 warp + pt) * 6 + r, slot j = kc * 6 + ridx[a][r], K-block j / 4, 16-byte chunk
+          // operand row m = warp * 6 + r, slot j = kc * 6 + ridx[a][r], K-block j / 4, 16-byte chunk
           // (j % 4) * 2 + nt, swizzled by (m % 8)
-          const uint32_t mbase = (2 * warp + pt) * kA;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -300,7 +284,7 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
             }
           }
           __syncwarp();  // every lane is done with this ring stage and its stores are issued
-          if (e == 11) {
+          if (a == kA - 1) {
             tc::fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(a_full);
