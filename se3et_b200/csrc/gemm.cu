@@ -71,8 +71,11 @@ struct GemmSmem {
   static int total(int stages, bool c_tile) { return stages * kStageBytes + 5120 + (c_tile ? kCBytes : 0) + 1024; }
 };
 
-template <int BN>
-__global__ void __launch_bounds__(kGemmThreads, (BN <= 128 ? 2 : 1))
+// kMulti = true : strips of row tiles per CTA, double-buffered accumulators (long K: the ring hides the load latency)
+// kMulti = false: one tile per CTA, <= 112 registers so that three CTAs share an SM (K of one or two blocks: the
+//                 epilogue dominates and more resident epilogue warps win)
+template <int BN, bool kMulti>
+__global__ void __launch_bounds__(kGemmThreads, (kMulti ? (BN <= 128 ? 2 : 1) : (BN <= 128 ? 3 : 2)))
 gemm_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, GemmShape shape,
                 GemmEpilogue ep) {
   using S = GemmSmem<BN>;
@@ -107,9 +110,9 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     if (tile0 * kGemmBM >= m_rows) return;  // uniform for the whole CTA, before any barrier / TMEM allocation
   }
   // tiles this CTA owns: [tile0, tile0 + ntiles)
-  const int ntiles = min(shape.tiles_per_cta, (m_rows - tile0 * kGemmBM + kGemmBM - 1) / kGemmBM);
+  const int ntiles = kMulti ? min(shape.tiles_per_cta, (m_rows - tile0 * kGemmBM + kGemmBM - 1) / kGemmBM) : 1;
   // two accumulator buffers when they fit TMEM next to a co-resident CTA (epilogue of tile t under the MMA of t + 1)
-  constexpr int kAccBufs = BN <= 128 ? 2 : 1;
+  constexpr int kAccBufs = (kMulti && BN <= 128) ? 2 : 1;
   constexpr uint32_t kTmemAlloc = kTmemCols * kAccBufs;
 
   if (threadIdx.x == 0) {
@@ -403,33 +406,44 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t 
   return SE3ET_OK;
 }
 
-template <int BN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, GemmShape shape, const GemmEpilogue& ep,
-                       int batch, cudaStream_t st) {
+template <int BN, bool kMulti>
+static int launch_gemm_variant(const CUtensorMap& ta, const CUtensorMap& tb, GemmShape shape, const GemmEpilogue& ep,
+                               int batch, int max_smem, cudaStream_t st) {
   using S = GemmSmem<BN>;
   const int num_kb = (shape.K + kGemmBK - 1) / kGemmBK;
   const bool c_tile = ep.norm_stats != nullptr;
-  // ring depth: as deep as two co-resident CTAs per SM allow (the ring runs ahead across the CTA's tiles, so it is
-  // useful even when K is a single block), at least 2
-  shape.stages = kGemmMaxStages;
-  while (shape.stages > 2 && S::total(shape.stages, c_tile) > 113 * 1024) --shape.stages;
+  // ring depth: as deep as the co-resident CTAs allow; the strip variant keeps the ring running across its tiles
+  shape.stages = kMulti ? kGemmMaxStages : (num_kb < kGemmMaxStages ? num_kb : kGemmMaxStages);
+  while (shape.stages > (kMulti ? 2 : 1) && S::total(shape.stages, c_tile) > max_smem) --shape.stages;
   const int smem = S::total(shape.stages, c_tile);
   static int configured = 0;
   if (configured < smem) {
-    SE3ET_CUDA_CHECK(cudaFuncSetAttribute(gemm_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SE3ET_CUDA_CHECK(cudaFuncSetAttribute(gemm_tma_kernel<BN, kMulti>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          smem));
     configured = smem;
   }
-  // strip of consecutive row tiles per CTA: enough CTAs for ~4 waves of 2 per SM, at most 16 tiles each
   const int64_t m_tiles = ceil_div(shape.M, kGemmBM);
   const int64_t n_tiles = shape.N / BN;
-  int64_t tpc = (m_tiles * n_tiles * batch) / ((int64_t)kNumSMs * 8);
-  tpc = tpc < 1 ? 1 : (tpc > 16 ? 16 : tpc);
-  if (shape.groups) tpc = 1;
+  int64_t tpc = 1;
+  if (kMulti && !shape.groups) {
+    // strip of consecutive row tiles per CTA: enough CTAs for ~4 waves of 2 per SM, at most 16 tiles each
+    tpc = (m_tiles * n_tiles * batch) / ((int64_t)kNumSMs * 8);
+    tpc = tpc < 1 ? 1 : (tpc > 16 ? 16 : tpc);
+  }
   shape.tiles_per_cta = (int)tpc;
   dim3 grid((unsigned)ceil_div(m_tiles, tpc), (unsigned)n_tiles, (unsigned)batch);
-  gemm_tma_kernel<BN><<<grid, kGemmThreads, smem, st>>>(ta, tb, shape, ep);
+  gemm_tma_kernel<BN, kMulti><<<grid, kGemmThreads, smem, st>>>(ta, tb, shape, ep);
   SE3ET_LAUNCH_CHECK();
   return SE3ET_OK;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& shape, const GemmEpilogue& ep,
+                       int batch, cudaStream_t st) {
+  const int num_kb = (shape.K + kGemmBK - 1) / kGemmBK;
+  if (num_kb <= 2 && !shape.groups)  // short K: three (BN <= 128) or two single-tile CTAs per SM
+    return launch_gemm_variant<BN, false>(ta, tb, shape, ep, batch, (BN <= 128 ? 75 : 113) * 1024, st);
+  return launch_gemm_variant<BN, true>(ta, tb, shape, ep, batch, (BN <= 128 ? 113 : 227) * 1024, st);
 }
 
 int pick_bn(int n) {

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kEmbThreads) geo_embed_indices_kernel(const fl
 //   warps 2-5: generate sin/cos (A operand, written straight into the 128B-swizzled smem tile), then epilogue
 // ---------------------------------------------------------------------------------------------
 constexpr int kEpStages = 2;
-constexpr int kEpThreads = 192;
+constexpr int kEpThreads = 320;  // TMA warp, MMA warp, 8 producer / epilogue warps (2 per TMEM lane quadrant)
 __constant__ float c_div_term[512];  // exp(-2j ln(1e4) / C), j < C/2
 
 template <int BN>
@@ -150,7 +150,7 @@ geo_embed_project_kernel(const __grid_constant__ CUtensorMap tma_wd, const __gri
     tc::tma_prefetch_desc(&tma_wd);
     tc::tma_prefetch_desc(&tma_wa);
     for (int s = 0; s < kEpStages; ++s) {
-      tc::mbar_init(&full_bar[s], 1 + 128);  // TMA thread (expect_tx) + 128 producer threads
+      tc::mbar_init(&full_bar[s], 1 + 256);  // TMA thread (expect_tx) + 256 producer threads
       tc::mbar_init(&empty_bar[s], 1);
     }
     tc::mbar_init(tmem_full_bar, 1);
@@ -200,6 +200,7 @@ geo_embed_project_kernel(const __grid_constant__ CUtensorMap tma_wd, const __gri
   } else {
     const int lane_base = (warp & 3) * 32;
     const int trow = lane_base + lane;  // tile row == TMEM lane
+    const int half = (warp - 2) >> 2;   // the two warps of a lane quadrant split the sinusoid chunks / output columns
     const int64_t row = r0 + trow;
     float x[4] = {0.f, 0.f, 0.f, 0.f};
     if (row < rows) {
@@ -214,7 +215,7 @@ geo_embed_project_kernel(const __grid_constant__ CUtensorMap tma_wd, const __gri
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {  // 16-byte chunk j: frequencies kb*32 + 4j .. +3, interleaved (sin, cos)
+        for (int j = 4 * half; j < 4 * half + 4; ++j) {  // 16-byte chunk j: frequencies kb*32 + 4j .. +3, (sin, cos)
           uint32_t w[4];
 #pragma unroll
           for (int f = 0; f < 4; ++f) {
@@ -237,7 +238,7 @@ geo_embed_project_kernel(const __grid_constant__ CUtensorMap tma_wd, const __gri
     tc::mbar_wait(tmem_full_bar, 0);
     tc::tcgen05_fence_after_sync();
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
+    for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 16) {
       uint32_t d[16], a0[16], a1[16], a2[16];
       const uint32_t t0 = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c0;
       tmem_ld_32x32b_x16(t0, d);
