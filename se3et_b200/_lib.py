@@ -25,7 +25,7 @@ _lib = None
 # kernels launched by one call of each entry point (cudaMemsetAsync nodes are not counted)
 KERNELS_PER_CALL = {
     "se3et_grid_subsample": 16, "se3et_radius_neighbors": 9, "se3et_gemm_bf16": 1, "se3et_gemm_bf16_gnstats": 1, "se3et_gemm_bf16_gnapply": 1, "se3et_gemm_grouped_bf16": 1,
-    "se3et_kpconv_gather": 1, "se3et_kpconv_fused": 1, "se3et_groupnorm_stats": 1, "se3et_groupnorm_apply": 1, "se3et_maxpool_nbr": 1,
+    "se3et_kpconv_gather": 1, "se3et_kpconv_fused": 1, "se3et_groupnorm_stats": 1, "se3et_groupnorm_apply": 1, "se3et_groupnorm_double": 1, "se3et_maxpool_nbr": 1,
     "se3et_anchor_max": 1, "se3et_upsample_concat": 1, "se3et_geo_embed_indices": 1, "se3et_geo_embed_project": 1,
     "se3et_flash_attention": 1, "se3et_add_layernorm": 1, "se3et_l2_normalize_rows": 1,
     "se3et_superpoint_matching": 3, "se3et_anchor_pair_stats": 1, "se3et_anchor_mix_weights": 1,
@@ -136,13 +136,14 @@ def require_cuda(*tensors):
 
 
 class Workspace:
-    """Grow-only per-device scratch buffer handed to the C ABI."""
+    """Grow-only scratch buffer handed to the C ABI, one per (device, CUDA stream): launch sequences running
+    concurrently on different streams must not share scratch memory."""
 
     def __init__(self):
         self._buf = {}
 
     def get(self, nbytes, device):
-        key = (device.type, device.index)
+        key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
         buf = self._buf.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)

@@ -300,6 +300,79 @@ __global__ void __launch_bounds__(256) groupnorm_apply_rows_kernel(NormSide a, N
 }
 
 
+// Two GroupNorm + LeakyReLU stages back to back (KPConvInterSO3Block's norm followed by the enclosing block's
+// norm, blocks_epn.py:737-741 + 790-794 / 841-843) without materialising the intermediate:
+//   f = LeakyReLU(GN_1(y)),  out = LeakyReLU(GN_2(f))
+// pass A (kApply = false): accumulates the statistics of f per (pair, group) into stats2 (fp64 atomics)
+// pass B (kApply = true) : recomputes f and writes out (bf16)
+template <bool kApply>
+__global__ void __launch_bounds__(256) groupnorm_double_kernel(NormSide a, NormSide b2, double* __restrict__ stats2_acc,
+                                                                int64_t rows, int C, int cpg,
+                                                                const int64_t* __restrict__ seg_off, int nseg,
+                                                                int rows_per_point, float eps, float slope,
+                                                                __nv_bfloat16* __restrict__ out_bf16) {
+  const int V = C >> 2;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (int)(tid % V) * 4;
+  const int64_t row_step = (int64_t)gridDim.x * blockDim.x / V;
+  const int G = C / cpg;
+  int seg = -1;
+  int64_t seg_end = 0;
+  NormCols n1, n2;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+  auto flush = [&]() {
+    if (kApply || seg < 0) return;
+    double* dst = stats2_acc + (int64_t)seg * G * 2;
+    if (cpg >= 4) {  // the four columns share one group
+      atomicAdd(dst + 2 * (c0 / cpg), (double)((s[0] + s[1]) + (s[2] + s[3])));
+      atomicAdd(dst + 2 * (c0 / cpg) + 1, (double)((ss[0] + ss[1]) + (ss[2] + ss[3])));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        atomicAdd(dst + 2 * ((c0 + j) / cpg), (double)s[j]);
+        atomicAdd(dst + 2 * ((c0 + j) / cpg) + 1, (double)ss[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[j] = ss[j] = 0.f;
+  };
+  for (int64_t row = tid / V; row < rows; row += row_step) {
+    if (row >= seg_end) {
+      flush();
+      if (seg < 0) seg = segment_of(seg_off, nseg, row / rows_per_point);
+      while (seg + 1 < nseg && seg_off[seg + 1] * rows_per_point <= row) ++seg;
+      seg_end = seg_off[seg + 1] * rows_per_point;
+      if (seg == nseg - 1) seg_end = rows;
+      const double cnt = (double)(seg_off[seg + 1] - seg_off[seg]) * rows_per_point * cpg;
+      load_norm_cols(a, seg, G, cpg, c0, cnt, eps, n1);
+      if (kApply) load_norm_cols(b2, seg, G, cpg, c0, cnt, eps, n2);
+    }
+    const float4 ya = __ldcs(reinterpret_cast<const float4*>(a.y + row * C + c0));
+    float v[4] = {(ya.x - n1.mean[0]) * n1.s[0] + n1.beta[0], (ya.y - n1.mean[1]) * n1.s[1] + n1.beta[1],
+                  (ya.z - n1.mean[2]) * n1.s[2] + n1.beta[2], (ya.w - n1.mean[3]) * n1.s[3] + n1.beta[3]};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = v[j] >= 0.f ? v[j] : v[j] * slope;
+    if (!kApply) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[j] += v[j];
+        ss[j] = fmaf(v[j], v[j], ss[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float w = (v[j] - n2.mean[j]) * n2.s[j] + n2.beta[j];
+        v[j] = w >= 0.f ? w : w * slope;
+      }
+      uint2 o;
+      o.x = pack_bf16(v[0], v[1]);
+      o.y = pack_bf16(v[2], v[3]);
+      *reinterpret_cast<uint2*>(out_bf16 + row * C + c0) = o;
+    }
+  }
+  flush();
+}
+
 // out[q][col] = max_n xpad[idx[q][n]][col]; shadow neighbours contribute 0 (blocks.py:100-109)
 __global__ void __launch_bounds__(256) maxpool_nbr_kernel(const __nv_bfloat16* __restrict__ x, int64_t ns, int width,
                                                            const int64_t* __restrict__ idx, int H_full,
@@ -513,6 +586,37 @@ extern "C" int se3et_upsample_concat(const void* x_bf16, int64_t nx, int64_t c1,
   upsample_concat_kernel<<<elementwise_blocks(n * (c1 + c2) / 2), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x_bf16), nx, (int)c1, up_idx, (int)up_ld,
       static_cast<const __nv_bfloat16*>(y_bf16), (int)c2, n, static_cast<__nv_bfloat16*>(out_bf16));
+  SE3ET_LAUNCH_CHECK();
+  return SE3ET_OK;
+}
+
+extern "C" int se3et_groupnorm_double(const float* y, const double* stats1, const float* gamma1, const float* beta1,
+                                      double* stats2, const float* gamma2, const float* beta2, int64_t rows,
+                                      int64_t channels, int64_t groups, const int64_t* seg_offsets, int64_t nseg,
+                                      int64_t rows_per_point, float eps, float leaky_slope, int apply, void* out_bf16,
+                                      se3et_stream_t stream) {
+  if (rows < 0 || channels <= 0 || channels % 4 || groups <= 0 || channels % groups || nseg <= 0 ||
+      rows_per_point <= 0 || !seg_offsets || !stats2)
+    return SE3ET_ERR_ARG;
+  const int64_t vecs = channels / 4;
+  if (vecs > 256 || (vecs & (vecs - 1)) != 0) return SE3ET_ERR_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!apply) SE3ET_CUDA_CHECK(cudaMemsetAsync(stats2, 0, sizeof(double) * 2 * nseg * groups, st));
+  if (rows == 0) return SE3ET_OK;
+  if (!y || !stats1 || !gamma1 || !beta1 || (apply && (!gamma2 || !beta2 || !out_bf16))) return SE3ET_ERR_ARG;
+  int64_t blocks = ceil_div(rows * vecs, 256);
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  if (blocks > cap) blocks = cap;
+  NormSide a{y, stats1, gamma1, beta1};
+  NormSide b{nullptr, stats2, gamma2, beta2};
+  const int cpg = (int)(channels / groups);
+  if (apply)
+    groupnorm_double_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(
+        a, b, stats2, rows, (int)channels, cpg, seg_offsets, (int)nseg, (int)rows_per_point, eps, leaky_slope,
+        static_cast<__nv_bfloat16*>(out_bf16));
+  else
+    groupnorm_double_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(
+        a, b, stats2, rows, (int)channels, cpg, seg_offsets, (int)nseg, (int)rows_per_point, eps, leaky_slope, nullptr);
   SE3ET_LAUNCH_CHECK();
   return SE3ET_OK;
 }

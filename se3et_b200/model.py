@@ -147,6 +147,45 @@ class GeoTransformer(nn.Module):
         }
 
     @torch.no_grad()
+    def forward_stacked_concurrent(self, inputs, num_streams=2):
+        """Runs several launch sequences (`inputs` = [(points, lengths), ...] as for forward_stacked) concurrently,
+        one host thread + CUDA stream per sequence slot: pairs are independent, and a second sequence fills the SMs
+        while the first sits in a latency-bound kernel or a host-side size read-back.  Returns the list of results."""
+        import threading
+        dev = inputs[0][0].device
+        if num_streams <= 1 or len(inputs) <= 1:
+            return [self.forward_stacked(p, l) for p, l in inputs]
+        if not hasattr(self, '_streams') or len(self._streams) < num_streams:
+            self._streams = [torch.cuda.Stream(device=dev) for _ in range(num_streams)]
+        results = [None] * len(inputs)
+        errors = []
+        start = torch.cuda.Event()
+        start.record(torch.cuda.current_stream(dev))
+
+        def worker(slot):
+            try:
+                torch.cuda.set_device(dev)
+                st = self._streams[slot]
+                st.wait_event(start)
+                with torch.cuda.stream(st), torch.no_grad():
+                    for i in range(slot, len(inputs), num_streams):
+                        results[i] = self.forward_stacked(*inputs[i])
+            except Exception as e:  # surfaced in the caller
+                errors.append(e)
+
+        threads = [threading.Thread(target=worker, args=(s,)) for s in range(num_streams)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        cur = torch.cuda.current_stream(dev)
+        for st in self._streams[:num_streams]:
+            cur.wait_stream(st)
+        return results
+
+    @torch.no_grad()
     def forward_pairs(self, clouds, pinned=None):
         """Public end-to-end entry: clouds = [(ref (n,3) float32 ndarray, src (m,3) float32 ndarray), ...] on the HOST.
         Copies the stacked points to the GPU (from pinned memory), runs the whole hot path and returns the

@@ -22,7 +22,7 @@ from . import octahedral
 
 
 # switches for A/B measurements and tests (the defaults are the product path)
-_GFLAGS = {'fused_kpconv': True, 'two_pass_unary': True}
+_GFLAGS = {'fused_kpconv': True, 'two_pass_unary': True, 'double_norm': True}
 
 
 def _gn_fusable_fused(cout, groups):
@@ -270,6 +270,21 @@ class KPConvInterSO3Block(nn.Module):
         return out.view(-1, self.conv.kanchor, self.out_dim)
 
 
+def _conv_double_norm(interso3, norm2, x, q_pts, s_pts, neighb_inds, seg):
+    """conv -> GroupNormEPN -> LeakyReLU (KPConvInterSO3Block) -> GroupNormEPN -> LeakyReLU (enclosing block), bf16 out.
+    The conv kernel delivers the first statistics; the intermediate activation is never written."""
+    n1 = interso3.norm
+    c = interso3.out_dim
+    if _GFLAGS['double_norm'] and K.groupnorm_double_supported(c) and n1.num_groups == norm2.num_groups and \
+            n1.norm.eps == norm2.norm.eps and q_pts.shape[0] > 0:
+        y, stats = interso3.conv.forward_stats(q_pts, s_pts, neighb_inds, x, n1.num_groups, seg)
+        return K.groupnorm_double(y.view(-1, c), stats, n1.norm.weight, n1.norm.bias, norm2.norm.weight,
+                                  norm2.norm.bias, n1.num_groups, seg, 6, slope=0.1, eps=n1.norm.eps)
+    f, _ = interso3.fused(x, q_pts, s_pts, neighb_inds, seg, out_f32=True)
+    _, out = norm2.fused(f, seg, 6, slope=0.1)
+    return out
+
+
 class SimpleBlockEPN(nn.Module):
     """blocks_epn.py:770-796: interso3 block, then a second GroupNormEPN + LeakyReLU."""
 
@@ -285,8 +300,7 @@ class SimpleBlockEPN(nn.Module):
 
     def forward(self, x, q_pts, s_pts, neighb_inds, seg=None):
         seg = _seg(seg, q_pts.shape[0], q_pts.device)
-        y, _ = self.interso3.fused(x, q_pts, s_pts, neighb_inds, seg, out_f32=True)
-        _, out = self.norm.fused(y, seg, 6, slope=0.1)
+        out = _conv_double_norm(self.interso3, self.norm, x, q_pts, s_pts, neighb_inds, seg)
         return out.view(-1, 6, self.out_dim)
 
 
@@ -326,8 +340,7 @@ class ResnetBottleneckBlockEPN(nn.Module):
             y = self.unary1(x, seg=s_seg)
         else:
             y = x
-        f, _ = self.interso3.fused(y, q_pts, s_pts, neighb_inds, seg, out_f32=True)
-        _, y = self.norm.fused(f, seg, 6, slope=0.1)
+        y = _conv_double_norm(self.interso3, self.norm, y, q_pts, s_pts, neighb_inds, seg)
         if 'strided' in self.block_name:
             skip = K.maxpool_nbr(skip, neighb_inds.contiguous(), seg if sub_width is not None else None, sub_width)
         has_skip_conv = isinstance(self.skip_conv, UnaryBlockEPN)

@@ -150,3 +150,25 @@ def kpconv_fused(q_pts, s_pts, neighbors, x_bf16, w_fused, kernel_points, kp_ext
         _lib.f32(kp_extent), _lib.ptr(out), _lib.ptr(stats), _lib.ptr(seg_off), _lib.i64(nseg), _lib.i64(groups),
         _lib.stream_ptr()), "kpconv_fused")
     return out, stats
+
+
+def groupnorm_double_supported(channels):
+    v = channels // 4
+    return channels % 4 == 0 and 0 < v <= 256 and (v & (v - 1)) == 0
+
+
+def groupnorm_double(y, stats1, gamma1, beta1, gamma2, beta2, groups, seg_off, rows_per_point, slope=0.1, eps=1e-5):
+    """LeakyReLU(GN_2(LeakyReLU(GN_1(y)))) -> bf16, two streaming passes over y (statistics of the intermediate, then
+    apply); see se3et_groupnorm_double."""
+    rows, c = y.shape
+    nseg = seg_off.numel() - 1
+    stats2 = torch.empty((nseg, groups, 2), dtype=torch.float64, device=y.device)
+    out = torch.empty((rows, c), dtype=torch.bfloat16, device=y.device)
+    L = _lib.lib()
+    for apply in (0, 1):
+        _lib.check(L.se3et_groupnorm_double(
+            _lib.ptr(y), _lib.ptr(stats1), _lib.ptr(gamma1), _lib.ptr(beta1), _lib.ptr(stats2), _lib.ptr(gamma2),
+            _lib.ptr(beta2), _lib.i64(rows), _lib.i64(c), _lib.i64(groups), _lib.ptr(seg_off), _lib.i64(nseg),
+            _lib.i64(rows_per_point), _lib.f32(eps), _lib.f32(slope), apply, _lib.ptr(out), _lib.stream_ptr()),
+            "groupnorm_double")
+    return out

@@ -234,6 +234,27 @@ def test_groupnorm_apply_two_operands_and_residual(c, G, rpp):
     assert torch.allclose(ob.float().cpu(), want, rtol=1e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("c,G", [(32, 32), (64, 32), (256, 32), (16, 4)])
+def test_double_groupnorm_equals_two_single_passes(c, G):
+    """se3et_groupnorm_double (no intermediate tensor) against GN -> LeakyReLU -> GN -> LeakyReLU in torch fp32."""
+    g = torch.Generator().manual_seed(c)
+    pts = [120, 0, 77, 301]
+    seg = torch.tensor(np.concatenate([[0], np.cumsum(pts)]), dtype=torch.int64, device=DEV)
+    y = torch.randn(6 * sum(pts), c, generator=g) * 1.3 + 0.2
+    g1, b1, g2, b2 = (torch.randn(c, generator=g) for _ in range(4))
+    want = []
+    for i in range(len(pts)):
+        blk = y[6 * int(seg[i]):6 * int(seg[i + 1])]
+        if blk.numel():
+            f = torch.nn.functional.leaky_relu(oe.group_norm_epn(blk.view(-1, 6, c), G, g1, b1), 0.1)
+            want.append(torch.nn.functional.leaky_relu(oe.group_norm_epn(f, G, g2, b2), 0.1).reshape(-1, c))
+    want = torch.cat(want)
+    yd = y.to(DEV)
+    st1 = K.groupnorm_stats(yd, G, seg, 6)
+    got = K.groupnorm_double(yd, st1, g1.to(DEV), b1.to(DEV), g2.to(DEV), b2.to(DEV), G, seg, 6)
+    assert torch.allclose(got.float().cpu(), want, rtol=2e-2, atol=2e-2), (got.float().cpu() - want).abs().max()
+
+
 def test_pooling_ops_match_oracle(pyramid):
     g = torch.Generator().manual_seed(4)
     n0, n1 = pyramid["points"][0].shape[0], pyramid["points"][1].shape[0]
