@@ -113,7 +113,7 @@ def algorithmic_work(cfg, n_levels, n_ref_c, n_src_c, limits):
             unary(6.0 * ns, cin, mid, False)
         conv_flops += 2.0 * nq * 6 * 36 * mid * mid              # class-pre-summed contraction (issued on tcgen05)
         hmma_flops += 2.0 * nq * 6 * mid * 16 * 48               # 16-row basis x 48 padded neighbours (mma.sync)
-        apply_bytes += 2 * nq * 6 * mid * (4 + 4) + nq * 6 * mid * (4 + 2)  # two GroupNorm+LeakyReLU passes
+        apply_bytes += nq * 6 * mid * (4 + 4 + 2)  # double GroupNorm: statistics pass + apply pass over fp32, bf16 out
         if cin != cout:
             unary(6.0 * nq, cin, cout, False)
         unary(6.0 * nq, mid, cout, True)
@@ -134,7 +134,7 @@ def algorithmic_work(cfg, n_levels, n_ref_c, n_src_c, limits):
     return {
         "se3et_kpconv_fused": ("tensor", conv_flops + hmma_flops),
         "se3et_gemm_bf16_gnstats": ("hbm", gemm_bytes * 0.5), "se3et_gemm_bf16_gnapply": ("hbm", gemm_bytes * 0.5),
-        "se3et_groupnorm_apply": ("hbm", apply_bytes),
+        "se3et_groupnorm_double": ("hbm", apply_bytes),
         "se3et_geo_embed_project": ("tensor", 8.0 * nn2 * c * c),
         "se3et_radius_neighbors": ("hbm", search_bytes + 24.0 * sum(n_levels)),
         # positional score term: HBM-bound, every self_eq layer streams the (sum n^2, C) bf16 embedding once
@@ -271,15 +271,15 @@ def main():
         pts = torch.from_numpy(np.concatenate([c for pair in g for c in pair])).to(dev)
         dev_inputs.append((pts, torch.from_numpy(lens)))
     in_bytes = sum(int(p.numel()) * 4 for p, _ in dev_inputs)
-    pinned = torch.empty((max(int(l.sum()) for _, l in dev_inputs), 3), dtype=torch.float32).pin_memory()
+    pinned = [torch.empty((max(int(l.sum()) for _, l in dev_inputs), 3), dtype=torch.float32).pin_memory()
+              for _ in range(max(1, args.streams))]
 
     def step_device():
         model.forward_stacked_concurrent(dev_inputs, num_streams=args.streams)
 
     def step_e2e():
         out_bytes = 0
-        for g in groups:
-            res = model.forward_pairs(g, pinned=pinned)
+        for res in model.forward_pairs_concurrent(groups, num_streams=args.streams, pinned=pinned):
             out_bytes += sum(r[0].nbytes + r[1].nbytes + r[2].nbytes for r in res)
         return out_bytes
 
@@ -295,11 +295,11 @@ def main():
 
     # ---- timed region: K steps, CUDA events, per-entry-point events for the roofline
     timed_names = ["se3et_kpconv_fused", "se3et_kpconv_gather", "se3et_gemm_bf16", "se3et_gemm_bf16_gnstats",
-                   "se3et_gemm_bf16_gnapply", "se3et_gemm_grouped_bf16", "se3et_groupnorm_apply",
-                   "se3et_groupnorm_stats", "se3et_maxpool_nbr", "se3et_radius_neighbors", "se3et_grid_subsample",
+                   "se3et_gemm_bf16_gnapply", "se3et_gemm_grouped_bf16", "se3et_groupnorm_double",
+                   "se3et_groupnorm_apply", "se3et_groupnorm_stats", "se3et_maxpool_nbr", "se3et_radius_neighbors", "se3et_grid_subsample",
                    "se3et_geo_embed_project", "se3et_flash_attention", "se3et_superpoint_matching"]
     L.enabled = True
-    L.reset(timed=timed_names)
+    L.reset(timed=timed_names if args.streams <= 1 else ())
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -313,6 +313,25 @@ def main():
     L.enabled = False
     ms = e0.elapsed_time(e1)
     launches = L.launches()
+    timing_pass = "timed region"
+    pass_ms, pass_pairs = ms, args.pairs * args.steps
+    if args.streams > 1:
+        # per-kernel durations are only meaningful without a second sequence sharing the SMs: one more step, serial,
+        # with CUDA events around every entry point (same inputs, not part of `value`)
+        timing_pass = "one serial step after the timed region (streams in flight make per-kernel events overlap)"
+        for pts_i, lens_i in dev_inputs:  # the default stream's allocator pool is cold after the concurrent steps
+            model.forward_stacked(pts_i, lens_i)
+        torch.cuda.synchronize()
+        L.enabled = True
+        L.reset(timed=timed_names)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for pts_i, lens_i in dev_inputs:
+            model.forward_stacked(pts_i, lens_i)
+        s1.record()
+        torch.cuda.synchronize()
+        L.enabled = False
+        pass_ms, pass_pairs = s0.elapsed_time(s1), args.pairs
     per_api = {n: L.timed_ms(n) for n in timed_names}
     if world > 1:
         t = torch.tensor([ms], device=dev)
@@ -339,7 +358,7 @@ def main():
     if rank == 0:
         peaks = load_peaks()
         # dominant entry point by summed device time inside the timed region
-        pair_units = args.pairs * args.steps  # pairs processed by this rank in the timed region
+        pair_units = pass_pairs  # pairs this rank processed in the pass the entry-point events cover
         # algorithmic work per pair from the layer table and the measured pyramid
         pts0, lens0 = dev_inputs[0]
         dd = model.forward_stacked(pts0, lens0)["data_dict"]
@@ -359,7 +378,7 @@ def main():
             peak, unit = peaks["bf16_tflops"], "TFLOP/s"
         roofline = {"kernel": dom, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
                     "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"],
-                    "share_of_step": dom_ms / ms, "calls": dom_calls,
+                    "share_of_step": dom_ms / pass_ms, "calls": dom_calls, "event_timing": timing_pass,
                     "per_entry_point_ms": {n: round(v[0], 3) for n, v in per_api.items()},
                     # achieved / measured peak of every entry point with a work model (same formula as `frac`)
                     "per_entry_point_frac": {

@@ -7,6 +7,7 @@ missing or a call fails.
 import ctypes
 import os
 import re
+import threading
 
 import torch
 
@@ -43,6 +44,7 @@ class _Instrumented:
         self.timed = set()
         self.events = {}
         self.enabled = False
+        self._lock = threading.Lock()  # launch sequences may run on several host threads
 
     def __getattr__(self, name):
         fn = getattr(self._cdll, name)
@@ -52,13 +54,15 @@ class _Instrumented:
         def call(*args):
             if not self.enabled:
                 return fn(*args)
-            self.counts[name] = self.counts.get(name, 0) + 1
+            with self._lock:
+                self.counts[name] = self.counts.get(name, 0) + 1
             if name in self.timed:
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record()
                 rc = fn(*args)
                 b.record()
-                self.events.setdefault(name, []).append((a, b))
+                with self._lock:
+                    self.events.setdefault(name, []).append((a, b))
                 return rc
             return fn(*args)
 

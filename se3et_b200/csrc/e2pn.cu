@@ -311,66 +311,71 @@ __global__ void __launch_bounds__(256) groupnorm_double_kernel(NormSide a, NormS
                                                                 const int64_t* __restrict__ seg_off, int nseg,
                                                                 int rows_per_point, float eps, float slope,
                                                                 __nv_bfloat16* __restrict__ out_bf16) {
+  // every CTA owns a contiguous range of rows and walks the pairs it intersects one after the other, so the
+  // statistics of a pair are reduced inside the CTA (shared-memory atomics) before one set of fp64 atomics
+  __shared__ float sh_acc[2 * 256];  // [group][sum, sum sq], G <= 256
   const int V = C >> 2;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int c0 = (int)(tid % V) * 4;
-  const int64_t row_step = (int64_t)gridDim.x * blockDim.x / V;
   const int G = C / cpg;
-  int seg = -1;
-  int64_t seg_end = 0;
-  NormCols n1, n2;
-  float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
-  auto flush = [&]() {
-    if (kApply || seg < 0) return;
-    double* dst = stats2_acc + (int64_t)seg * G * 2;
-    if (cpg >= 4) {  // the four columns share one group
-      atomicAdd(dst + 2 * (c0 / cpg), (double)((s[0] + s[1]) + (s[2] + s[3])));
-      atomicAdd(dst + 2 * (c0 / cpg) + 1, (double)((ss[0] + ss[1]) + (ss[2] + ss[3])));
-    } else {
+  const int c0 = (threadIdx.x % V) * 4;
+  const int rsub = threadIdx.x / V, rstep = blockDim.x / V;
+  const int64_t per_cta = (rows + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = (int64_t)blockIdx.x * per_cta, r1 = min(rows, r0 + per_cta);
+  if (r0 >= r1) return;
+  int seg = segment_of(seg_off, nseg, r0 / rows_per_point);
+  int64_t row0 = r0;
+  while (row0 < r1) {
+    while (seg + 1 < nseg && seg_off[seg + 1] * rows_per_point <= row0) ++seg;
+    int64_t seg_end = seg == nseg - 1 ? rows : seg_off[seg + 1] * rows_per_point;
+    const int64_t row1 = min(r1, seg_end);
+    const double cnt = (double)(seg_off[seg + 1] - seg_off[seg]) * rows_per_point * cpg;
+    NormCols n1, n2;
+    load_norm_cols(a, seg, G, cpg, c0, cnt, eps, n1);
+    if (kApply) load_norm_cols(b2, seg, G, cpg, c0, cnt, eps, n2);
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int64_t row = row0 + rsub; row < row1; row += rstep) {
+      const float4 ya = __ldcs(reinterpret_cast<const float4*>(a.y + row * C + c0));
+      float v[4] = {(ya.x - n1.mean[0]) * n1.s[0] + n1.beta[0], (ya.y - n1.mean[1]) * n1.s[1] + n1.beta[1],
+                    (ya.z - n1.mean[2]) * n1.s[2] + n1.beta[2], (ya.w - n1.mean[3]) * n1.s[3] + n1.beta[3]};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        atomicAdd(dst + 2 * ((c0 + j) / cpg), (double)s[j]);
-        atomicAdd(dst + 2 * ((c0 + j) / cpg) + 1, (double)ss[j]);
+      for (int j = 0; j < 4; ++j) v[j] = v[j] >= 0.f ? v[j] : v[j] * slope;
+      if (!kApply) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          s[j] += v[j];
+          ss[j] = fmaf(v[j], v[j], ss[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float w = (v[j] - n2.mean[j]) * n2.s[j] + n2.beta[j];
+          v[j] = w >= 0.f ? w : w * slope;
+        }
+        uint2 o;
+        o.x = pack_bf16(v[0], v[1]);
+        o.y = pack_bf16(v[2], v[3]);
+        *reinterpret_cast<uint2*>(out_bf16 + row * C + c0) = o;
       }
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) s[j] = ss[j] = 0.f;
-  };
-  for (int64_t row = tid / V; row < rows; row += row_step) {
-    if (row >= seg_end) {
-      flush();
-      if (seg < 0) seg = segment_of(seg_off, nseg, row / rows_per_point);
-      while (seg + 1 < nseg && seg_off[seg + 1] * rows_per_point <= row) ++seg;
-      seg_end = seg_off[seg + 1] * rows_per_point;
-      if (seg == nseg - 1) seg_end = rows;
-      const double cnt = (double)(seg_off[seg + 1] - seg_off[seg]) * rows_per_point * cpg;
-      load_norm_cols(a, seg, G, cpg, c0, cnt, eps, n1);
-      if (kApply) load_norm_cols(b2, seg, G, cpg, c0, cnt, eps, n2);
-    }
-    const float4 ya = __ldcs(reinterpret_cast<const float4*>(a.y + row * C + c0));
-    float v[4] = {(ya.x - n1.mean[0]) * n1.s[0] + n1.beta[0], (ya.y - n1.mean[1]) * n1.s[1] + n1.beta[1],
-                  (ya.z - n1.mean[2]) * n1.s[2] + n1.beta[2], (ya.w - n1.mean[3]) * n1.s[3] + n1.beta[3]};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = v[j] >= 0.f ? v[j] : v[j] * slope;
     if (!kApply) {
+      for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh_acc[i] = 0.f;
+      __syncthreads();
+      if (cpg >= 4) {  // the four columns share one group
+        atomicAdd(&sh_acc[2 * (c0 / cpg)], (s[0] + s[1]) + (s[2] + s[3]));
+        atomicAdd(&sh_acc[2 * (c0 / cpg) + 1], (ss[0] + ss[1]) + (ss[2] + ss[3]));
+      } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        s[j] += v[j];
-        ss[j] = fmaf(v[j], v[j], ss[j]);
+        for (int j = 0; j < 4; ++j) {
+          atomicAdd(&sh_acc[2 * ((c0 + j) / cpg)], s[j]);
+          atomicAdd(&sh_acc[2 * ((c0 + j) / cpg) + 1], ss[j]);
+        }
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float w = (v[j] - n2.mean[j]) * n2.s[j] + n2.beta[j];
-        v[j] = w >= 0.f ? w : w * slope;
-      }
-      uint2 o;
-      o.x = pack_bf16(v[0], v[1]);
-      o.y = pack_bf16(v[2], v[3]);
-      *reinterpret_cast<uint2*>(out_bf16 + row * C + c0) = o;
+      __syncthreads();
+      for (int i = threadIdx.x; i < 2 * G; i += blockDim.x)
+        atomicAdd(stats2_acc + (int64_t)seg * G * 2 + i, (double)sh_acc[i]);
+      __syncthreads();
     }
+    row0 = row1;
   }
-  flush();
 }
 
 // out[q][col] = max_n xpad[idx[q][n]][col]; shadow neighbours contribute 0 (blocks.py:100-109)
@@ -599,7 +604,7 @@ extern "C" int se3et_groupnorm_double(const float* y, const double* stats1, cons
       rows_per_point <= 0 || !seg_offsets || !stats2)
     return SE3ET_ERR_ARG;
   const int64_t vecs = channels / 4;
-  if (vecs > 256 || (vecs & (vecs - 1)) != 0) return SE3ET_ERR_UNSUPPORTED;
+  if (vecs > 256 || (vecs & (vecs - 1)) != 0 || groups > 256) return SE3ET_ERR_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!apply) SE3ET_CUDA_CHECK(cudaMemsetAsync(stats2, 0, sizeof(double) * 2 * nseg * groups, st));
   if (rows == 0) return SE3ET_OK;

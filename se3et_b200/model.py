@@ -146,44 +146,32 @@ class GeoTransformer(nn.Module):
             'feats_f': feats_f, 'points_c': points_c, 'data_dict': dd,
         }
 
+    def _stream_pool(self, dev, n):
+        if not hasattr(self, '_streams') or len(self._streams) < n:
+            self._streams = [torch.cuda.Stream(device=dev) for _ in range(n)]
+        return self._streams
+
     @torch.no_grad()
     def forward_stacked_concurrent(self, inputs, num_streams=2):
         """Runs several launch sequences (`inputs` = [(points, lengths), ...] as for forward_stacked) concurrently,
         one host thread + CUDA stream per sequence slot: pairs are independent, and a second sequence fills the SMs
         while the first sits in a latency-bound kernel or a host-side size read-back.  Returns the list of results."""
-        import threading
         dev = inputs[0][0].device
         if num_streams <= 1 or len(inputs) <= 1:
             return [self.forward_stacked(p, l) for p, l in inputs]
-        if not hasattr(self, '_streams') or len(self._streams) < num_streams:
-            self._streams = [torch.cuda.Stream(device=dev) for _ in range(num_streams)]
-        results = [None] * len(inputs)
-        errors = []
-        start = torch.cuda.Event()
-        start.record(torch.cuda.current_stream(dev))
+        return _run_concurrent(lambda i: self.forward_stacked(*inputs[i]), len(inputs), num_streams,
+                               self._stream_pool(dev, num_streams), dev)
 
-        def worker(slot):
-            try:
-                torch.cuda.set_device(dev)
-                st = self._streams[slot]
-                st.wait_event(start)
-                with torch.cuda.stream(st), torch.no_grad():
-                    for i in range(slot, len(inputs), num_streams):
-                        results[i] = self.forward_stacked(*inputs[i])
-            except Exception as e:  # surfaced in the caller
-                errors.append(e)
-
-        threads = [threading.Thread(target=worker, args=(s,)) for s in range(num_streams)]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-        if errors:
-            raise errors[0]
-        cur = torch.cuda.current_stream(dev)
-        for st in self._streams[:num_streams]:
-            cur.wait_stream(st)
-        return results
+    @torch.no_grad()
+    def forward_pairs_concurrent(self, groups, num_streams=2, pinned=None):
+        """forward_pairs for several groups of pairs at once (host arrays in, host results out), `num_streams`
+        groups in flight.  pinned: optional list of num_streams pinned staging buffers."""
+        dev = next(self.parameters()).device
+        if num_streams <= 1 or len(groups) <= 1:
+            return [self.forward_pairs(g, pinned=None if pinned is None else pinned[0]) for g in groups]
+        return _run_concurrent(
+            lambda i: self.forward_pairs(groups[i], pinned=None if pinned is None else pinned[i % num_streams]),
+            len(groups), num_streams, self._stream_pool(dev, num_streams), dev)
 
     @torch.no_grad()
     def forward_pairs(self, clouds, pinned=None):
@@ -208,6 +196,38 @@ class GeoTransformer(nn.Module):
         sc = out['node_corr_scores'].cpu().numpy()
         cnt = out['num_corr'].cpu().numpy()
         return [(ri[p, :cnt[p]], si[p, :cnt[p]], sc[p, :cnt[p]]) for p in range(len(clouds))]
+
+
+def _run_concurrent(fn, count, num_streams, streams, dev):
+    """fn(i) for i in range(count), slot s runs i = s, s + num_streams, ... on its own host thread and CUDA stream."""
+    import threading
+    results = [None] * count
+    errors = []
+    start = torch.cuda.Event()
+    start.record(torch.cuda.current_stream(dev))
+
+    def worker(slot):
+        try:
+            torch.cuda.set_device(dev)
+            st = streams[slot]
+            st.wait_event(start)
+            with torch.cuda.stream(st), torch.no_grad():
+                for i in range(slot, count, num_streams):
+                    results[i] = fn(i)
+        except Exception as e:  # surfaced in the caller
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(num_streams)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    cur = torch.cuda.current_stream(dev)
+    for st in streams[:num_streams]:
+        cur.wait_stream(st)
+    return results
 
 
 def create_model(config):
