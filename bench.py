@@ -223,8 +223,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=64, help="pairs per step per GPU")
-    ap.add_argument("--pairs-per-launch", type=int, default=16, help="pairs stacked into one launch sequence")
-    ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic pairs generated (cycled)")
+    ap.add_argument("--pairs-per-launch", type=int, default=32, help="pairs stacked into one launch sequence")
+    ap.add_argument("--distinct", type=int, default=32, help="distinct synthetic pairs generated (cycled)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=2,
                     help="launch sequences in flight per GPU (host thread + CUDA stream each)")
@@ -294,7 +294,7 @@ def main():
     barrier()
 
     # ---- timed region: K steps, CUDA events, per-entry-point events for the roofline
-    timed_names = ["se3et_kpconv_fused", "se3et_kpconv_gather", "se3et_gemm_bf16", "se3et_gemm_bf16_gnstats",
+    timed_names = ["se3et_kpconv_fused", "se3et_kpconv_cin1", "se3et_kpconv_gather", "se3et_gemm_bf16", "se3et_gemm_bf16_gnstats",
                    "se3et_gemm_bf16_gnapply", "se3et_gemm_grouped_bf16", "se3et_groupnorm_double",
                    "se3et_groupnorm_apply", "se3et_groupnorm_stats", "se3et_maxpool_nbr", "se3et_radius_neighbors", "se3et_grid_subsample",
                    "se3et_geo_embed_project", "se3et_flash_attention", "se3et_superpoint_matching"]

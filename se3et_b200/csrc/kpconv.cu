@@ -149,6 +149,140 @@ kpconv_gather_mma_kernel(const float* __restrict__ q_pts, const float* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// First backbone layer (SimpleBlockEPN on the lifted input, Cin = 1): the whole KPConvInterSO3.forward on CUDA cores.
+// K = 36 only, so no tensor-core tile is worth building: one warp per query point,
+//   D[row16][a] = sum_n W16[row16][n] x[idx[n]][a]                                  (96 values per point)
+//   out[r][d]   = sum_{kc, a} D[basis_row(r, kc)][a] * W[kc][ridx[a][r]][0][d]       (lanes own output channels)
+// plus the per-pair GroupNorm sums of the output.  Every CTA owns a contiguous range of points.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kC1Warps = 8;
+constexpr int kC1MaxH = 40;  // neighbour columns (static shared memory budget)
+__constant__ int8_t c_basis_row[6][6] = {
+#define SE3ET_BR(r) {(int8_t)basis_row(r, 0), (int8_t)basis_row(r, 1), (int8_t)basis_row(r, 2), (int8_t)basis_row(r, 3), \
+                     (int8_t)basis_row(r, 4), (int8_t)basis_row(r, 5)}
+    SE3ET_BR(0), SE3ET_BR(1), SE3ET_BR(2), SE3ET_BR(3), SE3ET_BR(4), SE3ET_BR(5)
+#undef SE3ET_BR
+};
+__constant__ int8_t c_ridx_tab[6][6] = {
+#define SE3ET_RI(a) {(int8_t)ridx_tab(a, 0), (int8_t)ridx_tab(a, 1), (int8_t)ridx_tab(a, 2), (int8_t)ridx_tab(a, 3), \
+                     (int8_t)ridx_tab(a, 4), (int8_t)ridx_tab(a, 5)}
+    SE3ET_RI(0), SE3ET_RI(1), SE3ET_RI(2), SE3ET_RI(3), SE3ET_RI(4), SE3ET_RI(5)
+#undef SE3ET_RI
+};
+
+template <int CPL>  // output channels per lane: cout = 32 * CPL
+__global__ void __launch_bounds__(kC1Warps * 32)
+kpconv_cin1_kernel(const float* __restrict__ q_pts, const float* __restrict__ s_pts, const int64_t* __restrict__ idx,
+                   int H, int64_t nq, int64_t ns, const __nv_bfloat16* __restrict__ x,
+                   const float* __restrict__ w /* [36][cout] */, const float* __restrict__ kernel_points,
+                   float inv_extent, float* __restrict__ out, double* __restrict__ stats,
+                   const int64_t* __restrict__ seg_off, int nseg, int cpg) {
+  constexpr int COUT = 32 * CPL;
+  __shared__ float sh_w[36 * COUT];
+  __shared__ float sh_kp[48];
+  __shared__ float sh_w16[kC1Warps][kC1MaxH][17];  // [warp][neighbour][basis row], padded
+  __shared__ __align__(16) float sh_x[kC1Warps][kC1MaxH][8];  // anchors 0-2 | pad | anchors 3-5 | pad
+  __shared__ float sh_d[kC1Warps][96];
+  __shared__ float sh_stat[2 * COUT];          // per output channel: sum, sum of squares of the current pair
+  __shared__ uint8_t sh_dsel[kA][36];          // [r][kc * 6 + a] -> index into D: basis_row(r, kc) * 6 + a
+  __shared__ uint8_t sh_wsel[kA][36];          // [r][kc * 6 + a] -> weight row kc * 6 + ridx[a][r]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < kA * 36) {
+    const int r = threadIdx.x / 36, t = threadIdx.x % 36, kc = t / kA, a = t % kA;
+    sh_dsel[r][t] = (uint8_t)(c_basis_row[r][kc] * kA + a);
+    sh_wsel[r][t] = (uint8_t)(kc * kA + c_ridx_tab[a][r]);
+  }
+  for (int i = threadIdx.x; i < 36 * COUT; i += blockDim.x) sh_w[i] = w[i];
+  if (threadIdx.x < 45) sh_kp[threadIdx.x] = kernel_points[threadIdx.x];
+  __syncthreads();
+  const int64_t per_cta = (nq + gridDim.x - 1) / gridDim.x;
+  const int64_t p0 = (int64_t)blockIdx.x * per_cta, p1 = min(nq, p0 + per_cta);
+  if (p0 >= p1) return;
+  const int G = COUT / cpg;
+  int seg = stats ? segment_of(seg_off, nseg, p0) : 0;
+  int64_t pa = p0;
+  while (pa < p1) {
+    int64_t pb = p1;
+    if (stats) {
+      while (seg + 1 < nseg && seg_off[seg + 1] <= pa) ++seg;
+      pb = min(p1, seg == nseg - 1 ? nq : seg_off[seg + 1]);
+      for (int i = threadIdx.x; i < 2 * COUT; i += blockDim.x) sh_stat[i] = 0.f;
+      __syncthreads();
+    }
+    float st_s[CPL], st_ss[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) st_s[c] = st_ss[c] = 0.f;
+    for (int64_t p = pa + warp; p < pb; p += kC1Warps) {
+      const float qx = q_pts[3 * p], qy = q_pts[3 * p + 1], qz = q_pts[3 * p + 2];
+      for (int n = lane; n < H; n += 32) {
+        int64_t j = idx[p * H + n];
+        const bool valid = j >= 0 && j < ns;
+        if (!valid) j = 0;
+        float row[16];
+        basis_weights(s_pts[3 * j] - qx, s_pts[3 * j + 1] - qy, s_pts[3 * j + 2] - qz, sh_kp, inv_extent, valid, row);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) sh_w16[warp][n][r] = row[r];
+#pragma unroll
+        for (int a = 0; a < kA; ++a) sh_x[warp][n][a + (a >= 3)] = valid ? __bfloat162float(x[j * kA + a]) : 0.f;
+      }
+      __syncwarp();
+      {  // 96 (basis row, anchor) products: lane = (basis row, anchor half), three anchors each
+        const int r16 = lane & 15, ah = lane >> 4;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int n = 0; n < H; ++n) {
+          const float wv = sh_w16[warp][n][r16];
+          const float4 xv = *reinterpret_cast<const float4*>(&sh_x[warp][n][4 * ah]);
+          a0 = fmaf(wv, xv.x, a0);
+          a1 = fmaf(wv, xv.y, a1);
+          a2 = fmaf(wv, xv.z, a2);
+        }
+        sh_d[warp][r16 * kA + 3 * ah] = a0;
+        sh_d[warp][r16 * kA + 3 * ah + 1] = a1;
+        sh_d[warp][r16 * kA + 3 * ah + 2] = a2;
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int r = 0; r < kA; ++r) {
+        float o[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) o[c] = 0.f;
+#pragma unroll 4
+        for (int t = 0; t < 36; ++t) {  // t = kc * 6 + a
+          const float dv = sh_d[warp][sh_dsel[r][t]];
+          const float* wr = sh_w + sh_wsel[r][t] * COUT + lane;
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) o[c] = fmaf(dv, wr[32 * c], o[c]);
+        }
+        float* dst = out + (p * kA + r) * COUT + lane;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          dst[32 * c] = o[c];
+          st_s[c] += o[c];
+          st_ss[c] = fmaf(o[c], o[c], st_ss[c]);
+        }
+      }
+      __syncwarp();
+    }
+    if (stats) {
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        atomicAdd(&sh_stat[2 * (lane + 32 * c)], st_s[c]);
+        atomicAdd(&sh_stat[2 * (lane + 32 * c) + 1], st_ss[c]);
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) {
+        const int g = i >> 1, which = i & 1;
+        float t = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) t += sh_stat[2 * c + which];
+        atomicAdd(stats + ((int64_t)seg * G + g) * 2 + which, (double)t);
+      }
+      __syncthreads();
+    }
+    pa = pb;
+  }
+}
+
 template <int KS>
 static int launch_gather_mma(const float* q_pts, const float* s_pts, const int64_t* neighbors, int64_t nq, int64_t ns,
                              int h, const __nv_bfloat16* x, int cin, const float* kp, float inv_extent,
@@ -178,3 +312,33 @@ int kpconv_gather_mma(const float* q_pts, const float* s_pts, const int64_t* nei
 }
 
 }  // namespace se3et
+
+extern "C" int se3et_kpconv_cin1(const float* q_pts, const float* s_pts, const int64_t* neighbors, int64_t nq, int64_t ns,
+                                 int64_t h, const void* x_bf16, const float* w_36xcout, int64_t cout,
+                                 const float* kernel_points_15x3, float kp_extent, float* out_f32, double* stats,
+                                 const int64_t* seg_offsets, int64_t nseg, int64_t groups, se3et_stream_t stream) {
+  using namespace se3et;
+  if (nq < 0 || ns <= 0 || h <= 0 || cout <= 0 || !(kp_extent > 0.f)) return SE3ET_ERR_ARG;
+  if (cout % 32 != 0 || cout > 64 || h > kC1MaxH) return SE3ET_ERR_UNSUPPORTED;  // static shared memory budget
+  if (!q_pts || !s_pts || !neighbors || !x_bf16 || !w_36xcout || !kernel_points_15x3 || !out_f32) return SE3ET_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int cpg = 1;
+  if (stats) {
+    if (!seg_offsets || nseg <= 0 || groups <= 0 || cout % groups) return SE3ET_ERR_ARG;
+    cpg = (int)(cout / groups);
+    SE3ET_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * nseg * groups, st));
+  }
+  if (nq == 0) return SE3ET_OK;
+  int64_t blocks = ceil_div(nq, kC1Warps * 4);
+  if (blocks > (int64_t)kNumSMs * 4) blocks = (int64_t)kNumSMs * 4;
+  const auto* x = static_cast<const __nv_bfloat16*>(x_bf16);
+#define SE3ET_C1(CPL)                                                                                                \
+  kpconv_cin1_kernel<CPL><<<(unsigned)blocks, kC1Warps * 32, 0, st>>>(q_pts, s_pts, neighbors, (int)h, nq, ns, x,    \
+                                                                       w_36xcout, kernel_points_15x3, 1.f / kp_extent, \
+                                                                       out_f32, stats, seg_offsets, (int)nseg, cpg)
+  if (cout == 32) SE3ET_C1(1);
+  else SE3ET_C1(2);
+#undef SE3ET_C1
+  SE3ET_LAUNCH_CHECK();
+  return SE3ET_OK;
+}

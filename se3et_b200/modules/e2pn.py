@@ -22,7 +22,9 @@ from . import octahedral
 
 
 # switches for A/B measurements and tests (the defaults are the product path)
-_GFLAGS = {'fused_kpconv': True, 'two_pass_unary': True, 'double_norm': True}
+# 'cin1_kernel': the CUDA-core first-layer kernel (csrc/kpconv.cu) measures slower than gather + GEMM on B200
+# (9.6 vs 8.4 ms per 64 pairs), so it is off by default and only exercised by the tests
+_GFLAGS = {'fused_kpconv': True, 'two_pass_unary': True, 'double_norm': True, 'cin1_kernel': False}
 
 
 def _gn_fusable_fused(cout, groups):
@@ -176,6 +178,11 @@ class KPConvInterSO3(nn.Module):
     def forward_stats(self, q_pts, s_pts, neighb_inds, x, groups, seg):
         """forward() plus the per-pair GroupNorm statistics of its output (accumulated in the GEMM epilogue)."""
         self._check_tables()
+        if _GFLAGS['cin1_kernel'] and neighb_inds.shape[0] > 0 and s_pts.shape[0] > 0 and \
+                K.kpconv_cin1_supported(self.in_channels, self.out_channels, neighb_inds.shape[1]):
+            w36 = self.weights.detach().reshape(36, self.out_channels).float().contiguous()
+            return K.kpconv_cin1(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), w36, self.kernel_points,
+                                 self.KP_extent, gn=(groups, seg))
         if self._fused_ok(neighb_inds) and _gn_fusable_fused(self.out_channels, groups):
             return K.kpconv_fused(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), self._w_fused(),
                                   self.kernel_points, self.KP_extent, gn=(groups, seg))

@@ -58,7 +58,7 @@ def test_tables_match_kernel_and_reference(gold):
     assert tuple(conv.kidx_rot.shape) == (15, 6, 6) and tuple(conv.ridx_rot.shape) == (15, 6, 6)
 
 
-@pytest.mark.parametrize("cin,cout", [(8, 16), (1, 16), (16, 32), (32, 32), (64, 128), (128, 64)])
+@pytest.mark.parametrize("cin,cout", [(8, 16), (1, 16), (1, 32), (1, 64), (16, 32), (32, 32), (64, 128), (128, 64)])
 def test_kpconv_matches_oracle(pyramid, cin, cout):
     t = oe.octahedral_tables()
     p1 = torch.from_numpy(pyramid["points"][1])
@@ -75,6 +75,15 @@ def test_kpconv_matches_oracle(pyramid, cin, cout):
         conv = conv.to(DEV)
         got = conv(q.to(DEV), s.to(DEV), nb.to(DEV), x.to(DEV)).cpu()
         assert got.shape == want.shape
+        if cin == 1 and cout in (32, 64):  # the CUDA-core first-layer kernel (off by default) must agree as well
+            M._GFLAGS['cin1_kernel'] = True
+            try:
+                seg = torch.tensor([0, q.shape[0]], dtype=torch.int64, device=DEV)
+                y1, st1 = conv.forward_stats(q.to(DEV), s.to(DEV), nb.to(DEV), x.to(DEV), 16, seg)
+            finally:
+                M._GFLAGS['cin1_kernel'] = False
+            assert rel_err(y1.cpu().view_as(want), want) < 5e-3
+            assert torch.allclose(st1, K.groupnorm_stats(y1, 16, seg, 6), rtol=1e-5, atol=1e-3)
         # the gathered operand is rounded to bf16 once more before the GEMM: atol scales with the output magnitude
         assert torch.allclose(got, want, rtol=2e-2, atol=5e-3 * want.abs().max().item() + 1e-6), \
             (got - want).abs().max().item()
