@@ -379,7 +379,79 @@ __global__ void __launch_bounds__(256) groupnorm_double_kernel(NormSide a, NormS
 }
 
 // out[q][col] = max_n xpad[idx[q][n]][col]; shadow neighbours contribute 0 (blocks.py:100-109)
+// A CTA handles kPoolQ query points; a thread owns 8 channels (one 16-byte load per neighbour row, two neighbours in
+// flight) of one query.
+constexpr int kPoolQ = 4;
+
+__device__ __forceinline__ void max_bf16x8(float (&m)[8], const uint4& v) {
+  m[0] = fmaxf(m[0], bf_lo(v.x)); m[1] = fmaxf(m[1], bf_hi(v.x));
+  m[2] = fmaxf(m[2], bf_lo(v.y)); m[3] = fmaxf(m[3], bf_hi(v.y));
+  m[4] = fmaxf(m[4], bf_lo(v.z)); m[5] = fmaxf(m[5], bf_hi(v.z));
+  m[6] = fmaxf(m[6], bf_lo(v.w)); m[7] = fmaxf(m[7], bf_hi(v.w));
+}
+
 __global__ void __launch_bounds__(256) maxpool_nbr_kernel(const __nv_bfloat16* __restrict__ x, int64_t ns, int width,
+                                                           const int64_t* __restrict__ idx, int H_full, int64_t nq,
+                                                           const int64_t* __restrict__ seg_off,
+                                                           const int32_t* __restrict__ seg_width, int nseg,
+                                                           __nv_bfloat16* __restrict__ out) {
+  __shared__ int sh_idx[kPoolQ][kMaxH];
+  __shared__ int sh_h[kPoolQ];
+  const int64_t q0 = (int64_t)blockIdx.x * kPoolQ;
+  for (int t = threadIdx.x; t < kPoolQ * H_full; t += blockDim.x) {
+    const int qi = t / H_full, n = t - qi * H_full;
+    const int64_t q = q0 + qi;
+    int j = -1;
+    if (q < nq) {
+      const int64_t jj = idx[q * H_full + n];
+      j = (jj >= 0 && jj < ns) ? (int)jj : -1;
+    }
+    sh_idx[qi][n] = j;
+  }
+  if (threadIdx.x < kPoolQ) {
+    const int64_t q = q0 + threadIdx.x;
+    int H = H_full;
+    if (seg_width && q < nq) H = min(H_full, max(1, seg_width[segment_of(seg_off, nseg, q)]));
+    sh_h[threadIdx.x] = H;
+  }
+  __syncthreads();
+  const int vecs = width / 8;  // 16-byte chunks per row
+  for (int u = threadIdx.x; u < kPoolQ * vecs; u += blockDim.x) {
+    const int qi = u / vecs, v = u - qi * vecs;
+    const int64_t q = q0 + qi;
+    if (q >= nq) continue;
+    const int H = sh_h[qi];
+    float m[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+    bool shadow = false;
+    int n = 0;
+    for (; n + 1 < H; n += 2) {
+      const int j0 = sh_idx[qi][n], j1 = sh_idx[qi][n + 1];
+      uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+      if (j0 >= 0) a = *reinterpret_cast<const uint4*>(x + (int64_t)j0 * width + 8 * v);
+      if (j1 >= 0) b = *reinterpret_cast<const uint4*>(x + (int64_t)j1 * width + 8 * v);
+      shadow |= (j0 < 0) | (j1 < 0);
+      if (j0 >= 0) max_bf16x8(m, a);
+      if (j1 >= 0) max_bf16x8(m, b);
+    }
+    if (n < H) {
+      const int j0 = sh_idx[qi][n];
+      if (j0 >= 0) max_bf16x8(m, *reinterpret_cast<const uint4*>(x + (int64_t)j0 * width + 8 * v));
+      else shadow = true;
+    }
+    if (shadow) {  // the zero shadow row takes part in the max
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], 0.f);
+    }
+    uint4 o;
+    o.x = pack_bf16(m[0], m[1]); o.y = pack_bf16(m[2], m[3]); o.z = pack_bf16(m[4], m[5]); o.w = pack_bf16(m[6], m[7]);
+    *reinterpret_cast<uint4*>(out + q * width + 8 * v) = o;
+  }
+}
+
+// two channels per thread: row widths that are not a multiple of 8
+__global__ void __launch_bounds__(256) maxpool_nbr_scalar_kernel(const __nv_bfloat16* __restrict__ x, int64_t ns, int width,
                                                            const int64_t* __restrict__ idx, int H_full,
                                                            const int64_t* __restrict__ seg_off,
                                                            const int32_t* __restrict__ seg_width, int nseg,
@@ -562,10 +634,19 @@ extern "C" int se3et_maxpool_nbr(const void* x_bf16, int64_t ns, int64_t width, 
   if (nq < 0 || ns < 0 || h <= 0 || h > kMaxH || width <= 0 || width % 2) return SE3ET_ERR_ARG;
   if (nq == 0) return SE3ET_OK;
   if (!x_bf16 || !neighbors || !out_bf16) return SE3ET_ERR_ARG;
-  const int threads = width / 2 >= 256 ? 256 : (width / 2 <= 64 ? 64 : 128);
-  maxpool_nbr_kernel<<<(unsigned)nq, threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x_bf16), ns, (int)width, neighbors, (int)h, seg_offsets, seg_width, (int)nseg,
-      static_cast<__nv_bfloat16*>(out_bf16));
+  if (width % 8 != 0) {
+    const int threads = width / 2 >= 256 ? 256 : (width / 2 <= 64 ? 64 : 128);
+    maxpool_nbr_scalar_kernel<<<(unsigned)nq, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x_bf16), ns, (int)width, neighbors, (int)h, seg_offsets, seg_width, (int)nseg,
+        static_cast<__nv_bfloat16*>(out_bf16));
+    SE3ET_LAUNCH_CHECK();
+    return SE3ET_OK;
+  }
+  const int64_t work = kPoolQ * (width / 8);
+  const int threads = work >= 256 ? 256 : (work <= 64 ? 64 : 128);
+  maxpool_nbr_kernel<<<(unsigned)ceil_div(nq, kPoolQ), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x_bf16), ns, (int)width, neighbors, (int)h, nq, seg_offsets, seg_width,
+      (int)nseg, static_cast<__nv_bfloat16*>(out_bf16));
   SE3ET_LAUNCH_CHECK();
   return SE3ET_OK;
 }
