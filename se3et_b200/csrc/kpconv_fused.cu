@@ -147,7 +147,19 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
     const uint32_t xs_s = smem_addr(xs);
     const uint32_t a_tile_s = smem_addr(a_tile);
     const uint32_t zero_s = smem_addr(zero16);
-    const LaneTargets T = make_lane_targets(lane, sh_target, sh_ridx);
+    // stmatrix address rows of this lane.  x4: matrix lane / 8 = (basis rows 0-7 | 8-15) x (channels 0-7 | 8-15), row
+    // lane % 8; each basis row has two (r, kc) targets.  x2 (centre copies): matrices = basis rows 8-15 x both channel
+    // halves, addresses from lanes 0-15.
+    const int ar4 = (lane & 7) + 8 * ((lane >> 3) & 1), nt4 = lane >> 4;
+    uint32_t r4[2], kc4[2], rw4[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int v = sh_target[ar4][t];
+      r4[t] = (uint32_t)(v >> 3);
+      kc4[t] = (uint32_t)(v & 7) * kA;
+      rw4[t] = sh_ridx[v >> 3];
+    }
+    const bool centre = (lane >> 2) == 7;  // accumulator row g + 8 == 15
     const int q = lane & 3;
     const int H = args.H, HR = args.HR;
     const int cin = args.cin;
@@ -256,31 +268,27 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
             mma_16816(d[0], afrag[ks], b[0], b[1]);
             mma_16816(d[1], afrag[ks], b[2], b[3]);
           }
-          // accumulator rows g / g + 8 = basis rows; each is copied to its (r, kc) targets:
-          // operand row m = warp * 6 + r, slot j = kc * 6 + ridx[a][r], K-block j / 4, 16-byte chunk
-          // (j % 4) * 2 + nt, swizzled by (m % 8)
+          // accumulator rows g / g + 8 = basis rows; each is copied to its (r, kc) targets: operand row
+          // m = warp * 6 + r, slot j = kc * 6 + ridx[a][r], K-block j / 4, 16-byte chunk (j % 4) * 2 + nt swizzled by
+          // (m % 8).  One stmatrix.x4 writes all 16 basis rows x 16 channels to their t-th targets.
+          const uint32_t p0 = pack2(d[0][0], d[0][1]), p1 = pack2(d[0][2], d[0][3]);
+          const uint32_t p2 = pack2(d[1][0], d[1][1]), p3 = pack2(d[1][2], d[1][3]);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-#pragma unroll
-            for (int t = 0; t < 2; ++t) {
-              const uint32_t ap = (T.ridx[h][t] >> (3 * a)) & 7u;
-              const uint32_t j = T.kc[h][t] * kA + ap;
-              const uint32_t m = mbase + T.r[h][t];
-              const uint32_t addr = a_tile_s + (j >> 2) * kFKBlockBytes + m * 128 + q * 4 +
-                                    ((((j & 3) * 2) ^ (m & 7)) << 4);
-              st_shared_b32(addr, pack2(d[0][2 * h], d[0][2 * h + 1]));
-              st_shared_b32(addr ^ 16u, pack2(d[1][2 * h], d[1][2 * h + 1]));
-            }
+          for (int t = 0; t < 2; ++t) {
+            const uint32_t j = kc4[t] + ((rw4[t] >> (3 * a)) & 7u);
+            const uint32_t m = mbase + r4[t];
+            stmatrix_x4(a_tile_s + (j >> 2) * kFKBlockBytes + m * 128 + ((((j & 3) * 2 + nt4) ^ (m & 7)) << 4), p0, p1,
+                        p2, p3);
           }
-          if (T.centre) {
+          if (centre) {  // the centre row (basis row 15, held by lanes 28-31) has four more targets r = 2..5
 #pragma unroll
             for (int r = 2; r < kA; ++r) {
               const uint32_t j = 5 * kA + ridx_tab(a, r);
               const uint32_t m = mbase + r;
               const uint32_t addr = a_tile_s + (j >> 2) * kFKBlockBytes + m * 128 + q * 4 +
                                     ((((j & 3) * 2) ^ (m & 7)) << 4);
-              st_shared_b32(addr, pack2(d[0][2], d[0][3]));
-              st_shared_b32(addr ^ 16u, pack2(d[1][2], d[1][3]));
+              st_shared_b32(addr, p1);
+              st_shared_b32(addr ^ 16u, p3);
             }
           }
           __syncwarp();  // every lane is done with this ring stage and its stores are issued
