@@ -91,6 +91,32 @@ def make_pairs(count, first=0, generator="make_3dmatch_pair"):
     return [(p["ref_points"], p["src_points"]) for p in pairs]
 
 
+NCU_KERNEL = {"se3et_kpconv_fused": "kpconv_fused_kernel", "se3et_gemm_bf16_gnstats": "gemm_tma_kernel",
+              "se3et_gemm_bf16_gnapply": "gemm_tma_kernel", "se3et_gemm_grouped_bf16": "gemm_tma_kernel",
+              "se3et_geo_embed_project": "geo_embed_project_kernel", "se3et_radius_neighbors": "radius_query_kernel",
+              "se3et_groupnorm_double": "groupnorm_double_kernel", "se3et_flash_attention": "flash_attention_kernel"}
+
+
+def ncu_traffic(entry_point, summary="profiles/r1_final_ncu_full_summary.csv"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch (bytes, mean over the launches of the entry point's
+    kernel) from the committed `ncu --set full` capture of the same launch sequence; None when there is no capture."""
+    import csv
+    path = os.path.join(ROOT, summary)
+    name = NCU_KERNEL.get(entry_point)
+    if not name or not os.path.exists(path):
+        return None
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    try:
+        ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    except ValueError:
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    vals = [float(r[ri]) * scale.get(units[ri], 1.0) + float(r[wi]) * scale.get(units[wi], 1.0)
+            for r in rows[2:] if r and r[0].startswith(name)]
+    return sum(vals) / len(vals) if vals else None
+
+
 def algorithmic_work(cfg, n_levels, n_ref_c, n_src_c, limits):
     """Algorithmic work of one pair per entry point: ('hbm', bytes) or ('tensor', flops), from the
     layer table of the E2PN backbone (se3et_b200/modules/e2pn.py:E2PN) and the transformer shapes.
@@ -377,7 +403,7 @@ def main():
             achieved = per_pair * pair_units / (dom_ms / 1e3) / 1e12
             peak, unit = peaks["bf16_tflops"], "TFLOP/s"
         roofline = {"kernel": dom, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
-                    "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"],
+                    "frac": achieved / peak, "traffic": ncu_traffic(dom), "peak_source": peaks["source"],
                     "share_of_step": dom_ms / pass_ms, "calls": dom_calls, "event_timing": timing_pass,
                     "per_entry_point_ms": {n: round(v[0], 3) for n, v in per_api.items()},
                     # achieved / measured peak of every entry point with a work model (same formula as `frac`)
