@@ -344,3 +344,35 @@ def test_backbone_batched_pairs_equal_single_pairs(gold, pyramid):
         # rows fall into differently aligned tiles when it is stacked behind another pair, so its statistics differ
         # at the 1e-7 level and a few bf16 roundings flip and propagate through the layers
         assert ea < 1e-2 and eb < 1e-2, (lvl, ea, eb)
+
+
+def test_fused_kpconv_is_equivariant_at_full_size():
+    """Size-independent property (no oracle needed): for anchor-constant input features (what LiftBlockEPN produces),
+    rotating the points by an element R of the octahedral group permutes the output anchors of KPConvInterSO3 by the
+    vertex permutation of R, out_R[p, perm[a]] = out[p, a] -- the reason the reference builds kidx_rot / ridx_rot
+    (blocks_epn.py:228-332).  Checked with the CPU oracle at toy size, here on a 35k-point level-0 cloud, fused kernel."""
+    from se3et_b200 import synthetic
+    from se3et_b200.precompute import precompute_data_stack_mode
+    p = synthetic.make_3dmatch_pair(4)
+    pts = torch.from_numpy(np.concatenate([p["ref_points"], p["src_points"]])).to(DEV)
+    lens = torch.tensor([len(p["ref_points"]), len(p["src_points"])])
+    d = precompute_data_stack_mode(pts, lens.to(DEV), 4, 0.025, 0.0625, [38, 36, 36, 38])
+    q, nb = d["points"][0], d["neighbors"][0]
+    assert q.shape[0] > 25000
+    cin, cout = 32, 32
+    conv = M.KPConvInterSO3(15, 6, cin, cout, 0.05, 0.0625, non_sep_conv=True, rot_by_permute=True, quotient_factor=4)
+    with torch.no_grad():
+        conv.weights.copy_(helpers.seeded_tensor("conv.weights", (6, 6, cin, cout)))
+    conv = conv.to(DEV)
+    assert conv._fused_ok(nb)
+    anchors, verts = octahedral.tables()["anchors"], octahedral.VERTICES
+    x = helpers.seeded_tensor("conv.input", (q.shape[0], 1, cin)).expand(-1, 6, -1).contiguous().to(DEV)
+    base = conv(q, q, nb, x).view(-1, 6, cout).float()
+    for g in (1, 2, 5):  # three non-trivial group elements
+        R = torch.tensor(anchors[g], dtype=torch.float32, device=DEV)
+        perm = [int(np.argmin(((verts - anchors[g] @ verts[a]) ** 2).sum(1))) for a in range(6)]
+        assert perm != list(range(6))
+        qr = (q @ R.t()).contiguous()  # signed permutation matrix: the rotated coordinates are exact
+        out = conv(qr, qr, nb, x).view(-1, 6, cout).float()
+        assert rel_err(out[:, perm, :], base) < 2e-3, (g, rel_err(out[:, perm, :], base))
+        assert rel_err(out, base) > 0.1  # and it is a genuine permutation, not the identity

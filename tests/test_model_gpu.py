@@ -124,3 +124,22 @@ def test_se3et_e_forward_matches_oracle():
     both = model.forward_pairs([(ref, src), (q["ref_points"], q["src_points"])])
     again = set(zip(both[0][0].tolist(), both[0][1].tolist()))
     assert len(again & got) >= 0.9 * len(got)
+
+
+def test_full_size_pair_matches_oracle():
+    """BASELINE.json configs[0] size: SE3ET-I2 on one full 3DMatch-shaped pair (~15k points per cloud), CUDA path vs the
+    fp32 CPU oracle end to end (pyramid bit-exact, coarse features by cosine, correspondences by overlap)."""
+    cfg, model, sd = build("se3eti2.3dmatch")
+    p = synthetic.make_3dmatch_pair(2)
+    assert len(p["ref_points"]) > 10000 and len(p["src_points"]) > 10000
+    d, fl, r, s, ri, si, sc = oracle_forward(cfg, sd, p["ref_points"], p["src_points"])
+    res = model.forward_stacked(torch.from_numpy(np.concatenate([p["ref_points"], p["src_points"]])).to(DEV),
+                                torch.tensor([len(p["ref_points"]), len(p["src_points"])]))
+    for k in ("points", "neighbors", "subsampling", "upsampling"):
+        for a, b in zip(d[k], res["data_dict"][k]):
+            assert np.array_equal(a, b.cpu().numpy()), k
+    assert min_cos(res["feats_f"], fl[0]) > 0.99
+    assert min_cos(res["ref_feats_c"], r) > 0.98 and min_cos(res["src_feats_c"], s) > 0.98
+    got = set(zip(res["ref_node_corr_indices"][0].tolist(), res["src_node_corr_indices"][0].tolist()))
+    want = set(zip(ri.tolist(), si.tolist()))
+    assert len(got & want) >= 0.85 * len(want), len(got & want) / len(want)
