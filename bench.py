@@ -93,7 +93,7 @@ def make_pairs(count, first=0, generator="make_3dmatch_pair"):
 
 NCU_KERNEL = {"se3et_kpconv_fused": "kpconv_fused_kernel", "se3et_gemm_bf16_gnstats": "gemm_tma_kernel",
               "se3et_gemm_bf16_gnapply": "gemm_tma_kernel", "se3et_gemm_grouped_bf16": "gemm_tma_kernel",
-              "se3et_geo_embed_project": "geo_embed_project_kernel", "se3et_radius_neighbors": "radius_query_kernel",
+              "se3et_geo_embed_project": "geo_embed_project_kernel", "se3et_geo_embed_lookup": "geo_embed_lookup_kernel", "se3et_radius_neighbors": "radius_query_kernel",
               "se3et_groupnorm_double": "groupnorm_double_kernel", "se3et_flash_attention": "flash_attention_kernel"}
 
 
@@ -162,6 +162,8 @@ def algorithmic_work(cfg, n_levels, n_ref_c, n_src_c, limits):
         "se3et_gemm_bf16_gnstats": ("hbm", gemm_bytes * 0.5), "se3et_gemm_bf16_gnapply": ("hbm", gemm_bytes * 0.5),
         "se3et_groupnorm_double": ("hbm", apply_bytes),
         "se3et_geo_embed_project": ("tensor", 8.0 * nn2 * c * c),
+        # tabulated embedding: index row in, bf16 row out (the table reads hit L2)
+        "se3et_geo_embed_lookup": ("hbm", nn2 * (16.0 + 2.0 * c)),
         "se3et_radius_neighbors": ("hbm", search_bytes + 24.0 * sum(n_levels)),
         # positional score term: HBM-bound, every self_eq layer streams the (sum n^2, C) bf16 embedding once
         "se3et_gemm_grouped_bf16": ("hbm", nself * nn2 * (2.0 * c + 4.0 * 6 * cfg.geotransformer.num_heads)),
@@ -323,7 +325,8 @@ def main():
     timed_names = ["se3et_kpconv_fused", "se3et_kpconv_cin1", "se3et_kpconv_gather", "se3et_gemm_bf16", "se3et_gemm_bf16_gnstats",
                    "se3et_gemm_bf16_gnapply", "se3et_gemm_grouped_bf16", "se3et_groupnorm_double",
                    "se3et_groupnorm_apply", "se3et_groupnorm_stats", "se3et_maxpool_nbr", "se3et_radius_neighbors", "se3et_grid_subsample",
-                   "se3et_geo_embed_project", "se3et_flash_attention", "se3et_superpoint_matching"]
+                   "se3et_geo_embed_project", "se3et_geo_embed_lookup", "se3et_geo_embed_indices", "se3et_flash_attention",
+                   "se3et_superpoint_matching"]
     L.enabled = True
     L.reset(timed=timed_names if args.streams <= 1 else ())
     sampler = ClockSampler(local_rank)

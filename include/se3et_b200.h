@@ -242,6 +242,13 @@ int se3et_geo_embed_indices(const float* points, const int64_t* cloud_offsets, i
  * [rows, channels].  The sinusoids are generated inside the kernel as the tcgen05 A operand. */
 int se3et_geo_embed_project(const float* idx4, int64_t rows, int64_t channels, const void* w_d_bf16,
                             const void* w_a_bf16, const float* bias_sum, void* out_bf16, se3et_stream_t stream);
+/* The same embedding assembled from tabulated projections: W emb(u) + b is a function of the scalar u alone, so
+ * table_d[i] = W_d emb(i * step) + b_d and table_a[i] = W_a emb(i * step) + b_a (bf16 [n, channels], built by the host
+ * once per weight version, se3et_b200/modules/transformer.py) give
+ *   out[r] = table_d[round(idx4[r].x / step)] + max_k table_a[round(idx4[r].{y,z,w} / step)]     (indices clamped).
+ * With step = 1/512 the tabulation error is below the bf16 rounding of the result.  channels in {64, 128, 256}. */
+int se3et_geo_embed_lookup(const float* idx4, int64_t rows, int64_t channels, const void* table_d_bf16, int64_t nd,
+                           const void* table_a_bf16, int64_t na, float step, void* out_bf16, se3et_stream_t stream);
 /* Fused attention: RPEMultiHeadAttention equivariant branch (rpe_transformer.py:56-131, bias = q.proj_p(emb)) and
  * MultiHeadAttention with 4-D value (vanilla_transformer.py:58-85).  problems: int64 [num_problems][5]
  * {q_start, n_q, kv_start, n_kv, bias_off}.  Strides in elements: *_pt per point, *_an per anchor (0 = none).

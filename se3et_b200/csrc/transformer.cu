@@ -289,6 +289,51 @@ static int launch_embed(const CUtensorMap& td, const CUtensorMap& ta, const floa
 }
 
 // ---------------------------------------------------------------------------------------------
+// geo_embed_lookup: the projected sinusoidal embedding of a scalar u, W emb(u) + b, is a smooth function R -> R^C that
+// depends on the weights only, so it is tabulated once per weight version (step 1/512: the embedding's highest
+// frequency is 1 rad per unit, the tabulation error stays below the bf16 rounding of the result) and the
+// (sum n^2, C) embedding is assembled from four 16-byte-per-lane table reads per row:
+//   out[row] = table_d[round(512 d)] + max_k table_a[round(512 a_k)]
+// One row per C / 8 lanes; tables are L2 resident.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& v, float (&f)[8]) {
+  f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+  f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+  f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+  f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+}
+
+__global__ void __launch_bounds__(256) geo_embed_lookup_kernel(const float4* __restrict__ idx, int64_t rows, int C,
+                                                                const __nv_bfloat16* __restrict__ table_d, int nd,
+                                                                const __nv_bfloat16* __restrict__ table_a, int na,
+                                                                float inv_step, __nv_bfloat16* __restrict__ out) {
+  const int lpr = C >> 3;  // lanes per row (16 bytes each); C is a power-of-two multiple of 64 up to 256 -> 8..32
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / lpr, c8 = (lane - sub * lpr) * 8, rpw = 32 / lpr;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0 * rpw + sub; row < rows; row += nwarps * rpw) {
+    const float4 v = __ldg(idx + row);
+    const int id = min(max(__float2int_rn(v.x * inv_step), 0), nd - 1);
+    const int i0 = min(max(__float2int_rn(v.y * inv_step), 0), na - 1);
+    const int i1 = min(max(__float2int_rn(v.z * inv_step), 0), na - 1);
+    const int i2 = min(max(__float2int_rn(v.w * inv_step), 0), na - 1);
+    const uint4 qd = __ldg(reinterpret_cast<const uint4*>(table_d + (int64_t)id * C + c8));
+    const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(table_a + (int64_t)i0 * C + c8));
+    const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(table_a + (int64_t)i1 * C + c8));
+    const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(table_a + (int64_t)i2 * C + c8));
+    float d[8], a0[8], a1[8], a2[8];
+    bf16x8_to_f32(qd, d); bf16x8_to_f32(q0, a0); bf16x8_to_f32(q1, a1); bf16x8_to_f32(q2, a2);
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      o[j] = pack2_bf16(d[2 * j] + fmaxf(fmaxf(a0[2 * j], a1[2 * j]), a2[2 * j]),
+                        d[2 * j + 1] + fmaxf(fmaxf(a0[2 * j + 1], a1[2 * j + 1]), a2[2 * j + 1]));
+    __stcs(reinterpret_cast<uint4*>(out + row * C + c8), make_uint4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // add_layernorm: one warp per row
 // ---------------------------------------------------------------------------------------------
 template <int kPerLane>
@@ -400,6 +445,23 @@ extern "C" int se3et_geo_embed_project(const float* idx4, int64_t rows, int64_t 
   auto* out = static_cast<__nv_bfloat16*>(out_bf16);
   return bn == 128 ? launch_embed<128>(td, ta, idx, rows, C, bias_sum, out, st)
                    : launch_embed<64>(td, ta, idx, rows, C, bias_sum, out, st);
+}
+
+extern "C" int se3et_geo_embed_lookup(const float* idx4, int64_t rows, int64_t channels, const void* table_d_bf16,
+                                      int64_t nd, const void* table_a_bf16, int64_t na, float step, void* out_bf16,
+                                      se3et_stream_t stream) {
+  if (rows < 0 || nd <= 0 || na <= 0 || !(step > 0.f)) return SE3ET_ERR_ARG;
+  if (channels != 64 && channels != 128 && channels != 256) return SE3ET_ERR_UNSUPPORTED;
+  if (rows == 0) return SE3ET_OK;
+  if (!idx4 || !table_d_bf16 || !table_a_bf16 || !out_bf16) return SE3ET_ERR_ARG;
+  int64_t blocks = ceil_div(rows * (channels / 8), 256);
+  if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+  geo_embed_lookup_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(idx4), rows, (int)channels, static_cast<const __nv_bfloat16*>(table_d_bf16),
+      (int)nd, static_cast<const __nv_bfloat16*>(table_a_bf16), (int)na, 1.f / step,
+      static_cast<__nv_bfloat16*>(out_bf16));
+  SE3ET_LAUNCH_CHECK();
+  return SE3ET_OK;
 }
 
 extern "C" int se3et_add_layernorm(const float* x, const void* resid_bf16, int64_t resid_div, int64_t rows,

@@ -30,6 +30,10 @@ from ..ops.gemm import linear_bf16
 from .e2pn import _Bf16Cache, _act
 
 
+# the tabulated embedding (se3et_geo_embed_lookup) replaces the in-kernel sinusoid GEMM unless switched off (tests)
+_EMBED_TABLE = {'on': True}
+
+
 class CloudContext:
     """Flat layout bookkeeping for a batch of pairs. sizes = [n_ref_0.., n_src_0..] (python ints)."""
 
@@ -130,10 +134,38 @@ class GeometricStructureEmbedding(nn.Module):
         """(A, 3, 3) fp32 anchors (the transpose of the stored l = 1 Wigner-D matrices)."""
         return self.anchors_wignerD[1].detach().transpose(1, 2).contiguous()
 
+    TABLE_STEP = 1.0 / 512.0  # spacing of the tabulated projections (highest embedding frequency: 1 rad / unit)
+
+    def _tables(self, u_max, device):
+        """bf16 tables of W_d emb(u) + b_d (u in [0, u_max]) and W_a emb(a) + b_a (a in [0, 180 / sigma_a]): exact fp32
+        sinusoids and an fp32 matmul, once per weight version and size bucket (parameter preprocessing like the bf16
+        weight copies, not part of the per-pair path)."""
+        nd = 1 << int(np.ceil(np.log2(max(u_max, 1.0) / self.TABLE_STEP + 2)))
+        key = (self.proj_d.weight._version, self.proj_a.weight._version, self.proj_d.bias._version,
+               self.proj_a.bias._version, self.proj_d.weight.data_ptr(), str(device), nd)
+        if getattr(self, '_table_key', None) != key:
+            with torch.no_grad():
+                div = self.embedding.div_term.to(device).float()
+
+                def table(n, lin):
+                    u = torch.arange(n, device=device, dtype=torch.float32) * self.TABLE_STEP
+                    om = u[:, None] * div[None, :]
+                    e = torch.stack([torch.sin(om), torch.cos(om)], dim=2).reshape(n, -1)
+                    return torch.addmm(lin.bias.float(), e, lin.weight.float().t()).to(torch.bfloat16).contiguous()
+                na = int(180.0 / self.sigma_a / self.TABLE_STEP) + 2
+                self._table_d, self._table_a = table(nd, self.proj_d), table(na, self.proj_a)
+            self._table_key = key
+        return self._table_d, self._table_a
+
     def embed(self, points_flat, ctx):
         """-> bf16 (sum n_b^2, C): row eoff[b] + n*n_b + m is the embedding of the pair (n, m) of cloud b."""
         idx4 = T.geo_embed_indices(points_flat, ctx.cu, ctx.max_n, ctx.eoff, ctx.R, self.sigma_d, self.sigma_a,
                                    self.angle_k)
+        c = self.proj_d.weight.shape[0]
+        if _EMBED_TABLE['on'] and c in (64, 128, 256) and idx4.shape[0] > 0:
+            u_max = float(idx4[:, 0].max())  # one scalar read-back per launch sequence
+            td, ta = self._tables(u_max, idx4.device)
+            return T.geo_embed_lookup(idx4, td, ta, self.TABLE_STEP)
         bias_sum = (self.proj_d.bias + self.proj_a.bias).detach().float().contiguous()
         return T.geo_embed_project(idx4, self._wd.get(self.proj_d.weight), self._wa.get(self.proj_a.weight), bias_sum)
 

@@ -26,6 +26,19 @@ def geo_embed_project(idx4, w_d, w_a, bias_sum):
     return out
 
 
+def geo_embed_lookup(idx4, table_d, table_a, step):
+    """idx4 (rows, 4) fp32; table_d (nd, C), table_a (na, C) bf16 tabulated projections with spacing `step`
+    -> (rows, C) bf16 = table_d[round(d / step)] + max_k table_a[round(a_k / step)]."""
+    rows, c = idx4.shape[0], table_d.shape[1]
+    assert table_d.dtype == torch.bfloat16 and table_a.dtype == torch.bfloat16
+    assert table_d.is_contiguous() and table_a.is_contiguous() and table_a.shape[1] == c
+    out = torch.empty((rows, c), dtype=torch.bfloat16, device=idx4.device)
+    _lib.check(_lib.lib().se3et_geo_embed_lookup(
+        _lib.ptr(idx4), _lib.i64(rows), _lib.i64(c), _lib.ptr(table_d), _lib.i64(table_d.shape[0]), _lib.ptr(table_a),
+        _lib.i64(table_a.shape[0]), _lib.f32(step), _lib.ptr(out), _lib.stream_ptr()), "geo_embed_lookup")
+    return out
+
+
 def gemm_grouped_t(a, a_rows, b, b_rows, groups, max_m, n, n_valid, k, out, alpha=1.0):
     """Grouped GEMM with transposed fp32 stores (see se3et_gemm_grouped_bf16)."""
     _lib.check(_lib.lib().se3et_gemm_grouped_bf16(

@@ -265,3 +265,23 @@ def test_transformer_e_matches_oracle_and_reference(gold, gold_e, tag, nlev):
     assert cos(r[0].float().cpu(), want_r, dim=-1).min() > 0.99
     assert cos(s[0].float().cpu(), want_s, dim=-1).min() > 0.99
     assert rel_err(r[0].float().cpu(), want_r) < 5e-2 and rel_err(s[0].float().cpu(), want_s) < 5e-2
+
+
+def test_tabulated_embedding_equals_the_sinusoid_gemm(gold):
+    """se3et_geo_embed_lookup (tabulated W emb(u) + b, step 1/512) against se3et_geo_embed_project (sinusoids generated
+    in the kernel, tcgen05 GEMM) and the fp32 oracle on the same superpoints."""
+    S = helpers.SMALL_CFG
+    rp, sp, _, _ = coarse_inputs(gold)
+    net, sd = build_transformer()
+    pts = rp[None].to(DEV)
+    MT._EMBED_TABLE['on'] = False
+    try:
+        exact = net.embedding(pts)[0].cpu()
+    finally:
+        MT._EMBED_TABLE['on'] = True
+    table = net.embedding(pts)[0].cpu()
+    p = ot.Params(sd, "transformer.embedding.")
+    want = ot.geometric_structure_embedding(p, rp, S["hidden_dim"], S["sigma_d"], S["sigma_a"], S["angle_k"])
+    assert rel_err(table, want) < 6e-3 and rel_err(exact, want) < 6e-3, (rel_err(table, want), rel_err(exact, want))
+    assert torch.allclose(table, want, rtol=2e-2, atol=2e-2)
+    assert rel_err(table, exact) < 8e-3
