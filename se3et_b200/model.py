@@ -121,7 +121,7 @@ class GeoTransformer(nn.Module):
         dev = points.device
         b = cfg.backbone
         dd = precompute_data_stack_mode(points, lengths.to(dev), b.num_stages, b.init_voxel_size, b.init_radius,
-                                        cfg.neighbor_limits)
+                                        cfg.neighbor_limits, backbone_only=num_pairs > 1)
         feats = torch.ones((points.shape[0], 1), dtype=torch.bfloat16, device=dev)
         feats_list = self.backbone(feats, dd)
         feats_c, feats_f = feats_list[-1], feats_list[0]

@@ -9,12 +9,16 @@ from . import _lib
 from .ops import grid_subsample, radius_search_deferred
 
 
-def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, neighbor_limits, normals=None):
+def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, neighbor_limits, normals=None,
+                               backbone_only=False):
     """`lengths` = [ref, src] reproduces the reference exactly (matrix widths min(max_count, limit), 2000-superpoint
     cap). `lengths` = [ref_1, src_1, ref_2, src_2, ...] stacks several pairs in one launch sequence: the dict then
     also carries 'pair_offsets' (per level, int64 [P+1]) and 'subsampling_width' (per level, int32 [P]: the width
     the reference's subsampling matrix would have for that pair alone), neighbour matrices keep `limit` columns
-    (extra columns are padding) and no host sync is needed for the searches."""
+    (extra columns are padding) and no host sync is needed for the searches.
+    backbone_only=True (what GeoTransformer.forward_stacked asks for): only what the E2PN backbone consumes is
+    searched -- nearest_upsample reads column 0 of upsampling[1:] (kpconv/functional.py:21) and nothing reads
+    upsampling[0] (the fine features live on level 1), so upsampling[0] is None and the others keep one column."""
     assert num_stages == len(neighbor_limits)
     num_pairs = lengths.shape[0] // 2
     batched = lengths.shape[0] > 2
@@ -64,8 +68,11 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
         if i < num_stages - 1:
             sub_points, sub_lengths = points_list[i + 1], lengths_list[i + 1]
             search(subsampling_list, sub_points, cur_points, sub_lengths, cur_lengths, radius, neighbor_limits[i])
-            search(upsampling_list, cur_points, sub_points, cur_lengths, sub_lengths, radius * 2,
-                   neighbor_limits[i + 1])
+            if backbone_only and i == 0:
+                upsampling_list.append(None)
+            else:
+                search(upsampling_list, cur_points, sub_points, cur_lengths, sub_lengths, radius * 2,
+                       1 if backbone_only else neighbor_limits[i + 1])
         radius *= 2
 
     if pending and not batched:
