@@ -33,6 +33,9 @@ WORKLOADS = {
                 "~15k pts/cloud, voxel 0.025 m, 4 stages"),
     "kitti": ("se3eti.kitti", "kitti_shape_pairs_per_sec", "make_kitti_pair",
               "~30k pts/cloud, voxel 0.3 m, 5 stages"),
+    # BASELINE.json configs[2]: SE3ET-E on ~5k-point pairs (a 1.5 m crop of the 3DMatch-shaped fragments)
+    "3dmatch-e": ("se3ete.3dmatch", "3dmatch_5k_shape_pairs_per_sec", "make_3dmatch_pair_5k",
+                  "~5k pts/cloud, voxel 0.025 m, 4 stages, SE3ET-E"),
 }
 
 
@@ -87,7 +90,18 @@ class ClockSampler(threading.Thread):
 
 def make_pairs(count, first=0, generator="make_3dmatch_pair"):
     from se3et_b200 import synthetic
-    pairs = [getattr(synthetic, generator)(first + i) for i in range(count)]
+    if generator == "make_3dmatch_pair_5k":
+        pairs, i = [], first
+        while len(pairs) < count:  # some seeds leave too little inside the crop
+            try:
+                p = synthetic.make_3dmatch_pair(i, crop=1.5)
+                if min(len(p["ref_points"]), len(p["src_points"])) > 2000:
+                    pairs.append(p)
+            except ValueError:
+                pass
+            i += 1
+    else:
+        pairs = [getattr(synthetic, generator)(first + i) for i in range(count)]
     return [(p["ref_points"], p["src_points"]) for p in pairs]
 
 
