@@ -107,6 +107,7 @@ def make_pairs(count, first=0, generator="make_3dmatch_pair"):
 
 NCU_KERNEL = {"se3et_kpconv_fused": "kpconv_fused_kernel", "se3et_gemm_bf16_gnstats": "gemm_tma_kernel",
               "se3et_gemm_bf16_gnapply": "gemm_tma_kernel", "se3et_gemm_grouped_bf16": "gemm_tma_kernel",
+              "se3et_gemm_bf16_gnapply_dual": "gemm_dual_gnapply_kernel", "se3et_linear_gnstats_gram": "gram_kernel",
               "se3et_geo_embed_project": "geo_embed_project_kernel", "se3et_geo_embed_lookup": "geo_embed_lookup_kernel", "se3et_radius_neighbors": "radius_query_kernel",
               "se3et_groupnorm_double": "groupnorm_double_kernel", "se3et_flash_attention": "flash_attention_kernel"}
 
@@ -138,25 +139,29 @@ def algorithmic_work(cfg, n_levels, n_ref_c, n_src_c, limits):
     d = cfg.backbone.init_dim
     S = cfg.backbone.num_stages
     conv_flops = hmma_flops = 0.0
-    gemm_flops = gemm_bytes = 0.0
-    apply_bytes = 0.0
+    norm_bytes = 0.0
+    # Linear + GroupNorm passes (ops/gemm.py): statistics (GEMM epilogue or Gram matrix of the input), apply, dual apply
+    ub = {"stats": 0.0, "gram": 0.0, "apply": 0.0, "dual": 0.0}
 
-    def unary(rows, k, n, resid):
-        nonlocal gemm_flops, gemm_bytes
-        gemm_flops += 2 * 2.0 * rows * k * n                      # statistics pass + apply pass
-        gemm_bytes += 2 * rows * k * 2 + rows * n * 2 * (2 if resid else 1)
+    def stats_pass(rows, k, n):
+        ub["gram" if (k in (32, 64, 128) and n >= 2 * k) else "stats"] += rows * k * 2
 
     def block(nq, ns, h, cin, cout, strided):
-        nonlocal conv_flops, hmma_flops, apply_bytes
+        nonlocal conv_flops, hmma_flops, norm_bytes
         mid = cout // 4
         if cin != mid:
-            unary(6.0 * ns, cin, mid, False)
+            stats_pass(6.0 * ns, cin, mid)
+            ub["apply"] += 6.0 * ns * (cin + mid) * 2
         conv_flops += 2.0 * nq * 6 * 36 * mid * mid              # class-pre-summed contraction (issued on tcgen05)
         hmma_flops += 2.0 * nq * 6 * mid * 16 * 48               # 16-row basis x 48 padded neighbours (mma.sync)
-        apply_bytes += nq * 6 * mid * (4 + 4 + 2)  # double GroupNorm: statistics pass + apply pass over fp32, bf16 out
+        norm_bytes += nq * 6 * mid * (4 + 4 + 2)  # double GroupNorm: statistics pass + apply pass over fp32, bf16 out
+        rows = 6.0 * nq
+        stats_pass(rows, mid, cout)
         if cin != cout:
-            unary(6.0 * nq, cin, cout, False)
-        unary(6.0 * nq, mid, cout, True)
+            stats_pass(rows, cin, cout)
+            ub["dual"] += rows * (mid + cin + cout) * 2          # both inputs in, the block output out
+        else:
+            ub["apply"] += rows * (mid + 2 * cout) * 2           # input, residual in, output out
 
     width = 2 * d
     block(n_levels[0], n_levels[0], limits[0], d, 2 * d, False)
@@ -173,8 +178,9 @@ def algorithmic_work(cfg, n_levels, n_ref_c, n_src_c, limits):
     search_bytes += sum(8.0 * n_levels[i + 1] * limits[i] + 8.0 * n_levels[i] * limits[i + 1] for i in range(S - 1))
     return {
         "se3et_kpconv_fused": ("tensor", conv_flops + hmma_flops),
-        "se3et_gemm_bf16_gnstats": ("hbm", gemm_bytes * 0.5), "se3et_gemm_bf16_gnapply": ("hbm", gemm_bytes * 0.5),
-        "se3et_groupnorm_double": ("hbm", apply_bytes),
+        "se3et_gemm_bf16_gnstats": ("hbm", ub["stats"]), "se3et_linear_gnstats_gram": ("hbm", ub["gram"]),
+        "se3et_gemm_bf16_gnapply": ("hbm", ub["apply"]), "se3et_gemm_bf16_gnapply_dual": ("hbm", ub["dual"]),
+        "se3et_groupnorm_double": ("hbm", norm_bytes),
         "se3et_geo_embed_project": ("tensor", 8.0 * nn2 * c * c),
         # tabulated embedding: index row in, bf16 row out (the table reads hit L2)
         "se3et_geo_embed_lookup": ("hbm", nn2 * (16.0 + 2.0 * c)),
@@ -337,7 +343,8 @@ def main():
 
     # ---- timed region: K steps, CUDA events, per-entry-point events for the roofline
     timed_names = ["se3et_kpconv_fused", "se3et_kpconv_cin1", "se3et_kpconv_gather", "se3et_gemm_bf16", "se3et_gemm_bf16_gnstats",
-                   "se3et_gemm_bf16_gnapply", "se3et_gemm_grouped_bf16", "se3et_groupnorm_double",
+                   "se3et_gemm_bf16_gnapply", "se3et_gemm_bf16_gnapply_dual", "se3et_linear_gnstats_gram",
+                   "se3et_gemm_grouped_bf16", "se3et_groupnorm_double",
                    "se3et_groupnorm_apply", "se3et_groupnorm_stats", "se3et_maxpool_nbr", "se3et_radius_neighbors", "se3et_grid_subsample",
                    "se3et_geo_embed_project", "se3et_geo_embed_lookup", "se3et_geo_embed_indices", "se3et_flash_attention",
                    "se3et_superpoint_matching"]

@@ -130,6 +130,31 @@ int se3et_gemm_bf16_gnapply(const void* a, int64_t lda, const void* b, int64_t l
                             const int64_t* seg_offsets, int64_t nseg, int64_t groups, int64_t rows_per_point,
                             se3et_stream_t stream);
 
+/* GroupNorm statistics of y = A W^T + bias WITHOUT forming y (UnaryBlockEPN, blocks_epn.py:639-665, when the Linear
+ * widens): one pass over A accumulates per pair the Gram matrix A^T A and the column sums (mma.sync, fp32 per CTA, fp64
+ * across CTAs), then sum y_j = w_j.s + R b_j and sum y_j^2 = w_j^T G w_j + 2 b_j w_j.s + R b_j^2 per channel in fp64.
+ * Same `stats` layout as se3et_gemm_bf16_gnstats ([nseg, groups, 2] {sum, sum sq}).  k must be 32, 64 or 128
+ * (SE3ET_ERR_UNSUPPORTED otherwise).  upper_tiles: 0, or an upper bound of sum_pairs ceil(rows / 128).
+ * workspace: se3et_linear_gnstats_gram_workspace_bytes(k, nseg). */
+int se3et_linear_gnstats_gram_workspace_bytes(int64_t k, int64_t nseg, size_t* bytes);
+int se3et_linear_gnstats_gram(const void* a, int64_t lda, int64_t m, int64_t k, const void* w_bf16, int64_t ldw,
+                              int64_t n, const float* bias, const int64_t* seg_offsets, int64_t nseg, int64_t groups,
+                              int64_t rows_per_point, int64_t upper_tiles, void* workspace, size_t workspace_bytes,
+                              double* stats, se3et_stream_t stream);
+
+/* Tail of ResnetBottleneckBlockEPN (blocks_epn.py:833-852) in one kernel:
+ *   out_bf16 = LeakyReLU_slope( GroupNorm_1(A1 B1^T + bias1) + GroupNorm_2(A2 B2^T + bias2) )
+ * unary2 on the conv branch (A1: [m, k1]) and the shortcut unary (A2: [m, k2]); both Linears are recomputed into two TMEM
+ * accumulators, their statistics come from se3et_gemm_bf16_gnstats passes (out_f32 = NULL).  B1: [n, k1], B2: [n, k2]
+ * (nn.Linear weights).  tile_n = 0 picks the output tile width (32 / 64 / 128 forces it). */
+int se3et_gemm_bf16_gnapply_dual(const void* a1, int64_t lda1, const void* b1, int64_t ldb1, int64_t k1,
+                                 const float* bias1, const double* stats1, const float* gamma1, const float* beta1,
+                                 const void* a2, int64_t lda2, const void* b2, int64_t ldb2, int64_t k2,
+                                 const float* bias2, const double* stats2, const float* gamma2, const float* beta2,
+                                 int64_t m, int64_t n, float eps, float leaky_slope, void* out_bf16, int64_t ldc,
+                                 const int64_t* seg_offsets, int64_t nseg, int64_t groups, int64_t rows_per_point,
+                                 int tile_n, se3et_stream_t stream);
+
 /* Grouped variant: problem g (blockIdx.z) reads A rows [a_row0, a_row0 + m_rows) and B rows
  * [b_row0, b_row0 + n) of the flat operands, groups = int64 [num_groups][6] {a_row0, b_row0, m_rows, c_off,
  * ldc, unused} on the device; max_m = largest m_rows.  transposed = 1 stores

@@ -142,7 +142,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       for (int t = 0; t < ntiles; ++t) {
         const int a_row = (int)a_row0 + (tile0 + t) * kGemmBM;
         for (int kb = 0; kb < num_kb; ++kb) {
-          tc::mbar_wait(&empty_bar[s], phase ^ 1);
+          tc::mbar_wait_long(&empty_bar[s], phase ^ 1);
           tc::mbar_arrive_expect_tx(&full_bar[s], S::kStageBytes);
           uint8_t* a_dst = smem + s * S::kStageBytes;
           tc::tma_load_2d(a_dst, &tma_a, &full_bar[s], kb * kGemmBK, a_row);
@@ -159,11 +159,11 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       for (int t = 0; t < ntiles; ++t) {
         const int buf = t % kAccBufs;
         const uint32_t use = (uint32_t)(t / kAccBufs);
-        tc::mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);  // the epilogue has drained this accumulator buffer
+        tc::mbar_wait_long(&tmem_empty_bar[buf], (use & 1) ^ 1);  // the epilogue has drained this accumulator buffer
         tc::tcgen05_fence_after_sync();
         const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * kTmemCols);
         for (int kb = 0; kb < num_kb; ++kb) {
-          tc::mbar_wait(&full_bar[s], phase);
+          tc::mbar_wait_long(&full_bar[s], phase);
           tc::tcgen05_fence_after_sync();
           const uint32_t a_addr = tc::smem_u32(smem + s * S::kStageBytes);
           const uint64_t a_desc = tc::umma_desc_sw128(a_addr);
@@ -240,7 +240,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
       }
-      tc::mbar_wait(&tmem_full_bar[buf], use & 1);
+      tc::mbar_wait_long(&tmem_full_bar[buf], use & 1);
       tc::tcgen05_fence_after_sync();
       if (ep.norm_stats) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");

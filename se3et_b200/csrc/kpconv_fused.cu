@@ -256,7 +256,7 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
           cp_async_wait<2>();
           __syncwarp();
           if (a == 0) {
-            tc::mbar_wait(a_empty, (gc & 1) ^ 1);  // the MMA of the previous chunk has consumed the operand tile
+            tc::mbar_wait_long(a_empty, (gc & 1) ^ 1);  // the MMA of the previous chunk has consumed the operand tile
           }
           float d[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
           const uint32_t xsb = xs_s + (a % kFStages) * xstage;
@@ -310,7 +310,7 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
 
       // ---- epilogue (warps 0-3 own TMEM lanes 32 w .. 32 w + 31 = operand rows) ------------------------------
       if (warp < 4) {
-        tc::mbar_wait(tmem_full, titer & 1);
+        tc::mbar_wait_long(tmem_full, titer & 1);
         tc::tcgen05_fence_after_sync();
         const int m = warp * 32 + lane;
         const int64_t grow = tile * kFRows + m;
@@ -375,13 +375,13 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
       constexpr uint32_t idesc = tc::umma_idesc_bf16(128, BN);
       uint32_t gc = 0, titer = 0, ws = 0, wphase = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++titer) {
-        tc::mbar_wait(tmem_empty, (titer & 1) ^ 1);  // the epilogue has drained the previous tile's accumulators
+        tc::mbar_wait_long(tmem_empty, (titer & 1) ^ 1);  // the epilogue has drained the previous tile's accumulators
         tc::tcgen05_fence_after_sync();
         for (int chunk = 0; chunk < nchunks; ++chunk, ++gc) {
-          tc::mbar_wait(a_full, gc & 1);
+          tc::mbar_wait_long(a_full, gc & 1);
           tc::tcgen05_fence_after_sync();
           for (int kb = 0; kb < kFKBlocks; ++kb) {
-            tc::mbar_wait(&w_full[ws], wphase);
+            tc::mbar_wait_long(&w_full[ws], wphase);
             tc::tcgen05_fence_after_sync();
             const uint64_t a_desc = tc::umma_desc_sw128(tc::smem_u32(a_tile + kb * kFKBlockBytes));
             const uint64_t b_desc = tc::umma_desc_sw128(tc::smem_u32(w_tile + ws * S::kWStage));
@@ -404,7 +404,7 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int chunk = 0; chunk < nchunks; ++chunk) {
           for (int kb = 0; kb < kFKBlocks; ++kb) {
-            tc::mbar_wait(&w_empty[ws], wphase ^ 1);
+            tc::mbar_wait_long(&w_empty[ws], wphase ^ 1);
             tc::mbar_arrive_expect_tx(&w_full[ws], BN * 128);
             tc::tma_load_2d(w_tile + ws * S::kWStage, &tma_w, &w_full[ws], (chunk * kFKBlocks + kb) * 64, n0);
             if (++ws == (uint32_t)wstages) { ws = 0; wphase ^= 1; }

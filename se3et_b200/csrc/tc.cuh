@@ -39,6 +39,40 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Waits that are expected to last: polling warps take issue slots and shared-memory bandwidth from the warps they wait for
+// (half of the executed instructions of the fused KPConv kernel were PHASECHK / BRA / YIELD of such loops).
+#ifndef SE3ET_WAIT_MODE
+#define SE3ET_WAIT_MODE 1
+#endif
+#ifndef SE3ET_WAIT_NS
+#define SE3ET_WAIT_NS 64
+#endif
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_long(uint64_t* bar, uint32_t parity) {
+#if SE3ET_WAIT_MODE == 0
+  mbar_wait(bar, parity);
+#elif SE3ET_WAIT_MODE == 1
+  while (!mbar_try_wait_hint(bar, parity, 100000u)) {
+  }
+#else
+  if (mbar_try_wait(bar, parity)) return;
+  do {
+    __nanosleep(SE3ET_WAIT_NS);
+  } while (!mbar_try_wait(bar, parity));
+#endif
+}
 
 // ---- proxies / fences ---------------------------------------------------------------------------
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)

@@ -167,7 +167,7 @@ geo_embed_project_kernel(const __grid_constant__ CUtensorMap tma_wd, const __gri
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kEpStages;
         const uint32_t phase = (kb / kEpStages) & 1;
-        tc::mbar_wait(&empty_bar[s], phase ^ 1);
+        tc::mbar_wait_long(&empty_bar[s], phase ^ 1);
         tc::mbar_arrive_expect_tx(&full_bar[s], S::kBBytes);
         uint8_t* b_dst = smem + s * S::kStageBytes + S::kABytes;
         tc::tma_load_2d(b_dst, &tma_wd, &full_bar[s], kb * 64, n0);
@@ -180,7 +180,7 @@ geo_embed_project_kernel(const __grid_constant__ CUtensorMap tma_wd, const __gri
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kEpStages;
         const uint32_t phase = (kb / kEpStages) & 1;
-        tc::mbar_wait(&full_bar[s], phase);
+        tc::mbar_wait_long(&full_bar[s], phase);
         tc::tcgen05_fence_after_sync();
         const uint32_t a_addr = tc::smem_u32(smem + s * S::kStageBytes);
         const uint32_t b_addr = a_addr + S::kABytes;
@@ -210,7 +210,7 @@ geo_embed_project_kernel(const __grid_constant__ CUtensorMap tma_wd, const __gri
     for (int kb = 0; kb < num_kb; ++kb) {
       const int s = kb % kEpStages;
       const uint32_t phase = (kb / kEpStages) & 1;
-      tc::mbar_wait(&empty_bar[s], phase ^ 1);
+      tc::mbar_wait_long(&empty_bar[s], phase ^ 1);
       uint8_t* a_base = smem + s * S::kStageBytes;
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
@@ -235,7 +235,7 @@ geo_embed_project_kernel(const __grid_constant__ CUtensorMap tma_wd, const __gri
       tc::mbar_arrive(&full_bar[s]);
     }
     // epilogue
-    tc::mbar_wait(tmem_full_bar, 0);
+    tc::mbar_wait_long(tmem_full_bar, 0);
     tc::tcgen05_fence_after_sync();
 #pragma unroll 1
     for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 16) {

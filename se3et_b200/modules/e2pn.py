@@ -17,14 +17,15 @@ from torch.nn.parameter import Parameter
 
 from .. import _lib
 from ..ops import e2pn_ops as K
-from ..ops.gemm import _gn_fusable, linear_bf16, linear_gn_apply, linear_gn_stats
+from ..ops.gemm import (_gn_fusable, dual_apply_supported, linear_bf16, linear_gn_apply, linear_gn_apply_dual,
+                        linear_gn_stats)
 from . import octahedral
 
 
 # switches for A/B measurements and tests (the defaults are the product path)
 # 'cin1_kernel': the CUDA-core first-layer kernel (csrc/kpconv.cu) measures slower than gather + GEMM on B200
 # (9.6 vs 8.4 ms per 64 pairs), so it is off by default and only exercised by the tests
-_GFLAGS = {'fused_kpconv': True, 'two_pass_unary': True, 'double_norm': True, 'cin1_kernel': False}
+_GFLAGS = {'fused_kpconv': True, 'two_pass_unary': True, 'double_norm': True, 'cin1_kernel': False, 'dual_apply': True}
 
 
 def _gn_fusable_fused(cout, groups):
@@ -358,6 +359,15 @@ class ResnetBottleneckBlockEPN(nn.Module):
             _, st2 = self.unary2.pre_norm(y3, seg, 6, store=False)
             if has_skip_conv:
                 _, st_s = self.skip_conv.pre_norm(skip, seg, 6, store=False)
+                if _GFLAGS['dual_apply'] and dual_apply_supported(self.out_dim, y3.shape[-1], self.in_dim):
+                    # both Linears recomputed into two accumulators of one kernel: the normalised shortcut is never stored
+                    u2, sc = self.unary2, self.skip_conv
+                    return linear_gn_apply_dual(
+                        y3.reshape(-1, u2.in_dim), u2._w_cache.get(u2.mlp.weight), u2.mlp.bias, st2,
+                        u2.norm.norm.weight, u2.norm.norm.bias,
+                        _act(skip).reshape(-1, sc.in_dim), sc._w_cache.get(sc.mlp.weight), sc.mlp.bias, st_s,
+                        sc.norm.norm.weight, sc.norm.norm.bias, u2.norm.norm.eps, 0.1, u2.norm.num_groups, seg,
+                        6).view(nq, 6, self.out_dim)
                 resid = self.skip_conv.apply(skip, st_s, seg, 6, 1.0)
             else:
                 resid = skip.contiguous().view(nq * 6, self.out_dim)

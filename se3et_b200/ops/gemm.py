@@ -1,4 +1,6 @@
 """Host wrapper of se3et_gemm_bf16 (tcgen05 GEMM): out = alpha * a @ b.T (+ bias) (ReLU)."""
+import ctypes
+
 import torch
 
 from .. import _lib
@@ -109,6 +111,8 @@ def linear_gn_stats(a, w, bias, groups, seg_off, rows_per_point, store=True):
     _check_ab(a, w, bias)
     assert seg_off.dtype == torch.int64
     nseg = seg_off.numel() - 1
+    if not store and gram_stats_supported(n, k) and a.stride(0) % 8 == 0:
+        return None, linear_gn_stats_gram(a, w, bias, groups, seg_off, rows_per_point)
     y = torch.empty((m, n), dtype=torch.float32, device=a.device) if store else None
     stats = torch.empty((nseg, groups, 2), dtype=torch.float64, device=a.device)
     _lib.check(_lib.lib().se3et_gemm_bf16_gnstats(
@@ -138,3 +142,61 @@ def linear_gn_apply(a, w, bias, stats, gamma, beta, eps, slope, groups, seg_off,
         _lib.f32(eps), _lib.f32(slope), _lib.ptr(resid), _lib.ptr(out), _lib.i64(n), _lib.ptr(seg_off),
         _lib.i64(nseg), _lib.i64(groups), _lib.i64(rows_per_point), _lib.stream_ptr()), "gemm_bf16_gnapply")
     return out
+
+
+_DUAL_TILE = {'n': 0}
+
+
+def linear_gn_apply_dual(a1, w1, bias1, stats1, gamma1, beta1, a2, w2, bias2, stats2, gamma2, beta2, eps, slope, groups,
+                         seg_off, rows_per_point):
+    """bf16 LeakyReLU_slope(GroupNorm(a1 @ w1.T + bias1) + GroupNorm(a2 @ w2.T + bias2)) in one kernel: the tail of
+    ResnetBottleneckBlockEPN (blocks_epn.py:833-852).  Statistics from linear_gn_stats(..., store=False)."""
+    _check_ab(a1, w1, bias1)
+    _check_ab(a2, w2, bias2)
+    m, k1 = a1.shape
+    k2 = a2.shape[1]
+    n = w1.shape[0]
+    assert a2.shape[0] == m and w2.shape[0] == n and n % groups == 0
+    assert seg_off.dtype == torch.int64 and stats1.dtype == torch.float64 and stats2.dtype == torch.float64
+    out = torch.empty((m, n), dtype=torch.bfloat16, device=a1.device)
+    if m == 0:
+        return out
+    nseg = seg_off.numel() - 1
+    _lib.check(_lib.lib().se3et_gemm_bf16_gnapply_dual(
+        _lib.ptr(a1), _lib.i64(a1.stride(0) if m > 1 else k1), _lib.ptr(w1), _lib.i64(w1.stride(0) if n > 1 else k1),
+        _lib.i64(k1), _lib.ptr(bias1), _lib.ptr(stats1), _lib.ptr(gamma1), _lib.ptr(beta1),
+        _lib.ptr(a2), _lib.i64(a2.stride(0) if m > 1 else k2), _lib.ptr(w2), _lib.i64(w2.stride(0) if n > 1 else k2),
+        _lib.i64(k2), _lib.ptr(bias2), _lib.ptr(stats2), _lib.ptr(gamma2), _lib.ptr(beta2),
+        _lib.i64(m), _lib.i64(n), _lib.f32(eps), _lib.f32(slope), _lib.ptr(out), _lib.i64(n), _lib.ptr(seg_off),
+        _lib.i64(nseg), _lib.i64(groups), _lib.i64(rows_per_point), ctypes.c_int(_DUAL_TILE['n']),
+        _lib.stream_ptr()), "gemm_bf16_gnapply_dual")
+    return out
+
+
+def dual_apply_supported(n, k1, k2):
+    return n % 32 == 0 and k1 % 8 == 0 and k2 % 8 == 0
+
+
+_GRAM = {'on': True}
+
+
+def gram_stats_supported(n, k):
+    """The Gram-matrix statistics pass pays off when the Linear widens (its cost does not depend on n)."""
+    return _GRAM['on'] and k in (32, 64, 128) and n >= 2 * k
+
+
+def linear_gn_stats_gram(a, w, bias, groups, seg_off, rows_per_point):
+    """GroupNorm statistics of a @ w.T + bias from the Gram matrix of `a` (se3et_linear_gnstats_gram): y is never formed."""
+    _check_ab(a, w, bias)
+    m, k = a.shape
+    n = w.shape[0]
+    nseg = seg_off.numel() - 1
+    stats = torch.empty((nseg, groups, 2), dtype=torch.float64, device=a.device)
+    nbytes = 8 * nseg * (k + 1) * k
+    ws = _lib.workspace.get(nbytes, a.device)
+    _lib.check(_lib.lib().se3et_linear_gnstats_gram(
+        _lib.ptr(a), _lib.i64(a.stride(0) if m > 1 else k), _lib.i64(m), _lib.i64(k), _lib.ptr(w),
+        _lib.i64(w.stride(0) if n > 1 else k), _lib.i64(n), _lib.ptr(bias), _lib.ptr(seg_off), _lib.i64(nseg),
+        _lib.i64(groups), _lib.i64(rows_per_point), _lib.i64(0), _lib.ptr(ws), ctypes.c_size_t(ws.numel()),
+        _lib.ptr(stats), _lib.stream_ptr()), "linear_gnstats_gram")
+    return stats

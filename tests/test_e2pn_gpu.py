@@ -210,6 +210,76 @@ def test_gemm_groupnorm_apply_epilogue(n_out, groups, k, rpp):
         assert torch.allclose(got.float().cpu(), ref, rtol=2e-2, atol=2e-2), (got.float().cpu() - ref).abs().max()
 
 
+@pytest.mark.parametrize("n_out,groups,k1,k2,rpp,tile_n", [(128, 32, 32, 64, 6, 0), (128, 32, 32, 64, 6, 64),
+                                                            (256, 32, 64, 128, 6, 0), (512, 32, 128, 256, 6, 0),
+                                                            (1024, 32, 256, 512, 6, 64), (64, 16, 16, 32, 6, 0),
+                                                            (96, 8, 24, 40, 1, 32)])
+def test_gemm_groupnorm_apply_dual(n_out, groups, k1, k2, rpp, tile_n):
+    """se3et_gemm_bf16_gnapply_dual -- LeakyReLU(GN(a1 w1^T + b1) + GN(a2 w2^T + b2)), the residual tail of
+    ResnetBottleneckBlockEPN (blocks_epn.py:833-852) -- against torch fp32; pair boundaries fall inside tiles."""
+    from se3et_b200.ops import gemm as G
+    g = torch.Generator().manual_seed(n_out + k1)
+    pts = [150, 0, 333, 41]
+    seg = torch.tensor(np.concatenate([[0], np.cumsum(pts)]), dtype=torch.int64, device=DEV)
+    rows = rpp * sum(pts)
+    ops = []
+    want = 0
+    for k in (k1, k2):
+        a = (torch.randn(rows, k, generator=g) + 0.3).to(torch.bfloat16)
+        w = (torch.randn(n_out, k, generator=g) / k ** 0.5).to(torch.bfloat16)
+        bias, gamma, beta = (torch.randn(n_out, generator=g) for _ in range(3))
+        y = a.float() @ w.float().t() + bias
+        parts = []
+        for i in range(len(pts)):
+            blk = y[rpp * int(seg[i]):rpp * int(seg[i + 1])]
+            if blk.numel():
+                parts.append(oe.group_norm_epn(blk.view(-1, rpp, n_out), groups, gamma, beta).reshape(-1, n_out))
+        want = want + torch.cat(parts)
+        ad, wd, bd = a.to(DEV), w.to(DEV), bias.to(DEV)
+        _, stats = G.linear_gn_stats(ad, wd, bd, groups, seg, rpp, store=False) if G._gn_fusable(n_out, groups) else \
+            G.linear_gn_stats(ad, wd, bd, groups, seg, rpp, store=True)
+        ops.append((ad, wd, bd, stats, gamma.to(DEV), beta.to(DEV)))
+    want = torch.nn.functional.leaky_relu(want, 0.1)
+    G._DUAL_TILE['n'] = tile_n
+    try:
+        got = G.linear_gn_apply_dual(*ops[0], *ops[1], 1e-5, 0.1, groups, seg, rpp)
+    finally:
+        G._DUAL_TILE['n'] = 0
+    assert torch.allclose(got.float().cpu(), want, rtol=2e-2, atol=2e-2), (got.float().cpu() - want).abs().max()
+
+
+@pytest.mark.parametrize("n_out,groups,k,rpp", [(128, 32, 32, 6), (128, 32, 64, 6), (256, 32, 64, 6), (512, 32, 128, 6),
+                                                 (64, 16, 32, 1)])
+def test_linear_gnstats_gram(n_out, groups, k, rpp):
+    """se3et_linear_gnstats_gram (statistics of a w^T + b from the Gram matrix of a) against fp64 torch and against the
+    GEMM-epilogue statistics pass; empty pairs, pairs shorter than a tile, pair ends inside tiles."""
+    from se3et_b200.ops import gemm as G
+    g = torch.Generator().manual_seed(n_out + k)
+    pts = [150, 0, 333, 5, 4100]
+    seg = torch.tensor(np.concatenate([[0], np.cumsum(pts)]), dtype=torch.int64, device=DEV)
+    rows = rpp * sum(pts)
+    a = (torch.randn(rows, k, generator=g) + 0.3).to(torch.bfloat16)
+    w = (torch.randn(n_out, k, generator=g) / k ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(n_out, generator=g)
+    y = a.double() @ w.double().t() + bias.double()
+    want = torch.zeros(len(pts), groups, 2, dtype=torch.float64)
+    for i in range(len(pts)):
+        blk = y[rpp * int(seg[i]):rpp * int(seg[i + 1])].view(-1, groups, n_out // groups)
+        want[i, :, 0] = blk.sum(dim=(0, 2))
+        want[i, :, 1] = (blk * blk).sum(dim=(0, 2))
+    ad, wd, bd = a.to(DEV), w.to(DEV), bias.to(DEV)
+    got = G.linear_gn_stats_gram(ad, wd, bd, groups, seg, rpp).cpu()
+    scale = want[:, :, 1].abs().max(dim=1, keepdim=True)[0].clamp_min(1.0)
+    assert float(((got[:, :, 1] - want[:, :, 1]).abs() / scale).max()) < 2e-5
+    assert float(((got[:, :, 0] - want[:, :, 0]).abs() / scale).max()) < 2e-5
+    G._GRAM['on'] = False
+    try:
+        _, ep = G.linear_gn_stats(ad, wd, bd, groups, seg, rpp, store=False)
+    finally:
+        G._GRAM['on'] = True
+    assert float(((got - ep.cpu()).abs() / scale.unsqueeze(-1)).max()) < 1e-4
+
+
 @pytest.mark.parametrize("c,G,rpp", [(32, 32, 6), (128, 32, 6), (1024, 32, 6), (256, 32, 1), (48, 16, 6), (2048, 32, 6)])
 def test_groupnorm_apply_two_operands_and_residual(c, G, rpp):
     """act(GN_a(ya) + GN_b(yb)) and act(GN_a(ya) + resid) against torch, several pairs of different sizes."""
