@@ -123,12 +123,18 @@ int se3et_gemm_bf16_gnstats(const void* a, int64_t lda, const void* b, int64_t l
  * in the epilogue, mean / rstd per (pair, group) from `stats` (as produced by se3et_gemm_bf16_gnstats with
  * out_f32 = NULL, which then only accumulates).  The pre-norm activations never reach global memory:
  * UnaryBlockEPN and the residual tail of ResnetBottleneckBlockEPN (blocks_epn.py:639-665, 833-852).
- * resid_bf16 (optional) has the output's shape and pitch.  slope = 1 disables the activation. */
+ * resid_bf16 (optional) has the output's shape and pitch.  slope = 1 disables the activation.
+ * workspace: 16 * n * nseg bytes (16-byte aligned) for the per-(pair, column) scale / shift table of the streaming kernel
+ * (persistent CTAs, eight epilogue warps; used whenever n % 64 == 0); NULL selects the one-tile-per-CTA kernel. */
 int se3et_gemm_bf16_gnapply(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int64_t n, int64_t k,
                             const float* bias, const double* stats, const float* gamma, const float* beta, float eps,
                             float leaky_slope, const void* resid_bf16, void* out_bf16, int64_t ldc,
                             const int64_t* seg_offsets, int64_t nseg, int64_t groups, int64_t rows_per_point,
-                            se3et_stream_t stream);
+                            void* workspace, size_t workspace_bytes, se3et_stream_t stream);
+
+/* Measurement switch: 0 routes se3et_gemm_bf16_gnapply(_dual) to the one-tile-per-CTA kernels instead of the streaming
+ * kernel (persistent CTAs, eight epilogue warps; the default whenever n % 64 == 0). */
+int se3et_gemm_set_stream_apply(int on);
 
 /* GroupNorm statistics of y = A W^T + bias WITHOUT forming y (UnaryBlockEPN, blocks_epn.py:639-665, when the Linear
  * widens): one pass over A accumulates per pair the Gram matrix A^T A and the column sums (mma.sync, fp32 per CTA, fp64
@@ -153,7 +159,7 @@ int se3et_gemm_bf16_gnapply_dual(const void* a1, int64_t lda1, const void* b1, i
                                  const float* bias2, const double* stats2, const float* gamma2, const float* beta2,
                                  int64_t m, int64_t n, float eps, float leaky_slope, void* out_bf16, int64_t ldc,
                                  const int64_t* seg_offsets, int64_t nseg, int64_t groups, int64_t rows_per_point,
-                                 int tile_n, se3et_stream_t stream);
+                                 int tile_n, void* workspace, size_t workspace_bytes, se3et_stream_t stream);
 
 /* Grouped variant: problem g (blockIdx.z) reads A rows [a_row0, a_row0 + m_rows) and B rows
  * [b_row0, b_row0 + n) of the flat operands, groups = int64 [num_groups][6] {a_row0, b_row0, m_rows, c_off,

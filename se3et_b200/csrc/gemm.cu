@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "gemm_stream.cuh"
 #include "gn_epilogue.cuh"
 #include "tc.cuh"
 
@@ -580,7 +581,8 @@ extern "C" int se3et_gemm_bf16_gnapply(const void* a, int64_t lda, const void* b
                                        int64_t k, const float* bias, const double* stats, const float* gamma,
                                        const float* beta, float eps, float leaky_slope, const void* resid_bf16,
                                        void* out_bf16, int64_t ldc, const int64_t* seg_offsets, int64_t nseg,
-                                       int64_t groups, int64_t rows_per_point, se3et_stream_t stream) {
+                                       int64_t groups, int64_t rows_per_point, void* workspace,
+                                       size_t workspace_bytes, se3et_stream_t stream) {
   if (m < 0 || n <= 0 || k <= 0 || m > INT32_MAX || n > INT32_MAX || k > INT32_MAX) return SE3ET_ERR_ARG;
   if (!stats || !gamma || !beta || !out_bf16 || !seg_offsets || nseg <= 0 || groups <= 0 || n % groups ||
       rows_per_point <= 0)
@@ -592,6 +594,12 @@ extern "C" int se3et_gemm_bf16_gnapply(const void* a, int64_t lda, const void* b
   if (resid_bf16 && (reinterpret_cast<uintptr_t>(resid_bf16) & 15)) return SE3ET_ERR_ARG;
   if (leaky_slope > 1.f) return SE3ET_ERR_ARG;
   if (m == 0) return SE3ET_OK;
+  if (workspace && gemm_stream_supported(n, k, 0, ldc) && !(reinterpret_cast<uintptr_t>(out_bf16) & 15)) {
+    const StreamNorm n1{stats, gamma, beta, bias};
+    return gemm_stream_gnapply(a, lda, b, ldb, k, n1, nullptr, 0, nullptr, 0, 0, n1, m, n, eps, leaky_slope, resid_bf16,
+                               out_bf16, ldc, seg_offsets, nseg, groups, rows_per_point, workspace, workspace_bytes,
+                               static_cast<cudaStream_t>(stream));
+  }
   GemmEpilogue ep;
   ep.out_f32 = nullptr;
   ep.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16);

@@ -12,6 +12,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "gemm_stream.cuh"
 #include "tc.cuh"
 
 namespace se3et {
@@ -247,13 +248,20 @@ extern "C" int se3et_gemm_bf16_gnapply_dual(const void* a1, int64_t lda1, const 
                                             const float* gamma2, const float* beta2, int64_t m, int64_t n, float eps,
                                             float leaky_slope, void* out_bf16, int64_t ldc,
                                             const int64_t* seg_offsets, int64_t nseg, int64_t groups,
-                                            int64_t rows_per_point, int tile_n, se3et_stream_t stream) {
+                                            int64_t rows_per_point, int tile_n, void* workspace,
+                                            size_t workspace_bytes, se3et_stream_t stream) {
   if (m < 0 || n <= 0 || k1 <= 0 || k2 <= 0 || m > INT32_MAX || n > INT32_MAX || k1 > INT32_MAX || k2 > INT32_MAX)
     return SE3ET_ERR_ARG;
   if (!a1 || !b1 || !a2 || !b2 || !stats1 || !gamma1 || !beta1 || !stats2 || !gamma2 || !beta2 || !out_bf16 ||
       !seg_offsets || nseg <= 0 || groups <= 0 || n % groups || rows_per_point <= 0 || leaky_slope > 1.f)
     return SE3ET_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(out_bf16) & 15) || (ldc % 8)) return SE3ET_ERR_ARG;
+  if (tile_n == 0 && m > 0 && workspace && gemm_stream_supported(n, k1, k2, ldc)) {
+    const StreamNorm n1{stats1, gamma1, beta1, bias1}, n2{stats2, gamma2, beta2, bias2};
+    return gemm_stream_gnapply(a1, lda1, b1, ldb1, k1, n1, a2, lda2, b2, ldb2, k2, n2, m, n, eps, leaky_slope, nullptr,
+                               out_bf16, ldc, seg_offsets, nseg, groups, rows_per_point, workspace, workspace_bytes,
+                               static_cast<cudaStream_t>(stream));
+  }
   int bn = tile_n;
   // 64-wide tiles: 128 TMEM columns and ~53 KB per CTA, four CTAs (16 epilogue warps) per SM; measured a little faster
   // than 128-wide tiles (two CTAs per SM by TMEM), the second read of the A tiles hits L2

@@ -199,20 +199,38 @@ __global__ void __launch_bounds__(128) gram_finalize_kernel(const double* __rest
   const double* s = G + (int64_t)K * K;
   const double rows = (double)(seg_off[seg + 1] - seg_off[seg]) * rpp;
   double sum = 0.0, sq = 0.0;
-  for (int jj = 0; jj < cpg; ++jj) {
-    const int j = g * cpg + jj;
-    const __nv_bfloat16* wj = w + (int64_t)j * ldw;
-    const double bj = bias ? (double)bias[j] : 0.0;
+  // eight channels at a time: one pass over column k1 of G (symmetric: G[k2][k1], coalesced over k1) serves all of them
+  __shared__ float wsh[8][128];
+  for (int j0 = 0; j0 < cpg; j0 += 8) {
+    const int nj = min(8, cpg - j0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 8 * K; i += blockDim.x) {
+      const int jj = i / K, k = i - jj * K;
+      wsh[jj][k] = jj < nj ? __bfloat162float(w[(int64_t)(g * cpg + j0 + jj) * ldw + k]) : 0.f;
+    }
+    __syncthreads();
     for (int k1 = threadIdx.x; k1 < K; k1 += blockDim.x) {
-      double t = 0.0;
-      for (int k2 = 0; k2 < K; ++k2) t += G[(int64_t)k2 * K + k1] * (double)__bfloat162float(wj[k2]);  // G is symmetric
-      const double w1 = (double)__bfloat162float(wj[k1]);
-      sq += w1 * t + 2.0 * bj * w1 * s[k1];
-      sum += w1 * s[k1];
+      double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int k2 = 0; k2 < K; ++k2) {
+        const double gv = G[(int64_t)k2 * K + k1];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) t[jj] += gv * (double)wsh[jj][k2];
+      }
+      const double s1 = s[k1];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const double bj = (bias && jj < nj) ? (double)bias[g * cpg + j0 + jj] : 0.0;
+        const double w1 = (double)wsh[jj][k1];
+        sq += w1 * t[jj] + 2.0 * bj * w1 * s1;
+        sum += w1 * s1;
+      }
     }
     if (threadIdx.x == 0) {
-      sum += rows * bj;
-      sq += rows * bj * bj;
+      for (int jj = 0; jj < nj; ++jj) {
+        const double bj = bias ? (double)bias[g * cpg + j0 + jj] : 0.0;
+        sum += rows * bj;
+        sq += rows * bj * bj;
+      }
     }
   }
   __shared__ double sh[2][4];

@@ -136,11 +136,13 @@ def linear_gn_apply(a, w, bias, stats, gamma, beta, eps, slope, groups, seg_off,
     if resid is not None:
         assert resid.dtype == torch.bfloat16 and resid.is_contiguous() and resid.numel() == m * n
     nseg = seg_off.numel() - 1
+    ws = _lib.workspace.get(16 * n * nseg, a.device)
     _lib.check(_lib.lib().se3et_gemm_bf16_gnapply(
         _lib.ptr(a), _lib.i64(a.stride(0) if m > 1 else k), _lib.ptr(w), _lib.i64(w.stride(0) if n > 1 else k),
         _lib.i64(m), _lib.i64(n), _lib.i64(k), _lib.ptr(bias), _lib.ptr(stats), _lib.ptr(gamma), _lib.ptr(beta),
         _lib.f32(eps), _lib.f32(slope), _lib.ptr(resid), _lib.ptr(out), _lib.i64(n), _lib.ptr(seg_off),
-        _lib.i64(nseg), _lib.i64(groups), _lib.i64(rows_per_point), _lib.stream_ptr()), "gemm_bf16_gnapply")
+        _lib.i64(nseg), _lib.i64(groups), _lib.i64(rows_per_point), _lib.ptr(ws), ctypes.c_size_t(ws.numel()),
+        _lib.stream_ptr()), "gemm_bf16_gnapply")
     return out
 
 
@@ -162,6 +164,7 @@ def linear_gn_apply_dual(a1, w1, bias1, stats1, gamma1, beta1, a2, w2, bias2, st
     if m == 0:
         return out
     nseg = seg_off.numel() - 1
+    ws = _lib.workspace.get(16 * n * nseg, a1.device)
     _lib.check(_lib.lib().se3et_gemm_bf16_gnapply_dual(
         _lib.ptr(a1), _lib.i64(a1.stride(0) if m > 1 else k1), _lib.ptr(w1), _lib.i64(w1.stride(0) if n > 1 else k1),
         _lib.i64(k1), _lib.ptr(bias1), _lib.ptr(stats1), _lib.ptr(gamma1), _lib.ptr(beta1),
@@ -169,7 +172,7 @@ def linear_gn_apply_dual(a1, w1, bias1, stats1, gamma1, beta1, a2, w2, bias2, st
         _lib.i64(k2), _lib.ptr(bias2), _lib.ptr(stats2), _lib.ptr(gamma2), _lib.ptr(beta2),
         _lib.i64(m), _lib.i64(n), _lib.f32(eps), _lib.f32(slope), _lib.ptr(out), _lib.i64(n), _lib.ptr(seg_off),
         _lib.i64(nseg), _lib.i64(groups), _lib.i64(rows_per_point), ctypes.c_int(_DUAL_TILE['n']),
-        _lib.stream_ptr()), "gemm_bf16_gnapply_dual")
+        _lib.ptr(ws), ctypes.c_size_t(ws.numel()), _lib.stream_ptr()), "gemm_bf16_gnapply_dual")
     return out
 
 
