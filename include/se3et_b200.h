@@ -212,11 +212,13 @@ int se3et_kpconv_fused(const float* q_pts, const float* s_pts, const int64_t* ne
 /* kpconv_cin1 -- KPConvInterSO3.forward for the first backbone layer (lifted input, one channel per anchor): K is
  * only 36, so the whole convolution runs on CUDA cores, one warp per query point.  x_bf16 [ns, 6]; w_36xcout fp32
  * [(kc, a'), cout] = weights[kc][a'][0][:]; out_f32 [nq * 6, cout]; optional GroupNorm statistics as for
- * se3et_kpconv_fused.  cout 32 or 64, h <= 40; otherwise SE3ET_ERR_UNSUPPORTED (gather + GEMM path). */
+ * se3et_kpconv_fused.  cout 32 or 64, h <= 40; otherwise SE3ET_ERR_UNSUPPORTED (gather + GEMM path).
+ * lifted = 1: the input is the LiftBlockEPN output (blocks_epn.py:993-1004), identical for the six anchors, and x_bf16
+ * is [ns] (one value per support point): 16 basis products and anchor-summed weights per point. */
 int se3et_kpconv_cin1(const float* q_pts, const float* s_pts, const int64_t* neighbors, int64_t nq, int64_t ns,
                       int64_t h, const void* x_bf16, const float* w_36xcout, int64_t cout,
                       const float* kernel_points_15x3, float kp_extent, float* out_f32, double* stats,
-                      const int64_t* seg_offsets, int64_t nseg, int64_t groups, se3et_stream_t stream);
+                      const int64_t* seg_offsets, int64_t nseg, int64_t groups, int lifted, se3et_stream_t stream);
 
 /* Diagnostics: {registers, static smem bytes, max threads per block, local bytes, max dynamic smem} of the fused
  * kernel instantiation for output tile width bn (16, 32, 64 or 128). */

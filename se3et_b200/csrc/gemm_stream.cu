@@ -211,16 +211,34 @@ gemm_stream_gnapply_kernel(const __grid_constant__ CUtensorMap tma_a1, const __g
           row_tab = args.tab + (int64_t)row_seg * args.N + n0;
         }
       }
-      // residual: this thread's 64 bytes of its own row, in flight while the accumulators are produced
-      uint4 res[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+      // residual: the warp's 32 rows x 64 bytes, loaded row-contiguously (four lanes per row) while the accumulators
+      // are produced, then transposed through the staging buffer so that every thread holds its own row
       const bool has_resid = !kDual && args.resid != nullptr;
-      if (has_resid && row_ok) {
-        const uint4* src = reinterpret_cast<const uint4*>(args.resid + row * args.ldc + n0);
+      uint4 res[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+      if (has_resid && warp_ok) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) res[j] = __ldg(src + j);
+        for (int q = 0; q < 4; ++q) {
+          const int i = q * 32 + lane;
+          const int rr = i >> 2, j = i & 3;
+          if (wfirst + rr < args.M)
+            res[q] = __ldg(reinterpret_cast<const uint4*>(args.resid + (wfirst + rr) * args.ldc + n0 + j * 8));
+        }
       }
       tc::mbar_wait_long(&tmem_full_bar[buf], use & 1u);
       tc::tcgen05_fence_after_sync();
+      if (has_resid && warp_ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = q * 32 + lane;
+          const int rr = i >> 2, j = i & 3;
+          *reinterpret_cast<uint4*>(staging + rr * 64 + ((j ^ ((rr >> 1) & 3)) << 4)) = res[q];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          res[c] = *reinterpret_cast<const uint4*>(staging + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4));
+        __syncwarp();
+      }
       if (warp_ok) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {

@@ -171,7 +171,10 @@ __constant__ int8_t c_ridx_tab[6][6] = {
 #undef SE3ET_RI
 };
 
-template <int CPL>  // output channels per lane: cout = 32 * CPL
+// kLifted: the input is the same for all six anchors (LiftBlockEPN output, x[ns] one value per support point).  Then
+// D does not depend on the anchor and out[r][d] = sum_kc D[basis_row(r, kc)] * (sum_a W[kc][a][0][d]): 16 products and
+// 6 weight rows per point instead of 96 and 36.
+template <int CPL, bool kLifted>  // output channels per lane: cout = 32 * CPL
 __global__ void __launch_bounds__(kC1Warps * 32)
 kpconv_cin1_kernel(const float* __restrict__ q_pts, const float* __restrict__ s_pts, const int64_t* __restrict__ idx,
                    int H, int64_t nq, int64_t ns, const __nv_bfloat16* __restrict__ x,
@@ -193,7 +196,16 @@ kpconv_cin1_kernel(const float* __restrict__ q_pts, const float* __restrict__ s_
     sh_dsel[r][t] = (uint8_t)(c_basis_row[r][kc] * kA + a);
     sh_wsel[r][t] = (uint8_t)(kc * kA + c_ridx_tab[a][r]);
   }
-  for (int i = threadIdx.x; i < 36 * COUT; i += blockDim.x) sh_w[i] = w[i];
+  if (kLifted) {  // rows 0-5 of sh_w: weights summed over the anchor slot
+    for (int i = threadIdx.x; i < kA * COUT; i += blockDim.x) {
+      const int kc = i / COUT, d = i - kc * COUT;
+      float t = 0.f;
+      for (int a = 0; a < kA; ++a) t += w[(kc * kA + a) * COUT + d];
+      sh_w[i] = t;
+    }
+  } else {
+    for (int i = threadIdx.x; i < 36 * COUT; i += blockDim.x) sh_w[i] = w[i];
+  }
   if (threadIdx.x < 45) sh_kp[threadIdx.x] = kernel_points[threadIdx.x];
   __syncthreads();
   const int64_t per_cta = (nq + gridDim.x - 1) / gridDim.x;
@@ -221,12 +233,48 @@ kpconv_cin1_kernel(const float* __restrict__ q_pts, const float* __restrict__ s_
         if (!valid) j = 0;
         float row[16];
         basis_weights(s_pts[3 * j] - qx, s_pts[3 * j + 1] - qy, s_pts[3 * j + 2] - qz, sh_kp, inv_extent, valid, row);
+        if (kLifted) {
+          const float f = valid ? __bfloat162float(x[j]) : 0.f;
+#pragma unroll
+          for (int r = 0; r < 16; ++r) sh_w16[warp][n][r] = row[r] * f;
+          continue;
+        }
 #pragma unroll
         for (int r = 0; r < 16; ++r) sh_w16[warp][n][r] = row[r];
 #pragma unroll
         for (int a = 0; a < kA; ++a) sh_x[warp][n][a + (a >= 3)] = valid ? __bfloat162float(x[j * kA + a]) : 0.f;
       }
       __syncwarp();
+      if (kLifted) {
+        // 16 basis products: lane = (basis row, neighbour parity)
+        const int r16 = lane & 15, par = lane >> 4;
+        float a0 = 0.f;
+        for (int n = par; n < H; n += 2) a0 += sh_w16[warp][n][r16];
+        a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+        if (par == 0) sh_d[warp][r16] = a0;
+        __syncwarp();
+#pragma unroll 1
+        for (int r = 0; r < kA; ++r) {
+          float o[CPL];
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) o[c] = 0.f;
+#pragma unroll
+          for (int kc = 0; kc < kA; ++kc) {
+            const float dv = sh_d[warp][c_basis_row[r][kc]];
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) o[c] = fmaf(dv, sh_w[kc * COUT + lane + 32 * c], o[c]);
+          }
+          float* dst = out + (p * kA + r) * COUT + lane;
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) {
+            dst[32 * c] = o[c];
+            st_s[c] += o[c];
+            st_ss[c] = fmaf(o[c], o[c], st_ss[c]);
+          }
+        }
+        __syncwarp();
+        continue;
+      }
       {  // 96 (basis row, anchor) products: lane = (basis row, anchor half), three anchors each
         const int r16 = lane & 15, ah = lane >> 4;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
@@ -316,7 +364,8 @@ int kpconv_gather_mma(const float* q_pts, const float* s_pts, const int64_t* nei
 extern "C" int se3et_kpconv_cin1(const float* q_pts, const float* s_pts, const int64_t* neighbors, int64_t nq, int64_t ns,
                                  int64_t h, const void* x_bf16, const float* w_36xcout, int64_t cout,
                                  const float* kernel_points_15x3, float kp_extent, float* out_f32, double* stats,
-                                 const int64_t* seg_offsets, int64_t nseg, int64_t groups, se3et_stream_t stream) {
+                                 const int64_t* seg_offsets, int64_t nseg, int64_t groups, int lifted,
+                                 se3et_stream_t stream) {
   using namespace se3et;
   if (nq < 0 || ns <= 0 || h <= 0 || cout <= 0 || !(kp_extent > 0.f)) return SE3ET_ERR_ARG;
   if (cout % 32 != 0 || cout > 64 || h > kC1MaxH) return SE3ET_ERR_UNSUPPORTED;  // static shared memory budget
@@ -332,12 +381,15 @@ extern "C" int se3et_kpconv_cin1(const float* q_pts, const float* s_pts, const i
   int64_t blocks = ceil_div(nq, kC1Warps * 4);
   if (blocks > (int64_t)kNumSMs * 4) blocks = (int64_t)kNumSMs * 4;
   const auto* x = static_cast<const __nv_bfloat16*>(x_bf16);
-#define SE3ET_C1(CPL)                                                                                                \
-  kpconv_cin1_kernel<CPL><<<(unsigned)blocks, kC1Warps * 32, 0, st>>>(q_pts, s_pts, neighbors, (int)h, nq, ns, x,    \
-                                                                       w_36xcout, kernel_points_15x3, 1.f / kp_extent, \
-                                                                       out_f32, stats, seg_offsets, (int)nseg, cpg)
-  if (cout == 32) SE3ET_C1(1);
-  else SE3ET_C1(2);
+#define SE3ET_C1(CPL, LIFT)                                                                                          \
+  kpconv_cin1_kernel<CPL, LIFT><<<(unsigned)blocks, kC1Warps * 32, 0, st>>>(                                          \
+      q_pts, s_pts, neighbors, (int)h, nq, ns, x, w_36xcout, kernel_points_15x3, 1.f / kp_extent, out_f32, stats,     \
+      seg_offsets, (int)nseg, cpg)
+  if (cout == 32) {
+    if (lifted) SE3ET_C1(1, true); else SE3ET_C1(1, false);
+  } else {
+    if (lifted) SE3ET_C1(2, true); else SE3ET_C1(2, false);
+  }
 #undef SE3ET_C1
   SE3ET_LAUNCH_CHECK();
   return SE3ET_OK;

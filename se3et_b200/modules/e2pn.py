@@ -25,7 +25,7 @@ from . import octahedral
 # switches for A/B measurements and tests (the defaults are the product path)
 # 'cin1_kernel': the CUDA-core first-layer kernel (csrc/kpconv.cu) measures slower than gather + GEMM on B200
 # (9.6 vs 8.4 ms per 64 pairs), so it is off by default and only exercised by the tests
-_GFLAGS = {'fused_kpconv': True, 'two_pass_unary': True, 'double_norm': True, 'cin1_kernel': False, 'dual_apply': True}
+_GFLAGS = {'fused_kpconv': True, 'two_pass_unary': True, 'double_norm': True, 'cin1_kernel': False, 'dual_apply': True, 'lifted_kernel': True}
 
 
 def _gn_fusable_fused(cout, groups):
@@ -179,8 +179,14 @@ class KPConvInterSO3(nn.Module):
     def forward_stats(self, q_pts, s_pts, neighb_inds, x, groups, seg):
         """forward() plus the per-pair GroupNorm statistics of its output (accumulated in the GEMM epilogue)."""
         self._check_tables()
-        if _GFLAGS['cin1_kernel'] and neighb_inds.shape[0] > 0 and s_pts.shape[0] > 0 and \
-                K.kpconv_cin1_supported(self.in_channels, self.out_channels, neighb_inds.shape[1]):
+        cin1_ok = neighb_inds.shape[0] > 0 and s_pts.shape[0] > 0 and K.kpconv_cin1_supported(
+            self.in_channels, self.out_channels, neighb_inds.shape[1])
+        if cin1_ok and _GFLAGS['lifted_kernel'] and x.dim() == 3 and x.stride(1) == 0:
+            # LiftBlockEPN output (an expand over the anchor axis): anchor-constant input, 16 products per point
+            w36 = self.weights.detach().reshape(36, self.out_channels).float().contiguous()
+            return K.kpconv_cin1(q_pts, s_pts, neighb_inds.contiguous(), _act(x[:, 0, 0]).contiguous(), w36,
+                                 self.kernel_points, self.KP_extent, gn=(groups, seg), lifted=True)
+        if _GFLAGS['cin1_kernel'] and cin1_ok:
             w36 = self.weights.detach().reshape(36, self.out_channels).float().contiguous()
             return K.kpconv_cin1(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), w36, self.kernel_points,
                                  self.KP_extent, gn=(groups, seg))
@@ -502,7 +508,7 @@ class E2PN(nn.Module):
         sub, up = data_dict['subsampling'], data_dict['upsampling']
         segs = data_dict.get('pair_offsets', [None] * len(pts))
         widths = data_dict.get('subsampling_width', [None] * len(pts))
-        x = self.preprocess(_act(feats)).contiguous()
+        x = self.preprocess(_act(feats))  # stays an expand: the first conv recognises the lifted (anchor-constant) input
         x = self.encoder1_1(x, pts[0], pts[0], nb[0], seg=segs[0])
         x = self.encoder1_2(x, pts[0], pts[0], nb[0], seg=segs[0])
         inv = {}

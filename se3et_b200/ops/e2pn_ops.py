@@ -178,11 +178,12 @@ def kpconv_cin1_supported(cin, cout, h):
     return cin == 1 and cout in (32, 64) and h <= 40
 
 
-def kpconv_cin1(q_pts, s_pts, neighbors, x_bf16, w36, kernel_points, kp_extent, gn=None):
-    """First-layer KPConvInterSO3 (one input channel per anchor). x (Ns, 6, 1) bf16, w36 fp32 (36, Cout).
-    -> (fp32 (Nq*6, Cout), stats or None)."""
+def kpconv_cin1(q_pts, s_pts, neighbors, x_bf16, w36, kernel_points, kp_extent, gn=None, lifted=False):
+    """First-layer KPConvInterSO3 (one input channel per anchor). x (Ns, 6, 1) bf16 -- or (Ns,) with lifted=True: the
+    LiftBlockEPN output, identical for the six anchors -- w36 fp32 (36, Cout).  -> (fp32 (Nq*6, Cout), stats or None)."""
     _lib.require_cuda(q_pts, s_pts, neighbors, x_bf16, w36, kernel_points)
-    assert x_bf16.dtype == torch.bfloat16 and x_bf16.is_contiguous() and x_bf16.shape[1:] == (6, 1)
+    assert x_bf16.dtype == torch.bfloat16 and x_bf16.is_contiguous()
+    assert (x_bf16.dim() == 1) if lifted else (x_bf16.shape[1:] == (6, 1))
     assert w36.dtype == torch.float32 and w36.is_contiguous() and w36.shape[0] == 36
     assert neighbors.dtype == torch.int64 and neighbors.is_contiguous()
     nq, h = neighbors.shape
@@ -196,5 +197,6 @@ def kpconv_cin1(q_pts, s_pts, neighbors, x_bf16, w36, kernel_points, kp_extent, 
     _lib.check(_lib.lib().se3et_kpconv_cin1(
         _lib.ptr(q_pts), _lib.ptr(s_pts), _lib.ptr(neighbors), _lib.i64(nq), _lib.i64(ns), _lib.i64(h),
         _lib.ptr(x_bf16), _lib.ptr(w36), _lib.i64(cout), _lib.ptr(kernel_points), _lib.f32(kp_extent), _lib.ptr(out),
-        _lib.ptr(stats), _lib.ptr(seg_off), _lib.i64(nseg), _lib.i64(groups), _lib.stream_ptr()), "kpconv_cin1")
+        _lib.ptr(stats), _lib.ptr(seg_off), _lib.i64(nseg), _lib.i64(groups), ctypes.c_int(1 if lifted else 0),
+        _lib.stream_ptr()), "kpconv_cin1")
     return out, stats

@@ -90,6 +90,35 @@ def test_kpconv_matches_oracle(pyramid, cin, cout):
         assert rel_err(got, want) < 5e-3
 
 
+@pytest.mark.parametrize("cout", [32, 64])
+def test_kpconv_lifted_input_matches_oracle(pyramid, cout):
+    """First backbone layer: the LiftBlockEPN output (an expand over the anchor axis) takes the anchor-constant kernel
+    (16 basis products per point, anchor-summed weights); same oracle, statistics included, two pairs."""
+    t = oe.octahedral_tables()
+    p0 = torch.from_numpy(pyramid["points"][0])
+    nb = torch.from_numpy(pyramid["neighbors"][0])
+    conv = M.KPConvInterSO3(15, 6, 1, cout, 0.05, 0.0625, non_sep_conv=True, rot_by_permute=True, quotient_factor=4)
+    with torch.no_grad():
+        conv.weights.copy_(helpers.seeded_tensor("conv.weights", (6, 6, 1, cout)))
+    f = helpers.seeded_tensor("conv.input", (p0.shape[0], 1)).bfloat16().float()
+    x = M.LiftBlockEPN('lift_epn', 1, type('C', (), {'kanchor': 6})())(f)
+    assert x.stride(1) == 0
+    want = oe.kpconv_inter_so3(p0, p0, nb, x.contiguous(), conv.weights.detach().float(), conv.kernel_points.detach(),
+                               0.05, t["kidx"], t["ridx"])
+    conv = conv.to(DEV)
+    nq = p0.shape[0]
+    seg = torch.tensor([0, nq // 3 + 5, nq], dtype=torch.int64, device=DEV)
+    xd = M.LiftBlockEPN('lift_epn', 1, type('C', (), {'kanchor': 6})())(f.to(DEV))
+    L = __import__('se3et_b200._lib', fromlist=['x']).lib()
+    L.enabled = True
+    L.reset()
+    y, st = conv.forward_stats(p0.to(DEV), p0.to(DEV), nb.to(DEV), xd, 16, seg)
+    assert L.counts.get("se3et_kpconv_cin1", 0) == 1, L.counts
+    L.enabled = False
+    assert rel_err(y.cpu().view_as(want), want) < 2e-3
+    assert torch.allclose(st, K.groupnorm_stats(y, 16, seg, 6), rtol=1e-5, atol=1e-3)
+
+
 @pytest.mark.parametrize("cin,cout,G", [(16, 16, 16), (32, 32, 32), (32, 64, 16), (64, 128, 32), (128, 256, 32),
                                         (48, 80, 5)])
 def test_fused_kpconv_equals_gather_plus_gemm(pyramid, cin, cout, G):
