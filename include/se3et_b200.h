@@ -342,6 +342,25 @@ int se3et_superpoint_matching(const float* ref_feats, const float* src_feats, in
                               int64_t* ref_idx, int64_t* src_idx, float* scores, int32_t* counts,
                               se3et_stream_t stream);
 
+/* point_to_node_partition -- geotransformer/modules/ops/pointcloud_partition.py:60-107 (called twice per pair from
+ * experiments/se3eti.3dmatch/model.py:109-114), batched over `batch` stacked clouds: cloud b owns point_lengths[b]
+ * consecutive rows of points [n_points, 3] and node_lengths[b] rows of nodes [n_nodes, 3] (both lengths on the device).
+ *   point_to_node    [n_points]           node (cloud-local index) nearest to each point; squared distance
+ *                                         (x2 - 2 x.y) + y2 clamped at 0 as pairwise_distance.py:27-30, fp32 in a fixed
+ *                                         operation order without FMA; ties -> lowest node index
+ *   node_masks       [n_nodes]            1 when the node received at least one point
+ *   node_sizes       [n_nodes] or NULL    number of points per node (return_count = True)
+ *   node_knn_indices [n_nodes, limit]     the node's nearest assigned points (cloud-local), ascending (distance, index),
+ *                                         padded with the cloud's point count
+ *   node_knn_masks   [n_nodes, limit]     1 for real entries
+ * workspace: se3et_point_to_node_partition_workspace_bytes(n_points, batch), 256-byte aligned. */
+int se3et_point_to_node_partition_workspace_bytes(int64_t n_points, int64_t batch, size_t* bytes);
+int se3et_point_to_node_partition(const float* points, const int64_t* point_lengths, int64_t n_points,
+                                  const float* nodes, const int64_t* node_lengths, int64_t n_nodes, int64_t batch,
+                                  int64_t point_limit, int64_t* point_to_node, uint8_t* node_masks, int64_t* node_sizes,
+                                  int64_t* node_knn_indices, uint8_t* node_knn_masks, void* workspace,
+                                  size_t workspace_bytes, se3et_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,7 @@ from . import _lib
 from .modules.e2pn import E2PN
 from .modules.transformer import GeometricTransformer, SuperPointMatching
 from .ops import transformer_ops as T
+from .ops.partition_ops import point_to_node_partition_stacked
 from .precompute import precompute_data_stack_mode
 
 
@@ -66,6 +67,7 @@ def make_cfg(variant='se3eti.3dmatch'):
                            # SE3ET-E's model.py does not pass attn_r_positive*: the module defaults apply
                            attn_r_positive='sq' if is_e else 'softplus',
                            attn_r_positive_rot_supervise='sigmoid' if is_e else 'minus')
+    c.model = Cfg(num_points_in_patch=128 if stages == 5 else 64)  # config.py:177 (3DMatch) / se3eti.kitti/config.py:180
     c.coarse_matching = Cfg(num_targets=128, overlap_threshold=0.1, num_correspondences=256, dual_normalization=True)
     c.neighbor_limits = list(limits)  # demo.py:52 for 3DMatch; KITTI limits are calibrated per dataset (data.py:212-252)
     return c
@@ -106,6 +108,20 @@ class GeoTransformer(nn.Module):
         out['ref_points_c'], out['src_points_c'] = points_c[:ref_length_c], points_c[ref_length_c:]
         out['ref_feats_c'], out['src_feats_c'] = ref_n, src_n
         out['ref_feats_f'], out['src_feats_f'] = feats_f[:ref_length_f], feats_f[ref_length_f:]
+        # point-to-node partition of the fine level (model.py:109-119 of the reference): node masks for the coarse
+        # matching, patch indices / masks for the fine stage
+        points_f = data_dict['points'][1]
+        lf = data_dict['lengths'][1].to(points_f.device)
+        lc = data_dict['lengths'][-1].to(points_f.device)
+        _, node_masks, knn, knn_masks = point_to_node_partition_stacked(points_f, lf, points_c, lc,
+                                                                         self.cfg.model.num_points_in_patch)
+        if ref_node_masks is None:
+            ref_node_masks = node_masks[:ref_length_c]
+        if src_node_masks is None:
+            src_node_masks = node_masks[ref_length_c:]
+        out['ref_node_masks'], out['src_node_masks'] = ref_node_masks, src_node_masks
+        out['ref_node_knn_indices'], out['src_node_knn_indices'] = knn[:ref_length_c], knn[ref_length_c:]
+        out['ref_node_knn_masks'], out['src_node_knn_masks'] = knn_masks[:ref_length_c], knn_masks[ref_length_c:]
         ri, si, sc = self.coarse_matching(ref_n, src_n, ref_node_masks, src_node_masks)
         out['ref_node_corr_indices'], out['src_node_corr_indices'], out['node_corr_scores'] = ri, si, sc
         return out
@@ -137,10 +153,16 @@ class GeoTransformer(nn.Module):
             points_c = points_c.index_select(0, order_t)
             feats_c = feats_c.index_select(0, order_t)
         tr = int(ref_sizes.sum())
+        # point-to-node partition of every cloud (fine level = stage 2, nodes = last stage), backbone order
+        _, node_masks, knn, knn_masks = point_to_node_partition_stacked(
+            dd['points'][1], dd['lengths'][1], dd['points'][-1], dd['lengths'][-1], cfg.model.num_points_in_patch)
+        masks_t = node_masks if num_pairs == 1 else node_masks.index_select(0, order_t)
         both = self.transformer.forward_clouds(points_c, feats_c, ref_sizes.tolist(), src_sizes.tolist())
         normed = T.l2_normalize_rows(both)
-        ri, si, sc, cnt = self.coarse_matching.forward_pairs(normed[:tr], normed[tr:], ref_sizes, src_sizes)
+        ri, si, sc, cnt = self.coarse_matching.forward_pairs(normed[:tr], normed[tr:], ref_sizes, src_sizes,
+                                                             masks_t[:tr].to(torch.uint8), masks_t[tr:].to(torch.uint8))
         return {
+            'node_masks': node_masks, 'node_knn_indices': knn, 'node_knn_masks': knn_masks,
             'ref_node_corr_indices': ri, 'src_node_corr_indices': si, 'node_corr_scores': sc, 'num_corr': cnt,
             'ref_feats_c': normed[:tr], 'src_feats_c': normed[tr:], 'ref_sizes': ref_sizes, 'src_sizes': src_sizes,
             'feats_f': feats_f, 'points_c': points_c, 'data_dict': dd,
