@@ -135,6 +135,8 @@ int se3et_gemm_bf16_gnapply(const void* a, int64_t lda, const void* b, int64_t l
 /* Measurement switch: 0 routes se3et_gemm_bf16_gnapply(_dual) to the one-tile-per-CTA kernels instead of the streaming
  * kernel (persistent CTAs, eight epilogue warps; the default whenever n % 64 == 0). */
 int se3et_gemm_set_stream_apply(int on);
+/* Measurement switch: 0 routes narrow grouped GEMMs back to the strip (two CTAs per SM) variant. */
+int se3et_gemm_set_grouped_small_cta(int on);
 
 /* GroupNorm statistics of y = A W^T + bias WITHOUT forming y (UnaryBlockEPN, blocks_epn.py:639-665, when the Linear
  * widens): one pass over A accumulates per pair the Gram matrix A^T A and the column sums (mma.sync, fp32 per CTA, fp64

@@ -438,11 +438,15 @@ static int launch_gemm_variant(const CUtensorMap& ta, const CUtensorMap& tb, Gem
   return SE3ET_OK;
 }
 
+static bool g_grouped_small_cta = true;
+
 template <int BN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& shape, const GemmEpilogue& ep,
                        int batch, cudaStream_t st) {
   const int num_kb = (shape.K + kGemmBK - 1) / kGemmBK;
-  if (num_kb <= 2 && !shape.groups)  // short K: three (BN <= 128) or two single-tile CTAs per SM
+  // short K: three (BN <= 128) or two single-tile CTAs per SM.  Grouped problems with narrow outputs (the positional
+  // score term: one small problem per query point, N = 32) are bound by CTAs in flight, not by the ring depth: same variant
+  if ((num_kb <= 2 && !shape.groups) || (shape.groups && BN <= 64 && g_grouped_small_cta))
     return launch_gemm_variant<BN, false>(ta, tb, shape, ep, batch, (BN <= 128 ? 75 : 113) * 1024, st);
   return launch_gemm_variant<BN, true>(ta, tb, shape, ep, batch, (BN <= 128 ? 113 : 227) * 1024, st);
 }
@@ -491,6 +495,11 @@ int gemm_bf16(const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b, int64
 }  // namespace se3et
 
 using namespace se3et;
+
+extern "C" int se3et_gemm_set_grouped_small_cta(int on) {
+  g_grouped_small_cta = on != 0;
+  return SE3ET_OK;
+}
 
 extern "C" int se3et_gemm_grouped_bf16(const void* a, int64_t lda, int64_t a_rows_total, const void* b, int64_t ldb,
                                        int64_t b_rows_total, const int64_t* groups, int64_t num_groups, int64_t max_m,
