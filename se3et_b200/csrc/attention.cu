@@ -51,8 +51,8 @@ template <int D>
 __global__ void __launch_bounds__(kAttnWarps * 32) flash_attention_kernel(AttnTensors t,
                                                                            const AttnProblem* __restrict__ problems) {
   constexpr int kLd = D + 8;  // padded smem row (elements): conflict-free fragment reads, 16-byte aligned rows
-  __shared__ __align__(16) __nv_bfloat16 sk[kAttnBK * kLd];
-  __shared__ __align__(16) __nv_bfloat16 sv[kAttnBK * kLd];
+  __shared__ __align__(16) __nv_bfloat16 sk_buf[2][kAttnBK * kLd];  // double-buffered: tile i + 1 lands under tile i's math
+  __shared__ __align__(16) __nv_bfloat16 sv_buf[2][kAttnBK * kLd];
   const AttnProblem pr = problems[blockIdx.z];
   const int q0 = blockIdx.x * kAttnBQ;
   if (q0 >= pr.n_q) return;
@@ -87,19 +87,34 @@ __global__ void __launch_bounds__(kAttnWarps * 32) flash_attention_kernel(AttnTe
   float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
   const float sc = t.scale * 1.4426950408889634f;  // scores are kept in log2 units
 
-  for (int k0 = 0; k0 < nkv; k0 += kAttnBK) {
-    __syncthreads();  // previous tile fully consumed
-    // ---- stage K and V tiles: 64 rows x D bf16, 16-byte chunks
+  // ---- K and V tiles: 64 rows x D bf16 as 16-byte cp.async chunks (keys past the end repeat the last one; masked below)
+  auto stage = [&](int k0, int buf) {
     constexpr int kChunks = D / 8;
     for (int c = threadIdx.x; c < kAttnBK * kChunks; c += kAttnWarps * 32) {
       const int row = c / kChunks, ch = c - row * kChunks;
       const int key = min(k0 + row, nkv - 1);
-      const uint4 kk = *reinterpret_cast<const uint4*>(t.k + (pr.kv_start + key) * t.k_pt + a * t.k_an + h * D + ch * 8);
-      const uint4 vv = *reinterpret_cast<const uint4*>(t.v + (pr.kv_start + key) * t.v_pt + a * t.v_an + h * D + ch * 8);
-      *reinterpret_cast<uint4*>(sk + row * kLd + ch * 8) = kk;
-      *reinterpret_cast<uint4*>(sv + row * kLd + ch * 8) = vv;
+      const uint32_t dk = (uint32_t)__cvta_generic_to_shared(sk_buf[buf] + row * kLd + ch * 8);
+      const uint32_t dv = (uint32_t)__cvta_generic_to_shared(sv_buf[buf] + row * kLd + ch * 8);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dk),
+                   "l"(t.k + (pr.kv_start + key) * t.k_pt + a * t.k_an + h * D + ch * 8) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dv),
+                   "l"(t.v + (pr.kv_start + key) * t.v_pt + a * t.v_an + h * D + ch * 8) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (nkv > 0) stage(0, 0);
+  int buf = 0;
+  for (int k0 = 0; k0 < nkv; k0 += kAttnBK, buf ^= 1) {
+    __syncthreads();  // the other buffer's tile is fully consumed
+    if (k0 + kAttnBK < nkv) {
+      stage(k0 + kAttnBK, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    const __nv_bfloat16* sk = sk_buf[buf];
+    const __nv_bfloat16* sv = sv_buf[buf];
 
     // ---- S = Q K^T  (16 x 64 per warp)
     float s[kAttnBK / 8][4];
