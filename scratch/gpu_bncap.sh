@@ -1,0 +1,22 @@
+#!/bin/bash
+for mode in 256 128 64; do
+python - $mode <<'PY'
+import sys, json, subprocess
+mode = int(sys.argv[1])
+code = """
+import sys
+sys.argv = ['bench.py', '--steps', '5', '--warmup', '3', '--no-cpu-baseline']
+from se3et_b200 import _lib
+_lib.lib().se3et_gemm_set_plain_tile_cap(%d)
+import runpy
+runpy.run_path('bench.py', run_name='__main__')
+""" % mode
+out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
+try:
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    pe = d['roofline']['per_entry_point_ms']
+    print('cap', mode, 'value %.1f e2e %.1f' % (d['value'], d['e2e']['value']), 'gemm', pe['se3et_gemm_bf16'], 'gnstats', pe['se3et_gemm_bf16_gnstats'])
+except Exception as e:
+    print(mode, 'failed', e, out.stdout[-500:], out.stderr[-1500:])
+PY
+done

@@ -439,6 +439,9 @@ static int launch_gemm_variant(const CUtensorMap& ta, const CUtensorMap& tb, Gem
 }
 
 static bool g_grouped_small_cta = true;
+// widest output tile of the plain / statistics GEMMs: 128 columns keep two CTAs (eight epilogue warps) per SM with
+// double-buffered accumulators; 256-wide tiles are epilogue-bound at the K of this path (566 vs 553 pairs/s)
+static int g_plain_bn_cap = 128;
 
 template <int BN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& shape, const GemmEpilogue& ep,
@@ -466,6 +469,7 @@ int gemm_bf16(const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b, int64
   int bn = pick_bn(N);
   if (!bn) return SE3ET_ERR_UNSUPPORTED;
   if (ep.norm_stats && bn > 128) bn = 128;  // apply mode stages its output tile: 3 CTAs per SM
+  if (bn > g_plain_bn_cap && !groups) bn = g_plain_bn_cap;
   if (ep.transposed && (!ep.out_f32 || ep.out_bf16)) return SE3ET_ERR_ARG;
   if (!ep.transposed && ep.out_f32 &&
       ((reinterpret_cast<uintptr_t>(ep.out_f32) & 15) || (ep.ldc % 4) || (ep.c_batch_stride % 4) || groups))
@@ -495,6 +499,12 @@ int gemm_bf16(const __nv_bfloat16* a, int64_t lda, const __nv_bfloat16* b, int64
 }  // namespace se3et
 
 using namespace se3et;
+
+extern "C" int se3et_gemm_set_plain_tile_cap(int bn) {
+  if (bn != 64 && bn != 128 && bn != 256) return SE3ET_ERR_ARG;
+  g_plain_bn_cap = bn;
+  return SE3ET_OK;
+}
 
 extern "C" int se3et_gemm_set_grouped_small_cta(int on) {
   g_grouped_small_cta = on != 0;
