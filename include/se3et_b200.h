@@ -139,6 +139,8 @@ int se3et_gemm_set_stream_apply(int on);
 int se3et_gemm_set_grouped_small_cta(int on);
 /* Measurement switch: widest output tile (64, 128 or 256 columns) of se3et_gemm_bf16 / se3et_gemm_bf16_gnstats. */
 int se3et_gemm_set_plain_tile_cap(int bn);
+/* Measurement switch: 0 keeps large bf16-output Linears of se3et_gemm_bf16 on the tile kernels (default: streaming kernel). */
+int se3et_gemm_set_stream_plain(int on);
 
 /* GroupNorm statistics of y = A W^T + bias WITHOUT forming y (UnaryBlockEPN, blocks_epn.py:639-665, when the Linear
  * widens): one pass over A accumulates per pair the Gram matrix A^T A and the column sums (mma.sync, fp32 per CTA, fp64

@@ -551,6 +551,11 @@ extern "C" int se3et_gemm_bf16(const void* a, int64_t lda, const void* b, int64_
   ep.transposed = 0;
   ep.n_valid = (int)n;
   if (batch > 65535) return SE3ET_ERR_UNSUPPORTED;
+  // large bf16-only Linears (q/k/v, FFN expand, in_proj): streaming kernel, eight epilogue warps per CTA
+  if (gemm_stream_plain_enabled() && batch == 1 && !out_f32 && out_bf16 && m >= 4096 && n % 64 == 0 && k % 8 == 0 &&
+      ldc % 8 == 0 && !(reinterpret_cast<uintptr_t>(out_bf16) & 15) && (act == 0 || act == 1) && m > 0)
+    return gemm_stream_plain(a, lda, b, ldb, m, n, k, bias, alpha, act == 1 ? 0.f : 1.f, out_bf16, ldc,
+                             static_cast<cudaStream_t>(stream));
   return gemm_bf16(static_cast<const __nv_bfloat16*>(a), lda, static_cast<const __nv_bfloat16*>(b), ldb, (int)m, (int)n,
                    (int)k, (int)batch, a_batch_rows, b_batch_rows, nullptr, 0, 0, ep, static_cast<cudaStream_t>(stream));
 }

@@ -40,8 +40,10 @@ struct StreamArgs {
   int64_t ldc;
   const int64_t* seg_off;
   int nseg, cpg, groups, rpp;
-  const float4* tab;    // [nseg][N] {scale1, scale2, shift, -} from gn_table_kernel
+  const float4* tab;    // [nseg][N] {scale1, scale2, shift, -} from gn_table_kernel; NULL = plain Linear (below)
   float slope;
+  const float* plain_bias;  // plain mode: out = act(alpha * acc + bias), act = LeakyReLU_slope (slope 0 = ReLU, 1 = none)
+  float plain_alpha;
 };
 
 __device__ __forceinline__ float2 stream_affine(const StreamNorm& n, int seg, int c, int groups, int cpg, double cnt,
@@ -194,7 +196,10 @@ gemm_stream_gnapply_kernel(const __grid_constant__ CUtensorMap tma_a1, const __g
       const float4* row_tab = args.tab;
       if (warp_ok) {
         const int64_t wlast = min(wfirst + 31, (int64_t)args.M - 1);
-        if (!(wfirst >= seg_lo && wlast < seg_hi)) {
+        if (!args.tab) {  // plain Linear: one segment, the table row is {alpha, 0, bias}
+          seg_lo = 0;
+          seg_hi = args.M;
+        } else if (!(wfirst >= seg_lo && wlast < seg_hi)) {
           seg_cached = segment_of(args.seg_off, args.nseg, wfirst / args.rpp);
           seg_lo = args.seg_off[seg_cached] * args.rpp;
           seg_hi = args.seg_off[seg_cached + 1] * args.rpp;
@@ -202,7 +207,9 @@ gemm_stream_gnapply_kernel(const __grid_constant__ CUtensorMap tma_a1, const __g
         uniform = wlast < seg_hi;
         if (uniform) {
           // this warp's 32 columns of the pair's table: one coalesced 512-byte load, broadcast from shared memory
-          const float4 te = __ldg(args.tab + (int64_t)seg_cached * args.N + n0 + lane);
+          const float4 te = args.tab ? __ldg(args.tab + (int64_t)seg_cached * args.N + n0 + lane)
+                                     : make_float4(args.plain_alpha, 0.f,
+                                                   args.plain_bias ? __ldg(args.plain_bias + n0 + lane) : 0.f, 0.f);
           __syncwarp();
           table[lane] = te;
           __syncwarp();
@@ -300,6 +307,7 @@ gemm_stream_gnapply_kernel(const __grid_constant__ CUtensorMap tma_a1, const __g
 }
 
 static bool g_stream_enabled = true;
+static bool g_stream_plain = true;
 
 bool gemm_stream_supported(int64_t n, int64_t k1, int64_t k2, int64_t ldc) {
   return g_stream_enabled && n % kSBN == 0 && k1 % 8 == 0 && k2 % 8 == 0 && ldc % 8 == 0;
@@ -341,6 +349,8 @@ int gemm_stream_gnapply(const void* a1, int64_t lda1, const void* b1, int64_t ld
   args.nseg = (int)nseg; args.cpg = (int)(n / groups); args.groups = (int)groups; args.rpp = (int)rpp;
   args.tab = static_cast<const float4*>(workspace);
   args.slope = slope;
+  args.plain_bias = nullptr;
+  args.plain_alpha = 1.f;
   gn_table_kernel<<<dim3((unsigned)ceil_div(n, 256), (unsigned)nseg), 256, 0, st>>>(
       n1, n2, dual ? 1 : 0, seg_off, (int)rpp, (int)n, (int)groups, eps, static_cast<float4*>(workspace));
   SE3ET_LAUNCH_CHECK();
@@ -362,7 +372,49 @@ int gemm_stream_gnapply(const void* a1, int64_t lda1, const void* b1, int64_t ld
   return SE3ET_OK;
 }
 
+// out_bf16 = act(alpha * A B^T + bias) through the streaming kernel (act: slope 0 = ReLU, 1 = none)
+int gemm_stream_plain(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int64_t n, int64_t k,
+                      const float* bias, float alpha, float slope, void* out, int64_t ldc, cudaStream_t st) {
+  if ((int64_t)ceil_div(m, kSBM) * (n / kSBN) > INT32_MAX) return SE3ET_ERR_UNSUPPORTED;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16_2d(&ta, a, m, k, lda, kSBM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tb, b, n, k, ldb, kSBN);
+  if (rc) return rc;
+  StreamArgs args;
+  args.M = (int)m; args.N = (int)n; args.K1 = (int)k; args.K2 = 0;
+  args.m_tiles = (int)ceil_div(m, kSBM);
+  args.n_tiles = (int)(n / kSBN);
+  args.out = static_cast<__nv_bfloat16*>(out);
+  args.resid = nullptr;
+  args.ldc = ldc;
+  args.seg_off = nullptr;
+  args.nseg = 1; args.cpg = 1; args.groups = 1; args.rpp = 1;
+  args.tab = nullptr;
+  args.slope = slope;
+  args.plain_bias = bias;
+  args.plain_alpha = alpha;
+  static bool configured = false;
+  if (!configured) {
+    SE3ET_CUDA_CHECK(cudaFuncSetAttribute(gemm_stream_gnapply_kernel<false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmem));
+    configured = true;
+  }
+  const int64_t work = (int64_t)args.m_tiles * args.n_tiles;
+  const unsigned grid = (unsigned)(work < 2 * kNumSMs ? work : 2 * kNumSMs);
+  gemm_stream_gnapply_kernel<false><<<grid, kSThreads, kSSmem, st>>>(ta, tb, ta, tb, args);
+  SE3ET_LAUNCH_CHECK();
+  return SE3ET_OK;
+}
+
+bool gemm_stream_plain_enabled() { return g_stream_plain; }
+
 }  // namespace se3et
+
+extern "C" int se3et_gemm_set_stream_plain(int on) {
+  se3et::g_stream_plain = on != 0;
+  return SE3ET_OK;
+}
 
 // A/B switch for measurements: 0 routes se3et_gemm_bf16_gnapply(_dual) back to the one-tile-per-CTA kernels
 extern "C" int se3et_gemm_set_stream_apply(int on) {

@@ -23,4 +23,9 @@ int gemm_stream_gnapply(const void* a1, int64_t lda1, const void* b1, int64_t ld
                         size_t workspace_bytes, cudaStream_t st);
 size_t gemm_stream_workspace_bytes(int64_t n, int64_t nseg);
 
+// out_bf16 = act(alpha * A B^T + bias): plain Linear with a bf16 output on the streaming kernel (slope 0 = ReLU, 1 = none)
+int gemm_stream_plain(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t m, int64_t n, int64_t k,
+                      const float* bias, float alpha, float slope, void* out, int64_t ldc, cudaStream_t st);
+bool gemm_stream_plain_enabled();
+
 }  // namespace se3et

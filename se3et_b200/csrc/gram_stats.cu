@@ -200,13 +200,13 @@ __global__ void __launch_bounds__(128) gram_finalize_kernel(const double* __rest
   const double rows = (double)(seg_off[seg + 1] - seg_off[seg]) * rpp;
   double sum = 0.0, sq = 0.0;
   // eight channels at a time: one pass over column k1 of G (symmetric: G[k2][k1], coalesced over k1) serves all of them
-  __shared__ float wsh[8][128];
+  __shared__ double wsh[8][128];  // fp64 once: the inner loop is bound by the fp64 pipe, conversions would double it
   for (int j0 = 0; j0 < cpg; j0 += 8) {
     const int nj = min(8, cpg - j0);
     __syncthreads();
     for (int i = threadIdx.x; i < 8 * K; i += blockDim.x) {
       const int jj = i / K, k = i - jj * K;
-      wsh[jj][k] = jj < nj ? __bfloat162float(w[(int64_t)(g * cpg + j0 + jj) * ldw + k]) : 0.f;
+      wsh[jj][k] = jj < nj ? (double)__bfloat162float(w[(int64_t)(g * cpg + j0 + jj) * ldw + k]) : 0.0;
     }
     __syncthreads();
     for (int k1 = threadIdx.x; k1 < K; k1 += blockDim.x) {
@@ -214,13 +214,13 @@ __global__ void __launch_bounds__(128) gram_finalize_kernel(const double* __rest
       for (int k2 = 0; k2 < K; ++k2) {
         const double gv = G[(int64_t)k2 * K + k1];
 #pragma unroll
-        for (int jj = 0; jj < 8; ++jj) t[jj] += gv * (double)wsh[jj][k2];
+        for (int jj = 0; jj < 8; ++jj) t[jj] += gv * wsh[jj][k2];
       }
       const double s1 = s[k1];
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
         const double bj = (bias && jj < nj) ? (double)bias[g * cpg + j0 + jj] : 0.0;
-        const double w1 = (double)wsh[jj][k1];
+        const double w1 = wsh[jj][k1];
         sq += w1 * t[jj] + 2.0 * bj * w1 * s1;
         sum += w1 * s1;
       }
