@@ -1,0 +1,10 @@
+#!/bin/bash
+# usage: gpurun_retry.sh <timeout> <command...>   retries while the pod answers "transient" (nothing charged)
+t=$1; shift
+for i in $(seq 1 12); do
+  out=$(/usr/local/graft/bin/gpurun --timeout $t -- "$@" 2>&1)
+  if echo "$out" | grep -q "status=transient"; then sleep 150; continue; fi
+  echo "$out" | tail -25
+  exit 0
+done
+echo "gave up: pod busy"

@@ -332,28 +332,41 @@ __global__ void __launch_bounds__(256) groupnorm_double_kernel(NormSide a, NormS
     load_norm_cols(a, seg, G, cpg, c0, cnt, eps, n1);
     if (kApply) load_norm_cols(b2, seg, G, cpg, c0, cnt, eps, n2);
     float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int64_t row = row0 + rsub; row < row1; row += rstep) {
-      const float4 ya = __ldcs(reinterpret_cast<const float4*>(a.y + row * C + c0));
-      float v[4] = {(ya.x - n1.mean[0]) * n1.s[0] + n1.beta[0], (ya.y - n1.mean[1]) * n1.s[1] + n1.beta[1],
-                    (ya.z - n1.mean[2]) * n1.s[2] + n1.beta[2], (ya.w - n1.mean[3]) * n1.s[3] + n1.beta[3]};
+    // four rows per thread and iteration: the loads are issued together (bytes in flight, this kernel is pure streaming)
+    constexpr int kU = 4;
+    for (int64_t rowb = row0 + rsub; rowb < row1; rowb += (int64_t)kU * rstep) {
+      float4 yv[kU];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = v[j] >= 0.f ? v[j] : v[j] * slope;
-      if (!kApply) {
+      for (int u = 0; u < kU; ++u) {
+        const int64_t row = rowb + (int64_t)u * rstep;
+        if (row < row1) yv[u] = __ldcs(reinterpret_cast<const float4*>(a.y + row * C + c0));
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          s[j] += v[j];
-          ss[j] = fmaf(v[j], v[j], ss[j]);
+      for (int u = 0; u < kU; ++u) {
+        const int64_t row = rowb + (int64_t)u * rstep;
+        if (row >= row1) continue;
+        const float4 ya = yv[u];
+        float v[4] = {(ya.x - n1.mean[0]) * n1.s[0] + n1.beta[0], (ya.y - n1.mean[1]) * n1.s[1] + n1.beta[1],
+                      (ya.z - n1.mean[2]) * n1.s[2] + n1.beta[2], (ya.w - n1.mean[3]) * n1.s[3] + n1.beta[3]};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = v[j] >= 0.f ? v[j] : v[j] * slope;
+        if (!kApply) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            s[j] += v[j];
+            ss[j] = fmaf(v[j], v[j], ss[j]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float w = (v[j] - n2.mean[j]) * n2.s[j] + n2.beta[j];
+            v[j] = w >= 0.f ? w : w * slope;
+          }
+          uint2 o;
+          o.x = pack_bf16(v[0], v[1]);
+          o.y = pack_bf16(v[2], v[3]);
+          *reinterpret_cast<uint2*>(out_bf16 + row * C + c0) = o;
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float w = (v[j] - n2.mean[j]) * n2.s[j] + n2.beta[j];
-          v[j] = w >= 0.f ? w : w * slope;
-        }
-        uint2 o;
-        o.x = pack_bf16(v[0], v[1]);
-        o.y = pack_bf16(v[2], v[3]);
-        *reinterpret_cast<uint2*>(out_bf16 + row * C + c0) = o;
       }
     }
     if (!kApply) {
