@@ -534,7 +534,25 @@ __global__ void __launch_bounds__(kQueryWarps * 32) radius_query_kernel(
   }
   if (!out || width <= 0) return;
   int64_t* row = out + qi * width;
-  if (nhit <= kHitCap) {
+  if (nhit <= 64) {
+    // the common case (neighbour limits are <= 40): rank every key against all others -- keys are unique, so the rank
+    // is its sorted position -- instead of a shared-memory bitonic network (21 synchronised passes for 64 keys)
+    __syncwarp();
+    unsigned long long mine[2];
+    int rank[2] = {0, 0};
+#pragma unroll
+    for (int u = 0; u < 2; ++u) mine[u] = lane + 32 * u < nhit ? keys[lane + 32 * u] : ~0ull;
+#pragma unroll 4
+    for (int f = 0; f < nhit; ++f) {
+      const unsigned long long kf = keys[f];
+      rank[0] += kf < mine[0] ? 1 : 0;
+      rank[1] += kf < mine[1] ? 1 : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (lane + 32 * u < nhit && rank[u] < width) row[rank[u]] = (int64_t)(mine[u] & 0xffffffffull);
+    for (int k = nhit + lane; k < width; k += 32) row[k] = ns_total;
+  } else if (nhit <= kHitCap) {
     int n2 = 32;
     while (n2 < nhit) n2 <<= 1;
     for (int i = nhit + lane; i < n2; i += 32) keys[i] = ~0ull;
