@@ -244,7 +244,9 @@ int se3et_groupnorm_apply(const float* ya, const double* stats_a, const float* g
 /* Two GroupNorm + LeakyReLU stages back to back without the intermediate tensor (KPConvInterSO3Block.norm followed
  * by the enclosing block's norm, blocks_epn.py:737-741 with 790-794 / 841-843):
  *   f = LeakyReLU(GN_1(y)), out = LeakyReLU(GN_2(f)).   apply = 0: accumulate the statistics of f into stats2
- * (zeroed by the call); apply = 1: recompute f and write out_bf16 using stats2.  channels / 4 a power of two <= 256. */
+ * (zeroed by the call); apply = 1: recompute f and write out_bf16 using stats2; apply = 2: accumulate the statistics of
+ * y itself into stats2 (stats1 / gamma / beta unused) -- the first norm's statistics as a streaming pass.
+ * channels / 4 a power of two <= 256. */
 int se3et_groupnorm_double(const float* y, const double* stats1, const float* gamma1, const float* beta1,
                            double* stats2, const float* gamma2, const float* beta2, int64_t rows, int64_t channels,
                            int64_t groups, const int64_t* seg_offsets, int64_t nseg, int64_t rows_per_point, float eps,

@@ -303,9 +303,11 @@ __global__ void __launch_bounds__(256) groupnorm_apply_rows_kernel(NormSide a, N
 // Two GroupNorm + LeakyReLU stages back to back (KPConvInterSO3Block's norm followed by the enclosing block's
 // norm, blocks_epn.py:737-741 + 790-794 / 841-843) without materialising the intermediate:
 //   f = LeakyReLU(GN_1(y)),  out = LeakyReLU(GN_2(f))
-// pass A (kApply = false): accumulates the statistics of f per (pair, group) into stats2 (fp64 atomics)
-// pass B (kApply = true) : recomputes f and writes out (bf16)
-template <bool kApply>
+// kMode 0 (pass A): accumulates the statistics of f per (pair, group) into stats2 (fp64 atomics)
+// kMode 1 (pass B): recomputes f and writes out (bf16)
+// kMode 2         : statistics of y itself into stats2 (the first norm's statistics, for producers whose epilogue
+//                   does not deliver them: cheaper here, as a streaming pass, than on the fused KPConv's critical path)
+template <int kMode>
 __global__ void __launch_bounds__(256) groupnorm_double_kernel(NormSide a, NormSide b2, double* __restrict__ stats2_acc,
                                                                 int64_t rows, int C, int cpg,
                                                                 const int64_t* __restrict__ seg_off, int nseg,
@@ -328,8 +330,9 @@ __global__ void __launch_bounds__(256) groupnorm_double_kernel(NormSide a, NormS
     int64_t seg_end = seg == nseg - 1 ? rows : seg_off[seg + 1] * rows_per_point;
     const int64_t row1 = min(r1, seg_end);
     const double cnt = (double)(seg_off[seg + 1] - seg_off[seg]) * rows_per_point * cpg;
+    constexpr bool kApply = kMode == 1;
     NormCols n1, n2;
-    load_norm_cols(a, seg, G, cpg, c0, cnt, eps, n1);
+    if (kMode != 2) load_norm_cols(a, seg, G, cpg, c0, cnt, eps, n1);
     if (kApply) load_norm_cols(b2, seg, G, cpg, c0, cnt, eps, n2);
     float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
     // four rows per thread and iteration: the loads are issued together (bytes in flight, this kernel is pure streaming)
@@ -346,10 +349,15 @@ __global__ void __launch_bounds__(256) groupnorm_double_kernel(NormSide a, NormS
         const int64_t row = rowb + (int64_t)u * rstep;
         if (row >= row1) continue;
         const float4 ya = yv[u];
-        float v[4] = {(ya.x - n1.mean[0]) * n1.s[0] + n1.beta[0], (ya.y - n1.mean[1]) * n1.s[1] + n1.beta[1],
-                      (ya.z - n1.mean[2]) * n1.s[2] + n1.beta[2], (ya.w - n1.mean[3]) * n1.s[3] + n1.beta[3]};
+        float v[4] = {ya.x, ya.y, ya.z, ya.w};
+        if (kMode != 2) {
+          v[0] = (ya.x - n1.mean[0]) * n1.s[0] + n1.beta[0];
+          v[1] = (ya.y - n1.mean[1]) * n1.s[1] + n1.beta[1];
+          v[2] = (ya.z - n1.mean[2]) * n1.s[2] + n1.beta[2];
+          v[3] = (ya.w - n1.mean[3]) * n1.s[3] + n1.beta[3];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = v[j] >= 0.f ? v[j] : v[j] * slope;
+          for (int j = 0; j < 4; ++j) v[j] = v[j] >= 0.f ? v[j] : v[j] * slope;
+        }
         if (!kApply) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -369,7 +377,7 @@ __global__ void __launch_bounds__(256) groupnorm_double_kernel(NormSide a, NormS
         }
       }
     }
-    if (!kApply) {
+    if (kMode != 1) {
       for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh_acc[i] = 0.f;
       __syncthreads();
       if (cpg >= 4) {  // the four columns share one group
@@ -700,21 +708,26 @@ extern "C" int se3et_groupnorm_double(const float* y, const double* stats1, cons
   const int64_t vecs = channels / 4;
   if (vecs > 256 || (vecs & (vecs - 1)) != 0 || groups > 256) return SE3ET_ERR_UNSUPPORTED;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!apply) SE3ET_CUDA_CHECK(cudaMemsetAsync(stats2, 0, sizeof(double) * 2 * nseg * groups, st));
+  if (apply != 1) SE3ET_CUDA_CHECK(cudaMemsetAsync(stats2, 0, sizeof(double) * 2 * nseg * groups, st));
   if (rows == 0) return SE3ET_OK;
-  if (!y || !stats1 || !gamma1 || !beta1 || (apply && (!gamma2 || !beta2 || !out_bf16))) return SE3ET_ERR_ARG;
+  if (apply < 0 || apply > 2) return SE3ET_ERR_ARG;
+  if (!y || (apply != 2 && (!stats1 || !gamma1 || !beta1)) || (apply == 1 && (!gamma2 || !beta2 || !out_bf16)))
+    return SE3ET_ERR_ARG;
   int64_t blocks = ceil_div(rows * vecs, 256);
   const int64_t cap = (int64_t)kNumSMs * 8;
   if (blocks > cap) blocks = cap;
   NormSide a{y, stats1, gamma1, beta1};
   NormSide b{nullptr, stats2, gamma2, beta2};
   const int cpg = (int)(channels / groups);
-  if (apply)
-    groupnorm_double_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(
+  if (apply == 1)
+    groupnorm_double_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(
         a, b, stats2, rows, (int)channels, cpg, seg_offsets, (int)nseg, (int)rows_per_point, eps, leaky_slope,
         static_cast<__nv_bfloat16*>(out_bf16));
+  else if (apply == 0)
+    groupnorm_double_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(
+        a, b, stats2, rows, (int)channels, cpg, seg_offsets, (int)nseg, (int)rows_per_point, eps, leaky_slope, nullptr);
   else
-    groupnorm_double_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(
+    groupnorm_double_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(
         a, b, stats2, rows, (int)channels, cpg, seg_offsets, (int)nseg, (int)rows_per_point, eps, leaky_slope, nullptr);
   SE3ET_LAUNCH_CHECK();
   return SE3ET_OK;

@@ -25,7 +25,7 @@ from . import octahedral
 # switches for A/B measurements and tests (the defaults are the product path)
 # 'cin1_kernel': the CUDA-core first-layer kernel (csrc/kpconv.cu) measures slower than gather + GEMM on B200
 # (9.6 vs 8.4 ms per 64 pairs), so it is off by default and only exercised by the tests
-_GFLAGS = {'fused_kpconv': True, 'two_pass_unary': True, 'double_norm': True, 'cin1_kernel': False, 'dual_apply': True, 'lifted_kernel': True}
+_GFLAGS = {'fused_kpconv': True, 'two_pass_unary': True, 'double_norm': True, 'cin1_kernel': False, 'dual_apply': True, 'lifted_kernel': True, 'conv_stats_stream': True}
 
 
 def _gn_fusable_fused(cout, groups):
@@ -191,6 +191,12 @@ class KPConvInterSO3(nn.Module):
             return K.kpconv_cin1(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), w36, self.kernel_points,
                                  self.KP_extent, gn=(groups, seg))
         if self._fused_ok(neighb_inds) and _gn_fusable_fused(self.out_channels, groups):
+            if _GFLAGS['conv_stats_stream'] and K.groupnorm_double_supported(self.out_channels):
+                # the statistics as a streaming pass over the (small) conv output: in the fused kernel's epilogue they
+                # sit on the producers' critical path (4-10 % of that kernel), here they cost one read of y
+                y, _ = K.kpconv_fused(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), self._w_fused(),
+                                      self.kernel_points, self.KP_extent)
+                return y, K.groupnorm_stats_stream(y, groups, seg, self.kanchor)
             return K.kpconv_fused(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), self._w_fused(),
                                   self.kernel_points, self.KP_extent, gn=(groups, seg))
         a = K.kpconv_gather(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), self.kernel_points,

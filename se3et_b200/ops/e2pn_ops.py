@@ -174,6 +174,19 @@ def groupnorm_double(y, stats1, gamma1, beta1, gamma2, beta2, groups, seg_off, r
     return out
 
 
+def groupnorm_stats_stream(y, groups, seg_off, rows_per_point):
+    """Per-pair GroupNorm statistics (double (nseg, groups, 2)) of fp32 y (rows, C) by the streaming kernel
+    (se3et_groupnorm_double, apply = 2).  Requires groupnorm_double_supported(C)."""
+    rows, c = y.shape
+    nseg = seg_off.numel() - 1
+    stats = torch.empty((nseg, groups, 2), dtype=torch.float64, device=y.device)
+    _lib.check(_lib.lib().se3et_groupnorm_double(
+        _lib.ptr(y), _lib.ptr(None), _lib.ptr(None), _lib.ptr(None), _lib.ptr(stats), _lib.ptr(None), _lib.ptr(None),
+        _lib.i64(rows), _lib.i64(c), _lib.i64(groups), _lib.ptr(seg_off), _lib.i64(nseg), _lib.i64(rows_per_point),
+        _lib.f32(1e-5), _lib.f32(1.0), 2, _lib.ptr(None), _lib.stream_ptr()), "groupnorm_double(stats)")
+    return stats
+
+
 def kpconv_cin1_supported(cin, cout, h):
     return cin == 1 and cout in (32, 64) and h <= 40
 
