@@ -154,7 +154,7 @@ def algorithmic_work(cfg, n_levels, n_ref_c, n_src_c, limits):
             ub["apply"] += 6.0 * ns * (cin + mid) * 2
         conv_flops += 2.0 * nq * 6 * 36 * mid * mid              # class-pre-summed contraction (issued on tcgen05)
         hmma_flops += 2.0 * nq * 6 * mid * 16 * 48               # 16-row basis x 48 padded neighbours (mma.sync)
-        norm_bytes += nq * 6 * mid * (4 + 4 + 2)  # double GroupNorm: statistics pass + apply pass over fp32, bf16 out
+        norm_bytes += nq * 6 * mid * (4 + 4 + 4 + 2)  # double GroupNorm: two statistics passes + apply over fp32, bf16 out
         rows = 6.0 * nq
         stats_pass(rows, mid, cout)
         if cin != cout:
