@@ -1,5 +1,6 @@
-"""One tiny end-to-end invocation of the hot path for __graft_entry__.smoke(): SE3ET-I2 on a small synthetic pair,
-pyramid + backbone + transformer + SuperPointMatching on the GPU, checked against the torch-CPU oracle."""
+"""TEST INFRASTRUCTURE (called by __graft_entry__.smoke() only): one tiny end-to-end invocation of the hot path,
+SE3ET-I2 on a small synthetic pair -- pyramid + backbone + transformer + SuperPointMatching on the GPU -- checked against the
+torch-CPU oracle.  Lives under oracle/ because it imports the oracle; nothing in se3et_b200/ does."""
 import numpy as np
 import torch
 
@@ -8,8 +9,8 @@ def run(dev):
     from oracle import e2pn as oe
     from oracle import points as op
     from oracle import transformer as ot
-    from . import synthetic
-    from .model import create_model, make_cfg
+    from se3et_b200 import synthetic
+    from se3et_b200.model import create_model, make_cfg
 
     cfg = make_cfg("se3eti2.3dmatch")
     torch.manual_seed(0)

@@ -32,3 +32,19 @@ def test_no_cpu_fallback():
         ext.grid_subsampling(pts, torch.tensor([4]), pts, 0.1)
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         ext.radius_neighbors(pts, pts, torch.tensor([4]), torch.tensor([4]), 0.1)
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under se3et_b200/ may import or execute it (no CPU fallback)."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "se3et_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|importlib\.import_module\(['\"]oracle", re.M)
+    bad = []
+    for d, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(d, f)).read()
+                if pat.search(src):
+                    bad.append(os.path.join(d, f))
+    assert not bad, bad
