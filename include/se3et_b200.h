@@ -369,6 +369,15 @@ int se3et_point_to_node_partition(const float* points, const int64_t* point_leng
                                   int64_t* node_knn_indices, uint8_t* node_knn_masks, void* workspace,
                                   size_t workspace_bytes, se3et_stream_t stream);
 
+/* log_optimal_transport -- LearnableLogOptimalTransport.forward (geotransformer/modules/sinkhorn/learnable_sinkhorn.py:
+ * 21-66, called from experiments/se3eti.3dmatch/model.py:202-205): log-domain Sinkhorn with a dustbin row / column.
+ *   scores [batch, num_row, num_col] fp32; row_masks / col_masks [batch, num_row] / [batch, num_col] (1 = valid) or NULL;
+ *   alpha: device pointer to the learnable dustbin score; out [batch, num_row + 1, num_col + 1] fp32.
+ * One CTA per matrix, all iterations in shared memory (the reference: 2 * num_iterations logsumexp launches). */
+int se3et_log_optimal_transport(const float* scores, const uint8_t* row_masks, const uint8_t* col_masks,
+                                const float* alpha, int64_t batch, int64_t num_row, int64_t num_col,
+                                int64_t num_iterations, float* out, se3et_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,8 @@ from . import _lib
 from .modules.e2pn import E2PN
 from .modules.transformer import GeometricTransformer, SuperPointMatching
 from .ops import transformer_ops as T
+from .modules.sinkhorn import LearnableLogOptimalTransport
+from .ops.gemm import bmm_bf16
 from .ops.partition_ops import point_to_node_partition_stacked
 from .precompute import precompute_data_stack_mode
 
@@ -67,7 +69,8 @@ def make_cfg(variant='se3eti.3dmatch'):
                            # SE3ET-E's model.py does not pass attn_r_positive*: the module defaults apply
                            attn_r_positive='sq' if is_e else 'softplus',
                            attn_r_positive_rot_supervise='sigmoid' if is_e else 'minus')
-    c.model = Cfg(num_points_in_patch=128 if stages == 5 else 64)  # config.py:177 (3DMatch) / se3eti.kitti/config.py:180
+    # config.py:177-178 (3DMatch) / se3eti.kitti/config.py:180-181
+    c.model = Cfg(num_points_in_patch=128 if stages == 5 else 64, num_sinkhorn_iterations=100)
     c.coarse_matching = Cfg(num_targets=128, overlap_threshold=0.1, num_correspondences=256, dual_normalization=True)
     c.neighbor_limits = list(limits)  # demo.py:52 for 3DMatch; KITTI limits are calibrated per dataset (data.py:212-252)
     return c
@@ -89,6 +92,27 @@ class GeoTransformer(nn.Module):
             align_mode=g.align_mode, alternative_impl=g.alternative_impl, n_level_equiv=g.n_level_equiv)
         self.coarse_matching = SuperPointMatching(cfg.coarse_matching.num_correspondences,
                                                   cfg.coarse_matching.dual_normalization)
+        self.optimal_transport = LearnableLogOptimalTransport(cfg.model.num_sinkhorn_iterations)  # model.py:76
+
+    @torch.no_grad()
+    def fine_matching_scores(self, out):
+        """Steps 7.2-8 of the reference forward (experiments/se3eti.3dmatch/model.py:184-205) on the output of
+        forward(): patch features of the selected superpoint pairs, (P, K, K) scores / sqrt(C) as one batched tcgen05
+        GEMM, log-domain optimal transport.  -> matching_scores (P, K + 1, K + 1) fp32 (also stored in `out`)."""
+        ri, si = out['ref_node_corr_indices'], out['src_node_corr_indices']
+        feats = []
+        for f, knn, idx in ((out['ref_feats_f'], out['ref_node_knn_indices'], ri),
+                            (out['src_feats_f'], out['src_node_knn_indices'], si)):
+            f = f.to(torch.bfloat16)
+            padded = torch.cat([f, torch.zeros_like(f[:1])], dim=0)                 # the shadow row (model.py:191-192)
+            k_idx = knn.index_select(0, idx)                                       # (P, K)
+            feats.append(padded.index_select(0, k_idx.reshape(-1)).view(k_idx.shape[0], k_idx.shape[1], -1).contiguous())
+        c = feats[0].shape[-1]
+        scores, _ = bmm_bf16(feats[0], feats[1], alpha=1.0 / c ** 0.5)
+        ms = self.optimal_transport(scores, out['ref_node_knn_masks'].index_select(0, ri),
+                                    out['src_node_knn_masks'].index_select(0, si))
+        out['matching_scores'] = ms
+        return ms
 
     # ---- one pair, reference data_dict -------------------------------------------------------------------------
     @torch.no_grad()

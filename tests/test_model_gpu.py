@@ -143,3 +143,43 @@ def test_full_size_pair_matches_oracle():
     got = set(zip(res["ref_node_corr_indices"][0].tolist(), res["src_node_corr_indices"][0].tolist()))
     want = set(zip(ri.tolist(), si.tolist()))
     assert len(got & want) >= 0.85 * len(want), len(got & want) / len(want)
+
+
+def test_fine_matching_scores_after_forward():
+    """forward() (reference data_dict) -> point-to-node partition -> coarse matching -> fine_matching_scores: patch gather,
+    batched score GEMM and log-domain optimal transport (model.py:184-205 of the reference), checked against the numpy
+    oracles applied to the same GPU features and patch indices."""
+    from oracle import partition as opart
+    from oracle import sinkhorn as osk
+    from se3et_b200.precompute import precompute_data_stack_mode
+    cfg, model, sd = build("se3eti2.3dmatch")
+    p = synthetic.make_3dmatch_pair(13, crop=0.9)
+    pts = torch.from_numpy(np.concatenate([p["ref_points"], p["src_points"]])).to(DEV)
+    lens = torch.tensor([len(p["ref_points"]), len(p["src_points"])], device=DEV)
+    b = cfg.backbone
+    dd = precompute_data_stack_mode(pts, lens, b.num_stages, b.init_voxel_size, b.init_radius, cfg.neighbor_limits)
+    dd['features'] = torch.ones((pts.shape[0], 1), dtype=torch.float32, device=DEV)
+    out = model(dd)
+    # partition outputs against the oracle (bit-exact)
+    pf, lf = dd['points'][1].cpu().numpy(), dd['lengths'][1].cpu().numpy()
+    pc, lc = dd['points'][-1].cpu().numpy(), dd['lengths'][-1].cpu().numpy()
+    _, _, w_masks, w_knn, w_km = opart.point_to_node_partition_stacked(pf, lf, pc, lc, cfg.model.num_points_in_patch)
+    n_ref = int(lc[0])
+    assert np.array_equal(out['ref_node_knn_indices'].cpu().numpy(), w_knn[:n_ref])
+    assert np.array_equal(out['src_node_knn_masks'].cpu().numpy(), w_km[n_ref:])
+    assert np.array_equal(out['ref_node_masks'].cpu().numpy(), w_masks[:n_ref])
+    ms = model.fine_matching_scores(out).cpu().numpy()
+    k = cfg.model.num_points_in_patch
+    ri, si = out['ref_node_corr_indices'].cpu(), out['src_node_corr_indices'].cpu()
+    assert ms.shape == (len(ri), k + 1, k + 1)
+    feats = []
+    for f, knn, idx in ((out['ref_feats_f'], out['ref_node_knn_indices'], ri), (out['src_feats_f'], out['src_node_knn_indices'], si)):
+        f = f.to(torch.bfloat16).float().cpu()
+        padded = torch.cat([f, torch.zeros_like(f[:1])])
+        feats.append(padded[knn.cpu()[idx]])
+    scores = torch.einsum('bnd,bmd->bnm', feats[0], feats[1]) / feats[0].shape[-1] ** 0.5
+    want = osk.log_optimal_transport(scores.numpy(), float(model.optimal_transport.alpha.detach()), cfg.model.num_sinkhorn_iterations,
+                                     out['ref_node_knn_masks'].cpu().numpy()[ri], out['src_node_knn_masks'].cpu().numpy()[si])
+    live = want > -1e11
+    assert np.array_equal(live, ms > -1e11)
+    assert np.abs(ms[live] - want[live]).max() < 2e-3
