@@ -1,8 +1,8 @@
 // LearnableLogOptimalTransport.forward (geotransformer/modules/sinkhorn/learnable_sinkhorn.py:13-66): log-domain Sinkhorn
 // with a dustbin row / column (SuperGlue style) on the (P, K, K) patch score matrices of the fine matching stage
 // (experiments/se3eti.3dmatch/model.py:202-205).  The reference runs 2 x num_iterations torch.logsumexp launches over the
-// (P, K+1, K+1) tensor; here one CTA owns one matrix, keeps it in shared memory for all iterations and writes the result
-// once.  Row pass: one warp per row, lanes over columns; column pass: one warp per column, lanes over rows (odd pitch:
+// (P, K+1, K+1) tensor; here one CTA owns one matrix, keeps it on chip for all iterations and writes the result once
+// (generic kernel: shared memory; K = 64: registers, see log_sinkhorn_reg_kernel).  Row pass: one warp per row, lanes over columns; column pass: one warp per column, lanes over rows (odd pitch:
 // conflict-free both ways).  fp32 throughout, logsumexp as max + log(sum(exp(x - max))) like torch.
 #include "common.cuh"
 
@@ -95,6 +95,88 @@ __global__ void __launch_bounds__(kOtThreads) log_sinkhorn_kernel(const float* _
   }
 }
 
+// K x K patches (K = 64, the 3DMatch configuration): thread-per-row / thread-per-column with the matrix held in registers.
+// Thread t owns row t AND column t of the padded (K+1) x (K+1) matrix (two register copies); u and v live in shared
+// memory and are read as broadcasts, so an iteration has no shuffles and no shared-memory traffic for S at all.
+template <int K>
+__global__ void __launch_bounds__(96) log_sinkhorn_reg_kernel(const float* __restrict__ scores,
+                                                              const uint8_t* __restrict__ row_masks,
+                                                              const uint8_t* __restrict__ col_masks,
+                                                              const float* __restrict__ alpha_ptr, int iters,
+                                                              float* __restrict__ out) {
+  constexpr int R = K + 1;
+  constexpr int kPitch = R | 1;
+  constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+  __shared__ float S[R * kPitch];
+  __shared__ float u[R], v[R];
+  __shared__ int sh_cnt[2];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const float alpha = *alpha_ptr;
+  const uint8_t* rm = row_masks ? row_masks + (int64_t)b * K : nullptr;
+  const uint8_t* cm = col_masks ? col_masks + (int64_t)b * K : nullptr;
+  if (t < 2) sh_cnt[t] = 0;
+  __syncthreads();
+  if (t < K) {
+    if (!rm || rm[t]) atomicAdd(&sh_cnt[0], 1);
+    if (!cm || cm[t]) atomicAdd(&sh_cnt[1], 1);
+  }
+  for (int e = t; e < R * R; e += 96) {
+    const int i = e / R, j = e - i * R;
+    const float sc = (i < K && j < K) ? scores[((int64_t)b * K + i) * K + j] : alpha;
+    const bool masked = (i < K && rm && !rm[i]) || (j < K && cm && !cm[j]);
+    S[i * kPitch + j] = masked ? -kOtInf : sc;
+  }
+  if (t < R) u[t] = v[t] = 0.f;
+  __syncthreads();
+  const float nvr = (float)sh_cnt[0], nvc = (float)sh_cnt[1];
+  const float norm = -logf(nvr + nvc);
+  const bool active = t < R;
+  const int me = active ? t : 0;
+  float log_mu = me < K ? norm : logf(nvc) + norm;
+  if (me < K && rm && !rm[me]) log_mu = -kOtInf;
+  float log_nu = me < K ? norm : logf(nvr) + norm;
+  if (me < K && cm && !cm[me]) log_nu = -kOtInf;
+  float srow[R], scol[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) {
+    srow[j] = S[me * kPitch + j];
+    scol[j] = S[j * kPitch + me];
+  }
+  for (int it = 0; it < iters; ++it) {
+    if (active) {  // u[i] = log_mu[i] - logsumexp_j(S[i][j] + v[j])
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < R; ++j) mx = fmaxf(mx, srow[j] + v[j]);
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < R; ++j) sum += exp2f((srow[j] + v[j] - mx) * kLog2e);
+      u[me] = log_mu - (mx + log2f(sum) * kLn2);
+    }
+    __syncthreads();
+    if (active) {  // v[j] = log_nu[j] - logsumexp_i(S[i][j] + u[i])
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < R; ++i) mx = fmaxf(mx, scol[i] + u[i]);
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < R; ++i) sum += exp2f((scol[i] + u[i] - mx) * kLog2e);
+      v[me] = log_nu - (mx + log2f(sum) * kLn2);
+    }
+    __syncthreads();
+  }
+  if (active) {
+    const float ui = u[me];
+#pragma unroll
+    for (int j = 0; j < R; ++j) S[me * kPitch + j] = srow[j] + ui + v[j] - norm;
+  }
+  __syncthreads();
+  float* o = out + (int64_t)b * R * R;
+  for (int e = t; e < R * R; e += 96) {
+    const int i = e / R, j = e - i * R;
+    o[e] = S[i * kPitch + j];
+  }
+}
+
 }  // namespace se3et
 
 using namespace se3et;
@@ -106,6 +188,12 @@ extern "C" int se3et_log_optimal_transport(const float* scores, const uint8_t* r
     return SE3ET_ERR_ARG;
   if (batch == 0) return SE3ET_OK;
   if (!scores || !alpha || !out) return SE3ET_ERR_ARG;
+  if (num_row == 64 && num_col == 64) {
+    log_sinkhorn_reg_kernel<64><<<(unsigned)batch, 96, 0, static_cast<cudaStream_t>(stream)>>>(
+        scores, row_masks, col_masks, alpha, (int)num_iterations, out);
+    SE3ET_LAUNCH_CHECK();
+    return SE3ET_OK;
+  }
   const int R = (int)num_row + 1, C = (int)num_col + 1;
   const size_t smem = sizeof(float) * ((size_t)R * (C | 1) + 2 * (size_t)R + 2 * (size_t)C);
   if (smem > 227 * 1024) return SE3ET_ERR_UNSUPPORTED;
