@@ -39,6 +39,11 @@ WORKLOADS = {
 }
 
 
+def model_name():
+    """SE3ET-I / SE3ET-E ... from the variant string (se3eti.3dmatch -> SE3ET-I)."""
+    return "SE3ET-" + VARIANT.split(".")[0][len("se3et"):].upper()
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -252,8 +257,8 @@ def reference_arm(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SE3ET-I %s-shaped inference, 1 synthetic pair per step (bounded sample of the "
-                               "%d-pair batch; %s), random-init weights" % (args.workload, args.pairs,
+        "config": {"workload": "%s %s-shaped inference, 1 synthetic pair per step (bounded sample of the "
+                               "%d-pair batch; %s), random-init weights" % (model_name(), args.workload, args.pairs,
                                                                            WORKLOADS[args.workload][3]),
                    "variant": VARIANT},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
@@ -445,8 +450,8 @@ def main():
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "SE3ET-I %s-shaped inference, batch of %d synthetic pairs per GPU per step "
-                                   "(%s), random-init weights" % (args.workload, args.pairs, shape_note),
+            "config": {"workload": "%s %s-shaped inference, batch of %d synthetic pairs per GPU per step "
+                                   "(%s), random-init weights" % (model_name(), args.workload, args.pairs, shape_note),
                        "variant": VARIANT, "pairs_per_gpu_per_step": args.pairs, "pairs_per_launch": ppl,
                        "distinct_pairs": len(distinct), "streams_per_gpu": args.streams, "parallelism": "pairs sharded over %d GPU(s), no collective" % world,
                        "l2": "working set per launch (activations of %d stacked pairs, > 1 GB) exceeds the 126 MB L2" % ppl},
