@@ -215,6 +215,26 @@ int se3et_kpconv_fused(const float* q_pts, const float* s_pts, const int64_t* ne
                        const float* kernel_points_15x3, float kp_extent, float* out_f32, double* stats,
                        const int64_t* seg_offsets, int64_t nseg, int64_t groups, se3et_stream_t stream);
 
+/* kpconv_rows -- the whole KPConvInterSO3.forward (blocks_epn.py:454-546, 334-390) in one kernel, UMMA rows = query
+ * points: per (16-channel chunk, input anchor a) the basis products B[p][beta][a][c] (kpconv_tables.cuh) of 128 / 96
+ * points are stored once in shared memory and the 36 (output anchor r, class kc) K = 16 tcgen05.mma pick their basis
+ * slab and their weight slice W[kc][ridx[a][r]] by descriptor; accumulators: 6 x 32 / 64 fp32 columns of TMEM per point,
+ * the basis weights of the tile's points are parked in the remaining TMEM columns.
+ *   x_bf16  [ns, 6, cin] bf16;  out_f32 [nq * 6, cout] fp32 (pre-norm, as KPConvInterSO3 returns it)
+ *   w_rows_bf16 [cout, 216 * cin] bf16, K-major, K index = (((chunk * 6 + a) * 36 + r * 6 + kc) * 16 + c'),
+ *           value weights[kc][ridx[a][r]][chunk * 16 + (c' ^ 8 * flip[r * 6 + kc])][d]; the slot / flip tables come
+ *           from se3et_kpconv_rows_layout (se3et_b200/modules/e2pn.py:KPConvInterSO3._w_rows)
+ * Requires cin % 16 == 0, cout % 32 == 0, h <= 48, ns * 6 * cin / 8 < 2^32; otherwise SE3ET_ERR_UNSUPPORTED and the
+ * host uses se3et_kpconv_fused.  Shadow neighbours (index >= ns) contribute zero (their weight is zero; their gathered
+ * row is row 0, which must be finite). */
+int se3et_kpconv_rows(const float* q_pts, const float* s_pts, const int64_t* neighbors, int64_t nq, int64_t ns,
+                      int64_t h, const void* x_bf16, int64_t cin, const void* w_rows_bf16, int64_t cout,
+                      const float* kernel_points_15x3, float kp_extent, float* out_f32, se3et_stream_t stream);
+
+/* Weight layout tables of se3et_kpconv_rows: src_slot[a][r * 6 + kc] = kc * 6 + ridx[a][r] (the weights[kc][a'] slice
+ * step a needs for (r, kc)); flip[r * 6 + kc] = 1 when that slice's two 8-channel halves are stored swapped. */
+int se3et_kpconv_rows_layout(int32_t* src_slot_6x36, int32_t* flip_36);
+
 /* kpconv_cin1 -- KPConvInterSO3.forward for the first backbone layer (lifted input, one channel per anchor): K is
  * only 36, so the whole convolution runs on CUDA cores, one warp per query point.  x_bf16 [ns, 6]; w_36xcout fp32
  * [(kc, a'), cout] = weights[kc][a'][0][:]; out_f32 [nq * 6, cout]; optional GroupNorm statistics as for

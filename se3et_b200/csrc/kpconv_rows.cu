@@ -1,0 +1,564 @@
+// KPConvInterSO3.forward (blocks_epn.py:454-546 with feat_gather_by_perm :334-390) with the UMMA rows = QUERY POINTS.
+//
+//   out[p][r][d] = sum_{kc, a, c} B[p][beta(r, kc)][a][c] * W[kc][ridx[a][r]][c][d]
+//   B[p][beta][a][c] = sum_n W16[p][beta][n] * x[idx[p][n]][a][c]            (16-row basis, kpconv_tables.cuh)
+//
+// The products B are stored ONCE; the (r, kc) fan-out that kpconv_fused.cu pays for with 2.25 copies of every product
+// is done by descriptor selection: a step = (16-channel chunk, input anchor a) produces the operand
+// [128 points][16 basis rows][16 channels] (64 KB, 4 sub-tiles of [128 rows x 128 B], 128-byte swizzle, double
+// buffered) and the MMA warp issues, for each of the 36 (r, kc), one K = 16 tcgen05.mma whose A descriptor points at
+// basis slab beta(r, kc) and whose B descriptor points at W[kc][ridx[a][r]][chunk] -- host pre-arranged in step order
+// (e2pn.py:KPConvInterSO3._w_rows) so a TMA ring streams it -- into the TMEM accumulator of output anchor r
+// (6 x BN fp32 columns).
+//
+// Persistent CTA, tile = 16 * PPW points:
+//   warps 0-15  producers, PPW points each (row = i * 16 + warp).  Per tile: the 16 x H basis weights of each point as
+//               mma.sync A fragments, kept for all steps of the tile in TENSOR MEMORY columns the accumulators leave free
+//               (tcgen05.st once, tcgen05.ld per step; the first PPW - TP points stay in registers).  Per (step,
+//               point): cp.async gather of the neighbour rows x[idx[n]][a][chunk] (32 B sectors, 3-stage ring per
+//               warp), mma.sync W16 . X, ONE stmatrix.x4 of the 16 x 16 product into the operand tile.
+//   warp 16     tcgen05.mma issuer.
+//   warp 17     TMA producer of the weight K-blocks (4 (r, kc) slices of 16 channels each).
+//   epilogue    all 16 producer warps (TMEM lane quadrant warp % 4, column group warp / 4): fp32 rows to global memory.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "kpconv_mma.cuh"
+#include "tc.cuh"
+
+namespace se3et {
+namespace rows {
+
+using namespace kpm;
+
+constexpr int kProdWarps = 16;
+constexpr int kThreads = (kProdWarps + 2) * 32;
+constexpr int kSubTile = 128 * 128;      // [128 rows][4 basis rows x 16 channels] bf16
+constexpr int kBBuf = 4 * kSubTile;      // operand of one step
+constexpr int kXRow = 32;                // bytes per gathered row (16 channels)
+constexpr int kXStages = 3;
+constexpr int kWMaxStages = 12;
+constexpr int kW16Row = 112;             // scratch row pitch (bytes): 48 neighbours + 8 pad, conflict-free ldmatrix
+
+__device__ __forceinline__ void mma_1688(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(b0));
+}
+__device__ __forceinline__ void ldmatrix_x2(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+// TMEM as a register stash: thread t of warp w <-> lane 32 (w % 4) + t, consecutive columns <-> consecutive registers
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t& a, uint32_t& b) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+// (r, kc) -> basis row, t = r * 6 + kc
+struct BetaTab {
+  int8_t v[36];
+};
+__host__ __device__ constexpr BetaTab make_beta_tab() {
+  BetaTab t{};
+  for (int r = 0; r < kA; ++r)
+    for (int kc = 0; kc < kKC; ++kc) t.v[r * 6 + kc] = (int8_t)basis_row(r, kc);
+  return t;
+}
+
+struct Args {
+  const float* q_pts;
+  const float* s_pts;
+  const int64_t* idx;
+  const __nv_bfloat16* x;
+  const float* kernel_points;
+  float* out;  // fp32 [nq * 6, cout]
+  int64_t nq, ns;
+  int H;
+  int cin, cout;
+  int wstages;
+  float inv_extent;
+};
+
+template <int BN, int KH>
+struct Smem {
+  static constexpr int kHR = 8 * KH;
+  static constexpr int kXStage = kHR * kXRow;
+  static constexpr int kBOff = 0;
+  static constexpr int kXOff = 2 * kBBuf;
+  static constexpr int kXBytes = kProdWarps * kXStages * kXStage;
+  static constexpr int kBarOff = kXOff + kXBytes;                       // 512 B of barriers
+  static constexpr int kKpOff = kBarOff + 512;                          // 48 floats
+  static constexpr int kWOff = (kKpOff + 192 + 1023) / 1024 * 1024;
+  static constexpr int kWStage = (BN * 128 + 1023) / 1024 * 1024;
+  static int max_wstages() {
+    const int n = (227 * 1024 - 1024 - kWOff) / kWStage;
+    return n > kWMaxStages ? kWMaxStages : n;
+  }
+  static int total(int wstages) { return kWOff + wstages * kWStage + 1024; }
+};
+
+// BN: output columns per CTA; KH: neighbour columns / 8 rounded up (4, 5, 6); PPW: points per producer warp;
+// TP: points per warp whose basis fragments live in tensor memory
+template <int BN, int KH, int PPW, int TP>
+__global__ void __launch_bounds__(kThreads, 1)
+kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
+  using S = Smem<BN, KH>;
+  constexpr int FR = 2 * KH;              // fragment registers per point
+  constexpr int RP = PPW - TP;            // points kept in registers
+  constexpr int kStash = TP * FR;         // stash columns per producer warp
+  constexpr int kAccCols = 6 * BN;
+  static_assert(kAccCols + 4 * kStash <= 512, "tensor memory over-subscribed");
+  static_assert(kW16Row * 16 <= kXStages * S::kXStage, "W16 scratch must fit the gather ring");
+  constexpr int kTilePts = 16 * PPW;
+  constexpr int kHR = S::kHR;
+  constexpr int kXStage = S::kXStage;
+  constexpr BetaTab kBeta = make_beta_tab();
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* b_tile = smem + S::kBOff;
+  uint8_t* w_tile = smem + S::kWOff;
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(smem + S::kBarOff);  // [2]
+  uint64_t* b_empty = b_full + 2;                                     // [2]
+  uint64_t* tmem_full = b_full + 4;
+  uint64_t* tmem_empty = b_full + 5;
+  uint64_t* w_full = b_full + 6;
+  uint64_t* w_empty = w_full + kWMaxStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_empty + kWMaxStages);
+  float* sh_kp = reinterpret_cast<float*>(smem + S::kKpOff);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * BN;
+  const int64_t ntiles = (args.nq + kTilePts - 1) / kTilePts;
+  const int nsteps = args.cin / kChunk * kA;  // (chunk, a), a fastest
+  const int wstages = args.wstages;
+
+  if (threadIdx.x < 45) sh_kp[threadIdx.x] = args.kernel_points[threadIdx.x];
+  if (threadIdx.x == 0) {
+    tc::tma_prefetch_desc(&tma_w);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&b_full[s], kProdWarps);
+      tc::mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < wstages; ++s) {
+      tc::mbar_init(&w_full[s], 1);
+      tc::mbar_init(&w_empty[s], 1);
+    }
+    tc::mbar_init(tmem_full, 1);
+    tc::mbar_init(tmem_empty, kProdWarps);
+    tc::mbar_fence_init();
+  }
+  if (PPW < 8) {
+    // rows 16 PPW .. 127 of the operand are never produced: keep them finite
+    for (int i = threadIdx.x; i < 2 * kBBuf / 16; i += kThreads) reinterpret_cast<uint4*>(b_tile)[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (warp == kProdWarps) tc::tmem_alloc<512>(tmem_ptr);
+  tc::fence_proxy_async_smem();
+  tc::tcgen05_fence_before_sync();
+  __syncthreads();
+  tc::tcgen05_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp < kProdWarps) {
+    // =========================================== producers ===================================================
+    uint8_t* xs = smem + S::kXOff + warp * kXStages * kXStage;
+    const uint32_t xs_s = smem_addr(xs);
+    const int H = args.H;
+    const uint32_t row_chunks = (uint32_t)(kA * args.cin / 8);  // 16-byte units per support row
+    // ldmatrix lane addressing inside a 16-neighbour k-step (see kpconv_fused.cu)
+    const int ld_row = (lane & 7) + ((lane >> 3) & 1) * 8, ld_half = lane >> 4;
+    uint32_t ld_off[(KH + 1) / 2];
+#pragma unroll
+    for (int ks = 0; ks < KH / 2; ++ks) {
+      const int n = ks * 16 + ld_row;
+      ld_off[ks] = n * kXRow + ((ld_half ^ ((n >> 2) & 1)) << 4);
+    }
+    if (KH & 1) {  // 8-neighbour tail: matrices (rows, channels 0-7), (rows, channels 8-15) from lanes 0-7, 8-15
+      const int n = (KH - 1) * 8 + (lane & 7), half = (lane >> 3) & 1;
+      ld_off[KH / 2] = n * kXRow + ((half ^ ((n >> 2) & 1)) << 4);
+    }
+    // gather pieces of this lane: piece i = lane + 32 u -> neighbour i / 2, 16-byte half i % 2
+    constexpr int NU = (2 * kHR + 31) / 32;
+    uint32_t gdst[NU];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      const int i = lane + 32 * u, n = i >> 1;
+      gdst[u] = xs_s + n * kXRow + (((i & 1) ^ ((n >> 2) & 1)) << 4);
+    }
+    // stmatrix.x4 row address of this lane: matrix lane / 8 = (basis rows 0-7 | 8-15) x (channels 0-7 | 8-15), basis
+    // row beta -> sub-tile beta / 4, slot beta % 4; odd sub-tiles hold the channel halves swapped (conflict-free
+    // stores; the step-ordered weights carry the same swap)
+    uint32_t st_off;
+    {
+      const int beta = (lane & 7) + 8 * ((lane >> 3) & 1), half = lane >> 4;
+      const int sub = beta >> 2, slot = beta & 3;
+      const int chunk = slot * 2 + (half ^ (sub & 1));
+      st_off = smem_addr(b_tile) + sub * kSubTile + warp * 128 + ((chunk ^ (warp & 7)) << 4);
+    }
+    const uint32_t stash = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kAccCols + (warp >> 2) * kStash);
+
+    uint32_t afrag[RP > 0 ? RP : 1][FR];
+    uint32_t goff[PPW][NU];  // 16-byte units relative to x (+ the piece's half)
+
+    // basis weights of point slot i of this warp as mma.sync A fragments (through the W16 scratch at the ring's head)
+    auto build = [&](int64_t tile, int i, uint32_t (&fr)[FR]) {
+      const int64_t p = tile * kTilePts + i * 16 + warp;
+      const bool pvalid = p < args.nq;
+      const int64_t pc = pvalid ? p : 0;
+      const float qx = args.q_pts[3 * pc], qy = args.q_pts[3 * pc + 1], qz = args.q_pts[3 * pc + 2];
+      for (int t = lane; t < 16 * kW16Row / 16; t += 32) reinterpret_cast<uint4*>(xs)[t] = make_uint4(0, 0, 0, 0);
+      __syncwarp();
+#pragma unroll 1
+      for (int n = lane; n < H; n += 32) {
+        const int64_t j = pvalid ? args.idx[pc * H + n] : -1;
+        if (j >= 0 && j < args.ns) {
+          float row[16];
+          basis_weights(args.s_pts[3 * j] - qx, args.s_pts[3 * j + 1] - qy, args.s_pts[3 * j + 2] - qz, sh_kp,
+                        args.inv_extent, true, row);
+          uint8_t* dst = xs + n * 2;
+#pragma unroll
+          for (int r = 0; r < 16; ++r) *reinterpret_cast<__nv_bfloat16*>(dst + r * kW16Row) = __float2bfloat16(row[r]);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int ks = 0; ks < KH / 2; ++ks) {
+        uint32_t t4[4];
+        ldmatrix_x4(t4, xs_s + ld_row * kW16Row + (ks * 16 + ld_half * 8) * 2);
+        fr[4 * ks] = t4[0]; fr[4 * ks + 1] = t4[1]; fr[4 * ks + 2] = t4[2]; fr[4 * ks + 3] = t4[3];
+      }
+      if (KH & 1) ldmatrix_x2(fr[FR - 2], fr[FR - 1], xs_s + (lane & 15) * kW16Row + (KH - 1) * 8 * 2);
+      __syncwarp();
+    };
+    auto setup = [&](int64_t tile) {
+      // gather offsets: the neighbour of piece u is lane / 2 + 16 u
+#pragma unroll
+      for (int i = 0; i < PPW; ++i) {
+        const int64_t p = tile * kTilePts + i * 16 + warp;
+        const bool pvalid = p < args.nq;
+        const int64_t pc = pvalid ? p : 0;
+        int64_t j0 = (pvalid && lane < H) ? args.idx[pc * H + lane] : -1;
+        int64_t j1 = (pvalid && 32 + lane < H) ? args.idx[pc * H + 32 + lane] : -1;
+        if (j0 >= args.ns) j0 = -1;
+        if (j1 >= args.ns) j1 = -1;
+        // shadow / padding slots carry weight zero: they re-read the point's first neighbour (same sectors as a valid
+        // piece of the same instruction: no extra traffic, and no hot spot on one row for the whole grid)
+        const int jfb = max(__shfl_sync(0xffffffffu, (int)j0, 0), 0);
+#pragma unroll
+        for (int u = 0; u < NU; ++u) {
+          const int src = (lane >> 1) + 16 * (u & 1);
+          const int jj = __shfl_sync(0xffffffffu, (int)(u < 2 ? j0 : j1), src);
+          goff[i][u] = (uint32_t)(jj >= 0 ? jj : jfb) * row_chunks + (uint32_t)(lane & 1);
+        }
+      }
+      if (TP > 0) {
+#pragma unroll 1
+        for (int i = RP; i < PPW; ++i) {
+          uint32_t fr[FR];
+          build(tile, i, fr);
+          const uint32_t ta = stash + (uint32_t)((i - RP) * FR);
+#pragma unroll
+          for (int f = 0; f + 4 <= FR; f += 4) tmem_st4(ta + f, fr + f);
+          if (FR & 2) tmem_st2(ta + FR - 2, fr[FR - 2], fr[FR - 1]);
+        }
+        tmem_st_wait();
+      }
+#pragma unroll
+      for (int i = 0; i < RP; ++i) build(tile, i, afrag[i]);
+      __syncwarp();
+    };
+
+    // 64-bit source base of a step: x + (a * cin + chunk * 16) elements
+    auto step_base = [&](int step) -> const uint8_t* {
+      const int chunk = step / kA, a = step - chunk * kA;
+      return reinterpret_cast<const uint8_t*>(args.x + a * args.cin + chunk * kChunk);
+    };
+    auto issue = [&](const uint8_t* base, int i, int stage) {
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+#ifndef SE3ET_ROWS_NOGATHER
+        if (u * 32 + 31 < 2 * kHR || lane + 32 * u < 2 * kHR)
+#else
+        if (false)
+#endif
+          cp_async_16(gdst[u] + stage * kXStage, base + (uint64_t)goff[i][u] * 16u, 16);
+      }
+    };
+
+    uint32_t gstep = 0;   // steps produced so far (all tiles)
+    // rotated tile loop (one call site per phase): production(t), setup(t + 1), epilogue(t)
+    for (int64_t tile = (int64_t)blockIdx.x - gridDim.x, titer = -1;; tile += gridDim.x, ++titer) {
+      const bool have = titer >= 0;
+      const bool have_next = tile + gridDim.x < ntiles;
+      if (have) {
+      // items (step, point) in order; the ring runs two items ahead
+      int stage = 0;
+      {
+        const uint8_t* b0 = step_base(0);
+        issue(b0, 0, 0);
+        cp_async_commit();
+        issue(b0, 1, 1);
+        cp_async_commit();
+      }
+      for (int step = 0; step < nsteps; ++step, ++gstep) {
+        const uint32_t buf = gstep & 1u;
+        const uint8_t* base = step_base(step);
+        const uint8_t* base_next = step + 1 < nsteps ? step_base(step + 1) : nullptr;
+        const uint32_t st_base = st_off + buf * kBBuf;
+#pragma unroll
+        for (int i = 0; i < PPW; ++i) {
+          {  // prefetch the item two ahead
+            const int i2 = (i + 2) % PPW;
+            const uint8_t* b2 = i + 2 < PPW ? base : base_next;
+            int st2 = stage + 2;
+            if (st2 >= kXStages) st2 -= kXStages;
+            if (b2) issue(b2, i2, st2);
+            cp_async_commit();
+          }
+          uint32_t fr[FR];
+          if (i < RP) {
+#pragma unroll
+            for (int f = 0; f < FR; ++f) fr[f] = afrag[i < RP ? i : 0][f];
+          } else {
+            const uint32_t ta = stash + (uint32_t)((i - RP) * FR);
+#ifdef SE3ET_ROWS_NOSTASH
+#pragma unroll
+            for (int f = 0; f < FR; ++f) fr[f] = goff[i][f % NU];
+#else
+            if (FR >= 8) {
+              tmem_ld8(ta, fr);
+              if (FR == 12) tmem_ld4(ta + 8, fr + 8);
+              if (FR == 10) tmem_ld2(ta + 8, fr[8], fr[9]);
+            } else {
+              tmem_ld4(ta, fr);
+              tmem_ld4(ta + 4, fr + 4);
+            }
+#endif
+          }
+          cp_async_wait<2>();
+          __syncwarp();
+          if (i == 0) {
+            // the MMAs of the step before last have consumed this operand buffer
+            tc::mbar_wait_long(&b_empty[buf], ((gstep >> 1) & 1u) ^ 1u);
+          }
+          if (i >= RP) tc::tmem_ld_wait();
+          float d[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+          const uint32_t xsb = xs_s + stage * kXStage;
+#ifndef SE3ET_ROWS_NOLDSM
+#pragma unroll
+          for (int ks = 0; ks < KH / 2; ++ks) {
+            uint32_t b[4];
+            ldmatrix_x4_trans(b, xsb + ld_off[ks]);
+            const uint32_t a4[4] = {fr[4 * ks], fr[4 * ks + 1], fr[4 * ks + 2], fr[4 * ks + 3]};
+            mma_16816(d[0], a4, b[0], b[1]);
+            mma_16816(d[1], a4, b[2], b[3]);
+          }
+          if (KH & 1) {
+            uint32_t b0, b1;
+            ldmatrix_x2_trans(b0, b1, xsb + ld_off[KH / 2]);
+            mma_1688(d[0], fr[FR - 2], fr[FR - 1], b0);
+            mma_1688(d[1], fr[FR - 2], fr[FR - 1], b1);
+          }
+#else
+          d[0][0] = __uint_as_float(fr[0] ^ xsb); d[1][1] = __uint_as_float(fr[FR - 1]);
+#endif
+#ifndef SE3ET_ROWS_NOSTSM
+          stmatrix_x4(st_base + i * (16 * 128), pack2(d[0][0], d[0][1]), pack2(d[0][2], d[0][3]), pack2(d[1][0], d[1][1]),
+                      pack2(d[1][2], d[1][3]));
+#else
+          if (d[0][0] == 1.2345f && d[1][1] == 3.f && d[0][3] == 7.f) st_shared_b32(st_base, pack2(d[0][2], d[1][0]));
+#endif
+          __syncwarp();  // every lane is done with this ring stage
+          if (++stage == kXStages) stage = 0;
+        }
+        tc::fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&b_full[buf]);
+      }
+        cp_async_wait<0>();
+        __syncwarp();
+      }
+      // the next tile's basis weights are built under this tile's last MMAs
+      if (have_next) setup(tile + gridDim.x);
+      if (have) {
+        // ---- epilogue: TMEM lane quadrant warp % 4 (rows = points), column group warp / 4 -------------------
+        tc::mbar_wait_long(tmem_full, (uint32_t)titer & 1u);
+        tc::tcgen05_fence_after_sync();
+        const int row = (warp & 3) * 32 + lane;
+        const int64_t p = tile * kTilePts + row;
+        const bool row_ok = row < kTilePts && p < args.nq;
+        constexpr int kColsPerWarp = kAccCols / 4;
+        const int c_begin = (warp >> 2) * kColsPerWarp;
+#pragma unroll 1
+        for (int c0 = c_begin; c0 < c_begin + kColsPerWarp; c0 += 16) {
+          uint32_t rr[16];
+          tc::tmem_ld_32x32b_x16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, rr);
+          tc::tmem_ld_wait();
+          if (row_ok) {
+            const int r = c0 / BN, dcol = c0 - r * BN;
+            float4* dst = reinterpret_cast<float4*>(args.out + (p * kA + r) * args.cout + n0 + dcol);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              dst[jj] = make_float4(__uint_as_float(rr[4 * jj]), __uint_as_float(rr[4 * jj + 1]),
+                                    __uint_as_float(rr[4 * jj + 2]), __uint_as_float(rr[4 * jj + 3]));
+          }
+        }
+        tc::tcgen05_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(tmem_empty);
+      }
+      if (!have_next) break;
+    }
+  } else if (warp == kProdWarps) {
+    // =========================================== MMA issuer ==================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::umma_idesc_bf16(128, BN);
+      uint32_t gstep = 0, titer = 0, ws = 0, wphase = 0;
+      const uint32_t b_s = tc::smem_u32(b_tile), w_s = tc::smem_u32(w_tile);
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++titer) {
+        tc::mbar_wait_long(tmem_empty, (titer & 1) ^ 1);  // the epilogue has drained the previous tile's accumulators
+        tc::tcgen05_fence_after_sync();
+        for (int step = 0; step < nsteps; ++step, ++gstep) {
+          const uint32_t buf = gstep & 1u;
+          tc::mbar_wait_long(&b_full[buf], (gstep >> 1) & 1u);
+          tc::tcgen05_fence_after_sync();
+          const uint32_t bb = b_s + buf * kBBuf;
+#pragma unroll
+          for (int kb = 0; kb < 9; ++kb) {
+            tc::mbar_wait_long(&w_full[ws], wphase);
+            tc::tcgen05_fence_after_sync();
+            const uint64_t b_desc = tc::umma_desc_sw128(w_s + ws * S::kWStage);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int t = kb * 4 + q;          // r * 6 + kc
+              const int beta = kBeta.v[t];
+              const int r = t / 6, kc = t - r * 6;
+              const uint64_t a_desc = tc::umma_desc_sw128(bb + (beta >> 2) * kSubTile) + (uint64_t)((beta & 3) * 2);
+#ifndef SE3ET_ROWS_NOMMA
+              tc::umma_bf16(tmem_base + (uint32_t)(r * BN), a_desc, b_desc + (uint64_t)(q * 2), idesc,
+                            (step | kc) != 0);
+#endif
+            }
+            tc::umma_commit(&w_empty[ws]);
+            if (++ws == (uint32_t)wstages) { ws = 0; wphase ^= 1; }
+          }
+          tc::umma_commit(&b_empty[buf]);
+        }
+        tc::umma_commit(tmem_full);
+      }
+    }
+  } else {
+    // =========================================== weight TMA ==================================================
+    if (lane == 0) {
+      uint32_t ws = 0, wphase = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int kbg = 0; kbg < nsteps * 9; ++kbg) {
+          tc::mbar_wait_long(&w_empty[ws], wphase ^ 1);
+          tc::mbar_arrive_expect_tx(&w_full[ws], BN * 128);
+          tc::tma_load_2d(w_tile + ws * S::kWStage, &tma_w, &w_full[ws], kbg * 64, n0);
+          if (++ws == (uint32_t)wstages) { ws = 0; wphase ^= 1; }
+        }
+      }
+    }
+  }
+  tc::tcgen05_fence_before_sync();
+  __syncthreads();
+  if (warp == kProdWarps) tc::tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace rows
+
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);  // gemm.cu
+
+namespace rows {
+
+template <int BN, int KH, int PPW, int TP>
+static int launch(const CUtensorMap& tw, Args args, cudaStream_t st) {
+  using S = Smem<BN, KH>;
+  args.wstages = S::max_wstages();
+  if (args.wstages < 2) return SE3ET_ERR_UNSUPPORTED;
+  const int smem = S::total(args.wstages);
+  SE3ET_CUDA_CHECK(cudaFuncSetAttribute(kpconv_rows_kernel<BN, KH, PPW, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        smem));
+  const int64_t ntiles = ceil_div(args.nq, 16 * PPW);
+  dim3 grid((unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs), (unsigned)(args.cout / BN));
+  kpconv_rows_kernel<BN, KH, PPW, TP><<<grid, kThreads, smem, st>>>(tw, args);
+  SE3ET_LAUNCH_CHECK();
+  return SE3ET_OK;
+}
+
+}  // namespace rows
+}  // namespace se3et
+
+using namespace se3et;
+
+extern "C" int se3et_kpconv_rows_layout(int32_t* src_slot_6x36, int32_t* flip_36) {
+  for (int a = 0; a < kA; ++a)
+    for (int r = 0; r < kA; ++r)
+      for (int kc = 0; kc < kKC; ++kc) src_slot_6x36[a * 36 + r * 6 + kc] = kc * 6 + ridx_tab(a, r);
+  for (int r = 0; r < kA; ++r)
+    for (int kc = 0; kc < kKC; ++kc) flip_36[r * 6 + kc] = (basis_row(r, kc) >> 2) & 1;
+  return SE3ET_OK;
+}
+
+extern "C" int se3et_kpconv_rows(const float* q_pts, const float* s_pts, const int64_t* neighbors, int64_t nq,
+                                 int64_t ns, int64_t h, const void* x_bf16, int64_t cin, const void* w_rows_bf16,
+                                 int64_t cout, const float* kernel_points_15x3, float kp_extent, float* out_f32,
+                                 se3et_stream_t stream) {
+  if (nq < 0 || ns <= 0 || h <= 0 || cin <= 0 || cout <= 0 || !(kp_extent > 0.f)) return SE3ET_ERR_ARG;
+  if (h > 48 || cin % kpm::kChunk != 0 || cout % 32 != 0) return SE3ET_ERR_UNSUPPORTED;
+  if (ns * kA * cin / 8 >= ((int64_t)1 << 32)) return SE3ET_ERR_UNSUPPORTED;  // 32-bit gather offsets (16-byte units)
+  if (!q_pts || !s_pts || !neighbors || !x_bf16 || !w_rows_bf16 || !kernel_points_15x3 || !out_f32) return SE3ET_ERR_ARG;
+  if (nq == 0) return SE3ET_OK;
+  const int bn = cout % 64 == 0 ? 64 : 32;
+  const int kh = h <= 32 ? 4 : (h <= 40 ? 5 : 6);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rows::Args a;
+  a.q_pts = q_pts; a.s_pts = s_pts; a.idx = neighbors; a.x = static_cast<const __nv_bfloat16*>(x_bf16);
+  a.kernel_points = kernel_points_15x3; a.out = out_f32; a.nq = nq; a.ns = ns; a.H = (int)h;
+  a.cin = (int)cin; a.cout = (int)cout; a.inv_extent = 1.f / kp_extent; a.wstages = 0;
+  CUtensorMap tw;
+  int rc = make_tmap_bf16_2d(&tw, w_rows_bf16, cout, 216 * cin, 216 * cin, bn);
+  if (rc) return rc;
+#ifdef SE3ET_ROWS_DEV
+  if (kh != 5) return SE3ET_ERR_UNSUPPORTED;
+  return bn == 32 ? rows::launch<32, 5, 8, 8>(tw, a, st) : rows::launch<64, 5, 6, 3>(tw, a, st);
+#else
+  if (bn == 32) {
+    switch (kh) {
+      case 4: return rows::launch<32, 4, 8, 8>(tw, a, st);
+      case 5: return rows::launch<32, 5, 8, 8>(tw, a, st);
+      default: return rows::launch<32, 6, 8, 6>(tw, a, st);
+    }
+  }
+  switch (kh) {
+    case 4: return rows::launch<64, 4, 6, 4>(tw, a, st);
+    case 5: return rows::launch<64, 5, 6, 3>(tw, a, st);
+    default: return rows::launch<64, 6, 6, 2>(tw, a, st);
+  }
+#endif
+}

@@ -25,7 +25,8 @@ from . import octahedral
 # switches for A/B measurements and tests (the defaults are the product path)
 # 'cin1_kernel': the CUDA-core first-layer kernel (csrc/kpconv.cu) measures slower than gather + GEMM on B200
 # (9.6 vs 8.4 ms per 64 pairs), so it is off by default and only exercised by the tests
-_GFLAGS = {'fused_kpconv': True, 'two_pass_unary': True, 'double_norm': True, 'cin1_kernel': False, 'dual_apply': True, 'lifted_kernel': True, 'conv_stats_stream': True}
+_GFLAGS = {'fused_kpconv': True, 'two_pass_unary': True, 'double_norm': True, 'cin1_kernel': False, 'dual_apply': True, 'lifted_kernel': True, 'conv_stats_stream': True,
+           'rows_kpconv': True, 'rows_max_cout': 64}
 
 
 def _gn_fusable_fused(cout, groups):
@@ -129,6 +130,7 @@ class KPConvInterSO3(nn.Module):
         self.reset_parameters()
         self._w_cache = _Bf16Cache()
         self._wf_cache = _Bf16Cache()
+        self._wr_cache = _Bf16Cache()
         self._tables_checked = False
 
     def reset_parameters(self):
@@ -160,6 +162,33 @@ class KPConvInterSO3(nn.Module):
             return w.reshape(36, cin // 16, 16, cout).permute(3, 1, 0, 2).reshape(cout, 36 * cin)
         return self._wf_cache.get(self.weights, tr)
 
+    def _w_rows(self):
+        """(Cout, 216*Cin) bf16 for se3et_kpconv_rows: K index = ((chunk*6 + a)*36 + r*6 + kc)*16 + c', value
+        W[kc, ridx[a][r], chunk*16 + (c' ^ 8*flip[r*6 + kc]), d] (tables from the library: se3et_kpconv_rows_layout)."""
+        def tr(w):
+            cin, cout = self.in_channels, self.out_channels
+            slot, flip = K.kpconv_rows_layout()
+            slot = torch.as_tensor(slot, device=w.device)                      # (6 a, 36 t)
+            c = torch.arange(16, device=w.device)
+            cidx = c[None, :] ^ (8 * torch.as_tensor(flip, device=w.device))[:, None]   # (36 t, 16)
+            w4 = w.reshape(36, cin // 16, 16, cout)[slot]                      # (6, 36, nch, 16, cout)
+            w4 = torch.gather(w4, 3, cidx[None, :, None, :, None].expand(6, 36, cin // 16, 16, cout))
+            return w4.permute(4, 2, 0, 1, 3).reshape(cout, 216 * cin)
+        return self._wr_cache.get(self.weights, tr)
+
+    def _rows_ok(self, neighb_inds, ns):
+        return _GFLAGS['rows_kpconv'] and neighb_inds.shape[0] > 0 and self.out_channels <= _GFLAGS['rows_max_cout'] \
+            and K.kpconv_rows_supported(self.in_channels, self.out_channels, neighb_inds.shape[1], ns)
+
+    def _conv(self, q_pts, s_pts, neighb_inds, x):
+        """fp32 (Nq*6, Cout) by the fused kernels (caller checked _fused_ok)."""
+        if self._rows_ok(neighb_inds, s_pts.shape[0]):
+            return K.kpconv_rows(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), self._w_rows(),
+                                 self.kernel_points, self.KP_extent)
+        y, _ = K.kpconv_fused(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), self._w_fused(),
+                              self.kernel_points, self.KP_extent)
+        return y
+
     def _fused_ok(self, neighb_inds):
         return _GFLAGS['fused_kpconv'] and neighb_inds.shape[0] > 0 and K.kpconv_fused_supported(
             self.in_channels, self.out_channels, neighb_inds.shape[1])
@@ -168,9 +197,7 @@ class KPConvInterSO3(nn.Module):
         """-> fp32 (Nq, A, Cout), pre-norm (blocks_epn.py:454-546)."""
         self._check_tables()
         if self._fused_ok(neighb_inds):
-            y, _ = K.kpconv_fused(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), self._w_fused(),
-                                  self.kernel_points, self.KP_extent)
-            return y.view(-1, self.kanchor, self.out_channels)
+            return self._conv(q_pts, s_pts, neighb_inds, x).view(-1, self.kanchor, self.out_channels)
         a = K.kpconv_gather(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), self.kernel_points,
                             self.KP_extent)
         y, _ = linear_bf16(a, self._w_flat())
@@ -194,8 +221,7 @@ class KPConvInterSO3(nn.Module):
             if _GFLAGS['conv_stats_stream'] and K.groupnorm_double_supported(self.out_channels):
                 # the statistics as a streaming pass over the (small) conv output: in the fused kernel's epilogue they
                 # sit on the producers' critical path (4-10 % of that kernel), here they cost one read of y
-                y, _ = K.kpconv_fused(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), self._w_fused(),
-                                      self.kernel_points, self.KP_extent)
+                y = self._conv(q_pts, s_pts, neighb_inds, x)
                 return y, K.groupnorm_stats_stream(y, groups, seg, self.kanchor)
             return K.kpconv_fused(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), self._w_fused(),
                                   self.kernel_points, self.KP_extent, gn=(groups, seg))

@@ -152,6 +152,40 @@ def kpconv_fused(q_pts, s_pts, neighbors, x_bf16, w_fused, kernel_points, kp_ext
     return out, stats
 
 
+def kpconv_rows_layout():
+    """(src_slot (6, 36), flip (36,)) int arrays: weight slice and channel-half swap per (step anchor, (r, kc))."""
+    s = (ctypes.c_int32 * 216)()
+    f = (ctypes.c_int32 * 36)()
+    _lib.check(_lib.lib().se3et_kpconv_rows_layout(s, f), "kpconv_rows_layout")
+    return np.array(s, dtype=np.int64).reshape(6, 36), np.array(f, dtype=np.int64)
+
+
+def kpconv_rows_supported(cin, cout, h, ns=0):
+    """Shapes se3et_kpconv_rows covers (mirrors csrc/kpconv_rows.cu)."""
+    return cin % 16 == 0 and cout % 32 == 0 and h <= 48 and ns * 6 * cin // 8 < (1 << 32)
+
+
+def kpconv_rows(q_pts, s_pts, neighbors, x_bf16, w_rows, kernel_points, kp_extent):
+    """KPConvInterSO3.forward in one kernel, UMMA rows = points. x (Ns, 6, Cin) bf16, w_rows (Cout, 216*Cin) bf16 in
+    step order (KPConvInterSO3._w_rows). -> fp32 (Nq*6, Cout)."""
+    _lib.require_cuda(q_pts, s_pts, neighbors, x_bf16, w_rows, kernel_points)
+    assert x_bf16.dtype == torch.bfloat16 and x_bf16.is_contiguous() and x_bf16.dim() == 3 and x_bf16.shape[1] == 6
+    assert w_rows.dtype == torch.bfloat16 and w_rows.is_contiguous()
+    assert neighbors.dtype == torch.int64 and neighbors.is_contiguous()
+    assert q_pts.dtype == torch.float32 and s_pts.dtype == torch.float32 and q_pts.is_contiguous() and s_pts.is_contiguous()
+    assert kernel_points.dtype == torch.float32 and kernel_points.is_contiguous() and kernel_points.shape == (15, 3)
+    nq, h = neighbors.shape
+    ns, _, cin = x_bf16.shape
+    cout = w_rows.shape[0]
+    assert w_rows.shape[1] == 216 * cin and s_pts.shape[0] == ns and q_pts.shape[0] == nq
+    out = torch.empty((nq * 6, cout), dtype=torch.float32, device=x_bf16.device)
+    _lib.check(_lib.lib().se3et_kpconv_rows(
+        _lib.ptr(q_pts), _lib.ptr(s_pts), _lib.ptr(neighbors), _lib.i64(nq), _lib.i64(ns), _lib.i64(h),
+        _lib.ptr(x_bf16), _lib.i64(cin), _lib.ptr(w_rows), _lib.i64(cout), _lib.ptr(kernel_points),
+        _lib.f32(kp_extent), _lib.ptr(out), _lib.stream_ptr()), "kpconv_rows")
+    return out
+
+
 def groupnorm_double_supported(channels):
     v = channels // 4
     return channels % 4 == 0 and 0 < v <= 256 and (v & (v - 1)) == 0

@@ -90,6 +90,46 @@ def test_kpconv_matches_oracle(pyramid, cin, cout):
         assert rel_err(got, want) < 5e-3
 
 
+@pytest.mark.parametrize("cin,cout,hcols", [(32, 32, 38), (64, 64, 36), (16, 64, 30), (32, 32, 44), (48, 96, 38),
+                                            (64, 64, 46)])
+def test_kpconv_rows_matches_oracle(pyramid, cin, cout, hcols):
+    """se3et_kpconv_rows (UMMA rows = points, basis weights parked in TMEM) against the oracle: self and strided
+    convolution, ragged last tile, neighbour widths that select every fragment variant (<= 32, <= 40, <= 48 columns;
+    widths above the pyramid's are padded with shadow indices, narrower ones truncate), shadow rows included."""
+    t = oe.octahedral_tables()
+    p1 = torch.from_numpy(pyramid["points"][1])
+    p0 = torch.from_numpy(pyramid["points"][0])
+    for q, s, nb in ((p0, p0, pyramid["neighbors"][0]), (p1, p0, pyramid["subsampling"][0])):
+        nb = torch.from_numpy(nb)
+        if hcols <= nb.shape[1]:
+            nb = nb[:, :hcols].contiguous()
+        else:
+            nb = torch.cat([nb, torch.full((nb.shape[0], hcols - nb.shape[1]), s.shape[0], dtype=nb.dtype)], 1)
+        conv = M.KPConvInterSO3(15, 6, cin, cout, 0.05, 0.0625, non_sep_conv=True, rot_by_permute=True,
+                                quotient_factor=4)
+        with torch.no_grad():
+            conv.weights.copy_(helpers.seeded_tensor("conv.weights", (6, 6, cin, cout)))
+        x = helpers.seeded_tensor("conv.input", (s.shape[0], 6, cin)).bfloat16().float()
+        w = conv.weights.detach().bfloat16().float()
+        want = oe.kpconv_inter_so3(q, s, nb, x, w, conv.kernel_points.detach(), 0.05, t["kidx"], t["ridx"])
+        conv = conv.to(DEV)
+        M._GFLAGS['rows_max_cout'] = 1 << 20
+        try:
+            assert conv._fused_ok(nb) and conv._rows_ok(nb, s.shape[0])
+            L = __import__('se3et_b200._lib', fromlist=['x']).lib()
+            L.enabled = True
+            L.reset()
+            got = conv(q.to(DEV), s.to(DEV), nb.to(DEV), x.to(DEV)).cpu()
+            assert L.counts.get("se3et_kpconv_rows", 0) == 1, L.counts
+            L.enabled = False
+        finally:
+            M._GFLAGS['rows_max_cout'] = 64
+        assert torch.isfinite(got).all()
+        assert torch.allclose(got, want, rtol=2e-2, atol=5e-3 * want.abs().max().item() + 1e-6), \
+            (got - want).abs().max().item()
+        assert rel_err(got, want) < 5e-3
+
+
 @pytest.mark.parametrize("cout", [32, 64])
 def test_kpconv_lifted_input_matches_oracle(pyramid, cout):
     """First backbone layer: the LiftBlockEPN output (an expand over the anchor axis) takes the anchor-constant kernel
