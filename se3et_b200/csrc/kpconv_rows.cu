@@ -52,6 +52,16 @@ __device__ __forceinline__ void ldmatrix_x2(uint32_t& r0, uint32_t& r1, uint32_t
 __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
 }
+__device__ __forceinline__ void cp_async_16_if(uint32_t dst, const void* src, bool pred) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %2, 0;\n"
+      "@p cp.async.cg.shared.global [%0], [%1], 16;\n"
+      "}\n" ::"r"(dst),
+      "l"(src), "r"((uint32_t)pred)
+      : "memory");
+}
 // TMEM as a register stash: thread t of warp w <-> lane 32 (w % 4) + t, consecutive columns <-> consecutive registers
 __device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t a, uint32_t b) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
@@ -76,6 +86,32 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr)
                : "memory");
+}
+
+// basis_weights (kpconv_mma.cuh) with the approximate square root (MUFU.SQRT, <= 2 ulp): the result is rounded to bf16
+// right after, so the two agree except on bf16 rounding ties; invalid slots give zero rows
+__device__ __forceinline__ float sqrt_approx(float v) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void basis_weights_fast(float dx, float dy, float dz, const float4* __restrict__ kp,
+                                                   float inv_extent, bool valid, float (&row)[16]) {
+  float w[kKP];
+#pragma unroll
+  for (int k = 0; k < kKP; ++k) {
+    const float4 kk = kp[k];  // one 16-byte shared-memory load per kernel point
+    const float ex = dx - kk.x, ey = dy - kk.y, ez = dz - kk.z;
+    w[k] = valid ? fmaxf(0.f, 1.f - sqrt_approx(ex * ex + ey * ey + ez * ez) * inv_extent) : 0.f;
+  }
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kKP; ++k)
+      if (basis_mask(r) & (1u << k)) s += w[k];
+    row[r] = s;
+  }
 }
 
 // (r, kc) -> basis row, t = r * 6 + kc
@@ -111,8 +147,8 @@ struct Smem {
   static constexpr int kXOff = 2 * kBBuf;
   static constexpr int kXBytes = kProdWarps * kXStages * kXStage;
   static constexpr int kBarOff = kXOff + kXBytes;                       // 512 B of barriers
-  static constexpr int kKpOff = kBarOff + 512;                          // 48 floats
-  static constexpr int kWOff = (kKpOff + 192 + 1023) / 1024 * 1024;
+  static constexpr int kKpOff = kBarOff + 512;                          // 15 x float4
+  static constexpr int kWOff = (kKpOff + 256 + 1023) / 1024 * 1024;
   static constexpr int kWStage = (BN * 128 + 1023) / 1024 * 1024;
   static int max_wstages() {
     const int n = (227 * 1024 - 1024 - kWOff) / kWStage;
@@ -149,7 +185,7 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
   uint64_t* w_full = b_full + 6;
   uint64_t* w_empty = w_full + kWMaxStages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_empty + kWMaxStages);
-  float* sh_kp = reinterpret_cast<float*>(smem + S::kKpOff);
+  float4* sh_kp = reinterpret_cast<float4*>(smem + S::kKpOff);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * BN;
@@ -157,7 +193,9 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
   const int nsteps = args.cin / kChunk * kA;  // (chunk, a), a fastest
   const int wstages = args.wstages;
 
-  if (threadIdx.x < 45) sh_kp[threadIdx.x] = args.kernel_points[threadIdx.x];
+  if (threadIdx.x < kKP)
+    sh_kp[threadIdx.x] = make_float4(args.kernel_points[3 * threadIdx.x], args.kernel_points[3 * threadIdx.x + 1],
+                                     args.kernel_points[3 * threadIdx.x + 2], 0.f);
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&tma_w);
     for (int s = 0; s < 2; ++s) {
@@ -224,25 +262,50 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
     uint32_t afrag[RP > 0 ? RP : 1][FR];
     uint32_t goff[PPW][NU];  // 16-byte units relative to x (+ the piece's half)
 
-    // basis weights of point slot i of this warp as mma.sync A fragments (through the W16 scratch at the ring's head)
-    auto build = [&](int64_t tile, int i, uint32_t (&fr)[FR]) {
+    // ---- per-tile setup: basis weights of a point as mma.sync A fragments (through the W16 scratch at the ring's
+    // head).  Neighbour ids are loaded two points ahead and neighbour coordinates one point ahead of the arithmetic.
+    struct Ids { int j0, j1; };
+    struct Rel { float x0, y0, z0, x1, y1, z1; };
+    auto load_ids = [&](int64_t tile, int i) -> Ids {
       const int64_t p = tile * kTilePts + i * 16 + warp;
-      const bool pvalid = p < args.nq;
-      const int64_t pc = pvalid ? p : 0;
-      const float qx = args.q_pts[3 * pc], qy = args.q_pts[3 * pc + 1], qz = args.q_pts[3 * pc + 2];
-      for (int t = lane; t < 16 * kW16Row / 16; t += 32) reinterpret_cast<uint4*>(xs)[t] = make_uint4(0, 0, 0, 0);
-      __syncwarp();
-#pragma unroll 1
-      for (int n = lane; n < H; n += 32) {
-        const int64_t j = pvalid ? args.idx[pc * H + n] : -1;
-        if (j >= 0 && j < args.ns) {
-          float row[16];
-          basis_weights(args.s_pts[3 * j] - qx, args.s_pts[3 * j + 1] - qy, args.s_pts[3 * j + 2] - qz, sh_kp,
-                        args.inv_extent, true, row);
-          uint8_t* dst = xs + n * 2;
+      Ids r{-1, -1};
+      if (p < args.nq) {
+        const int64_t* row = args.idx + p * H;
+        if (lane < H) { const int64_t j = row[lane]; r.j0 = j < args.ns ? (int)j : -1; }
+        if (KH > 4 && 32 + lane < H) { const int64_t j = row[32 + lane]; r.j1 = j < args.ns ? (int)j : -1; }
+      }
+      return r;
+    };
+    auto load_rel = [&](int64_t tile, int i, Ids id) -> Rel {
+      int64_t p = tile * kTilePts + i * 16 + warp;
+      if (p >= args.nq) p = 0;
+      const float qx = args.q_pts[3 * p], qy = args.q_pts[3 * p + 1], qz = args.q_pts[3 * p + 2];
+      Rel r{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (id.j0 >= 0) {
+        const float* s = args.s_pts + 3 * (int64_t)id.j0;
+        r.x0 = s[0] - qx; r.y0 = s[1] - qy; r.z0 = s[2] - qz;
+      }
+      if (KH > 4 && id.j1 >= 0) {
+        const float* s = args.s_pts + 3 * (int64_t)id.j1;
+        r.x1 = s[0] - qx; r.y1 = s[1] - qy; r.z1 = s[2] - qz;
+      }
+      return r;
+    };
+    auto build = [&](Ids id, Rel rel, uint32_t (&fr)[FR]) {
+      // every column below 8 KH is written (zeros for shadow / padding slots): no separate clearing pass
+      {
+        float row[16];
+        basis_weights_fast(rel.x0, rel.y0, rel.z0, sh_kp, args.inv_extent, id.j0 >= 0, row);
+        uint8_t* dst = xs + lane * 2;
 #pragma unroll
-          for (int r = 0; r < 16; ++r) *reinterpret_cast<__nv_bfloat16*>(dst + r * kW16Row) = __float2bfloat16(row[r]);
-        }
+        for (int r = 0; r < 16; ++r) *reinterpret_cast<__nv_bfloat16*>(dst + r * kW16Row) = __float2bfloat16(row[r]);
+      }
+      if (KH > 4 && 32 + lane < kHR) {
+        float row[16];
+        basis_weights_fast(rel.x1, rel.y1, rel.z1, sh_kp, args.inv_extent, id.j1 >= 0, row);
+        uint8_t* dst = xs + (32 + lane) * 2;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) *reinterpret_cast<__nv_bfloat16*>(dst + r * kW16Row) = __float2bfloat16(row[r]);
       }
       __syncwarp();
 #pragma unroll
@@ -275,11 +338,26 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
           goff[i][u] = (uint32_t)(jj >= 0 ? jj : jfb) * row_chunks + (uint32_t)(lane & 1);
         }
       }
+      Ids id_a = load_ids(tile, 0);
+      Rel rel_a = load_rel(tile, 0, id_a);
+      Ids id_b = load_ids(tile, 1);
+#pragma unroll
+      for (int i = 0; i < RP; ++i) {
+        const Rel rel_b = i + 1 < PPW ? load_rel(tile, i + 1, id_b) : Rel{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const Ids id_c = i + 2 < PPW ? load_ids(tile, i + 2) : Ids{-1, -1};
+        build(id_a, rel_a, afrag[i]);
+        id_a = id_b; rel_a = rel_b; id_b = id_c;
+      }
       if (TP > 0) {
 #pragma unroll 1
         for (int i = RP; i < PPW; ++i) {
+          Rel rel_b{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          Ids id_c{-1, -1};
+          if (i + 1 < PPW) rel_b = load_rel(tile, i + 1, id_b);
+          if (i + 2 < PPW) id_c = load_ids(tile, i + 2);
           uint32_t fr[FR];
-          build(tile, i, fr);
+          build(id_a, rel_a, fr);
+          id_a = id_b; rel_a = rel_b; id_b = id_c;
           const uint32_t ta = stash + (uint32_t)((i - RP) * FR);
 #pragma unroll
           for (int f = 0; f + 4 <= FR; f += 4) tmem_st4(ta + f, fr + f);
@@ -287,8 +365,6 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
         }
         tmem_st_wait();
       }
-#pragma unroll
-      for (int i = 0; i < RP; ++i) build(tile, i, afrag[i]);
       __syncwarp();
     };
 
@@ -301,11 +377,11 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
 #pragma unroll
       for (int u = 0; u < NU; ++u) {
 #ifndef SE3ET_ROWS_NOGATHER
-        if (u * 32 + 31 < 2 * kHR || lane + 32 * u < 2 * kHR)
-#else
-        if (false)
-#endif
+        if (u * 32 + 31 < 2 * kHR)
           cp_async_16(gdst[u] + stage * kXStage, base + (uint64_t)goff[i][u] * 16u, 16);
+        else  // partial instruction: predicated, no branch
+          cp_async_16_if(gdst[u] + stage * kXStage, base + (uint64_t)goff[i][u] * 16u, lane + 32 * u < 2 * kHR);
+#endif
       }
     };
 
@@ -316,7 +392,6 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
       const bool have_next = tile + gridDim.x < ntiles;
       if (have) {
       // items (step, point) in order; the ring runs two items ahead
-      int stage = 0;
       {
         const uint8_t* b0 = step_base(0);
         issue(b0, 0, 0);
@@ -324,7 +399,12 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
         issue(b0, 1, 1);
         cp_async_commit();
       }
-      for (int step = 0; step < nsteps; ++step, ++gstep) {
+      // three steps per trip: the ring stage of item (step, i) is then a compile-time constant (nsteps = 6 chunks)
+#pragma unroll 1
+      for (int step3 = 0; step3 < nsteps; step3 += 3) {
+#pragma unroll
+      for (int s3 = 0; s3 < 3; ++s3, ++gstep) {
+        const int step = step3 + s3;
         const uint32_t buf = gstep & 1u;
         const uint8_t* base = step_base(step);
         const uint8_t* base_next = step + 1 < nsteps ? step_base(step + 1) : nullptr;
@@ -334,8 +414,8 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
           {  // prefetch the item two ahead
             const int i2 = (i + 2) % PPW;
             const uint8_t* b2 = i + 2 < PPW ? base : base_next;
-            int st2 = stage + 2;
-            if (st2 >= kXStages) st2 -= kXStages;
+            const int stage = (s3 * PPW + i) % kXStages;
+            const int st2 = (stage + 2) % kXStages;
             if (b2) issue(b2, i2, st2);
             cp_async_commit();
           }
@@ -367,7 +447,7 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
           }
           if (i >= RP) tc::tmem_ld_wait();
           float d[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-          const uint32_t xsb = xs_s + stage * kXStage;
+          const uint32_t xsb = xs_s + ((s3 * PPW + i) % kXStages) * kXStage;
 #ifndef SE3ET_ROWS_NOLDSM
 #pragma unroll
           for (int ks = 0; ks < KH / 2; ++ks) {
@@ -393,11 +473,11 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
           if (d[0][0] == 1.2345f && d[1][1] == 3.f && d[0][3] == 7.f) st_shared_b32(st_base, pack2(d[0][2], d[1][0]));
 #endif
           __syncwarp();  // every lane is done with this ring stage
-          if (++stage == kXStages) stage = 0;
         }
         tc::fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&b_full[buf]);
+      }
       }
         cp_async_wait<0>();
         __syncwarp();
