@@ -110,7 +110,25 @@ def make_pairs(count, first=0, generator="make_3dmatch_pair"):
     return [(p["ref_points"], p["src_points"]) for p in pairs]
 
 
-NCU_KERNEL = {"se3et_kpconv_fused": "kpconv_fused_kernel", "se3et_gemm_bf16_gnstats": "gemm_tma_kernel",
+def calibrated_limits(cfg, generator, dev=None):
+    """KITTI neighbour limits are calibrated on the dataset by the reference (utils/data.py:212-252, keep_ratio 0.8,
+    2000 samples per stage): same procedure on the synthetic KITTI-shaped pairs of seeds 0.., on the GPU path
+    (se3et_b200.calibrate) or, for the CPU arm, with the reference's own C++ operators (oracle/calibrate.py); the two
+    agree exactly (tests/test_points_gpu.py)."""
+    b = cfg.backbone
+    clouds = make_pairs(4, first=0, generator=generator)
+    if dev is not None:
+        from se3et_b200.calibrate import calibrate_neighbors_stack_mode
+        lim = calibrate_neighbors_stack_mode(clouds, b.num_stages, b.init_voxel_size, b.init_radius, device=dev)
+    else:
+        from oracle import calibrate as ocal
+        from oracle import points as op
+        lim = ocal.calibrate_neighbors_stack_mode(clouds, b.num_stages, b.init_voxel_size, b.init_radius,
+                                                  impl="ref" if op.have_ref() else "oracle")
+    return [int(v) for v in lim]
+
+
+NCU_KERNEL = {"se3et_kpconv_rows": "kpconv_rows_kernel", "se3et_kpconv_fused": "kpconv_fused_kernel", "se3et_gemm_bf16_gnstats": "gemm_tma_kernel",
               "se3et_gemm_bf16_gnapply": "gemm_tma_kernel", "se3et_gemm_grouped_bf16": "gemm_tma_kernel",
               "se3et_gemm_bf16_gnapply_dual": "gemm_dual_gnapply_kernel", "se3et_linear_gnstats_gram": "gram_kernel",
               "se3et_geo_embed_project": "geo_embed_project_kernel", "se3et_geo_embed_lookup": "geo_embed_lookup_kernel", "se3et_radius_neighbors": "radius_query_kernel",
@@ -143,7 +161,7 @@ def algorithmic_work(cfg, n_levels, n_ref_c, n_src_c, limits):
     n_levels = stacked point counts per pyramid level, limits = neighbour columns per level."""
     d = cfg.backbone.init_dim
     S = cfg.backbone.num_stages
-    conv_flops = hmma_flops = 0.0
+    conv_flops = {"se3et_kpconv_rows": 0.0, "se3et_kpconv_fused": 0.0}   # tcgen05 contraction only
     norm_bytes = 0.0
     # Linear + GroupNorm passes (ops/gemm.py): statistics (GEMM epilogue or Gram matrix of the input), apply, dual apply
     ub = {"stats": 0.0, "gram": 0.0, "apply": 0.0, "dual": 0.0}
@@ -152,13 +170,14 @@ def algorithmic_work(cfg, n_levels, n_ref_c, n_src_c, limits):
         ub["gram" if (k in (32, 64, 128) and n >= 2 * k) else "stats"] += rows * k * 2
 
     def block(nq, ns, h, cin, cout, strided):
-        nonlocal conv_flops, hmma_flops, norm_bytes
+        nonlocal norm_bytes
         mid = cout // 4
         if cin != mid:
             stats_pass(6.0 * ns, cin, mid)
             ub["apply"] += 6.0 * ns * (cin + mid) * 2
-        conv_flops += 2.0 * nq * 6 * 36 * mid * mid              # class-pre-summed contraction (issued on tcgen05)
-        hmma_flops += 2.0 * nq * 6 * mid * 16 * 48               # 16-row basis x 48 padded neighbours (mma.sync)
+        # class-pre-summed contraction as issued on tcgen05 (rows = points for mid <= 64: e2pn.py:_rows_ok); the
+        # mma.sync basis weighting that feeds it is NOT counted against the tcgen05 peak
+        conv_flops["se3et_kpconv_rows" if mid <= 64 else "se3et_kpconv_fused"] += 2.0 * nq * 6 * 36 * mid * mid
         norm_bytes += nq * 6 * mid * (4 + 4 + 4 + 2)  # double GroupNorm: two statistics passes + apply over fp32, bf16 out
         rows = 6.0 * nq
         stats_pass(rows, mid, cout)
@@ -179,10 +198,14 @@ def algorithmic_work(cfg, n_levels, n_ref_c, n_src_c, limits):
     c = cfg.geotransformer.hidden_dim
     nn2 = float(n_ref_c ** 2 + n_src_c ** 2)
     nself = sum(1 for b in cfg.geotransformer.blocks if b == "self_eq")
+    # index bytes the timed path produces (precompute.py, backbone_only=True): neighbours and subsampling at full
+    # width, one column for upsampling[1:], upsampling[0] skipped
     search_bytes = sum(8.0 * n_levels[i] * limits[i] for i in range(S))
-    search_bytes += sum(8.0 * n_levels[i + 1] * limits[i] + 8.0 * n_levels[i] * limits[i + 1] for i in range(S - 1))
+    search_bytes += sum(8.0 * n_levels[i + 1] * limits[i] for i in range(S - 1))
+    search_bytes += sum(8.0 * n_levels[i] for i in range(1, S - 1))
     return {
-        "se3et_kpconv_fused": ("tensor", conv_flops + hmma_flops),
+        "se3et_kpconv_rows": ("tensor", conv_flops["se3et_kpconv_rows"]),
+        "se3et_kpconv_fused": ("tensor", conv_flops["se3et_kpconv_fused"]),
         "se3et_gemm_bf16_gnstats": ("hbm", ub["stats"]), "se3et_linear_gnstats_gram": ("hbm", ub["gram"]),
         "se3et_gemm_bf16_gnapply": ("hbm", ub["apply"]), "se3et_gemm_bf16_gnapply_dual": ("hbm", ub["dual"]),
         "se3et_groupnorm_double": ("hbm", norm_bytes),
@@ -206,6 +229,8 @@ def cpu_forward_factory():
     from oracle import transformer as ot
     from se3et_b200.model import create_model, make_cfg
     cfg = make_cfg(VARIANT)
+    if VARIANT.endswith(".kitti"):
+        cfg.neighbor_limits = calibrated_limits(cfg, "make_kitti_pair")
     torch.manual_seed(0)
     sd = {k: v.detach().clone() for k, v in create_model(cfg).state_dict().items()}
     impl = "ref_raw" if op.have_ref() else "oracle"
@@ -268,6 +293,82 @@ def reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def measure_extra(name, args, world, rank, dev, steps=3, warmup=2):
+    """Secondary workloads of BASELINE.json (configs[2] SE3ET-E on ~5k-point pairs, configs[3] KITTI-shaped pairs), run in
+    the same job at the same number of GPUs so that the driver's BENCH / SCALE records carry them: device-timed
+    pairs/s (max over ranks), end to end through forward_pairs, and the dominant entry point of one serial step."""
+    import torch
+    import torch.distributed as dist
+    from se3et_b200 import _lib, sharding
+    from se3et_b200.model import create_model, make_cfg
+    variant, metric, generator, note = WORKLOADS[name]
+    pairs_per_gpu, ppl = (16, 8) if name == "kitti" else (64, 32)
+    cfg = make_cfg(variant)
+    if name == "kitti":
+        cfg.neighbor_limits = calibrated_limits(cfg, generator, dev)
+    torch.manual_seed(0)
+    model = create_model(cfg).to(dev).eval()
+    distinct = make_pairs(min(pairs_per_gpu, 16), first=0, generator=generator)
+    mine = sharding.pairs_for_rank(world * pairs_per_gpu, rank, world)
+    clouds = [distinct[i % len(distinct)] for i in mine]
+    groups = [clouds[i:i + ppl] for i in range(0, len(clouds), ppl)]
+    dev_inputs = []
+    for g in groups:
+        lens = np.array([len(c) for pair in g for c in pair], dtype=np.int64)
+        dev_inputs.append((torch.from_numpy(np.concatenate([c for pair in g for c in pair])).to(dev), torch.from_numpy(lens)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxed(v):
+        if world > 1:
+            t = torch.tensor([v], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return v
+
+    for _ in range(warmup):
+        model.forward_stacked_concurrent(dev_inputs, num_streams=args.streams)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        model.forward_stacked_concurrent(dev_inputs, num_streams=args.streams)
+    e1.record()
+    barrier()
+    ms = maxed(e0.elapsed_time(e1))
+    model.forward_pairs_concurrent(groups, num_streams=args.streams)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        model.forward_pairs_concurrent(groups, num_streams=args.streams)
+    torch.cuda.synchronize()
+    e2e_s = maxed(time.perf_counter() - t0)
+    # one serial step with per-entry-point events
+    L = _lib.lib()
+    names = [n for n in _lib.KERNELS_PER_CALL]
+    L.enabled = True
+    L.reset(timed=names)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for pts_i, lens_i in dev_inputs:
+        model.forward_stacked(pts_i, lens_i)
+    s1.record()
+    torch.cuda.synchronize()
+    L.enabled = False
+    per = {n: L.timed_ms(n)[0] for n in names}
+    top = sorted(per.items(), key=lambda kv: -kv[1])[:4]
+    total = world * pairs_per_gpu * steps
+    return {"metric": metric, "value": total / (ms / 1e3), "unit": "pairs/s", "ms_per_step": ms / steps,
+            "e2e": {"value": total / e2e_s, "unit": "pairs/s"},
+            "config": {"workload": "%s %s-shaped inference (%s)" % ("SE3ET-" + variant.split(".")[0][5:].upper(), name, note),
+                       "variant": variant, "pairs_per_gpu_per_step": pairs_per_gpu, "pairs_per_launch": ppl,
+                       "neighbor_limits": list(cfg.neighbor_limits), "steps": steps, "warmup": warmup},
+            "top_entry_points_ms": {k: round(v, 3) for k, v in top}, "serial_step_ms": round(s0.elapsed_time(s1), 3)}
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -277,8 +378,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=64, help="pairs per step per GPU")
     ap.add_argument("--pairs-per-launch", type=int, default=32, help="pairs stacked into one launch sequence")
-    ap.add_argument("--distinct", type=int, default=32, help="distinct synthetic pairs generated (cycled)")
+    ap.add_argument("--distinct", type=int, default=64, help="distinct synthetic pairs generated (cycled)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (KITTI-shaped, SE3ET-E)")
     ap.add_argument("--streams", type=int, default=2,
                     help="launch sequences in flight per GPU (host thread + CUDA stream each)")
     ap.add_argument("--workload", default="3dmatch", choices=sorted(WORKLOADS),
@@ -307,6 +409,8 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     cfg = make_cfg(VARIANT)
+    if args.workload == "kitti":
+        cfg.neighbor_limits = calibrated_limits(cfg, generator, dev)
     torch.manual_seed(0)
     model = create_model(cfg).to(dev).eval()
 
@@ -347,7 +451,7 @@ def main():
     barrier()
 
     # ---- timed region: K steps, CUDA events, per-entry-point events for the roofline
-    timed_names = ["se3et_kpconv_fused", "se3et_kpconv_cin1", "se3et_kpconv_gather", "se3et_gemm_bf16", "se3et_gemm_bf16_gnstats",
+    timed_names = ["se3et_kpconv_rows", "se3et_kpconv_fused", "se3et_kpconv_cin1", "se3et_kpconv_gather", "se3et_gemm_bf16", "se3et_gemm_bf16_gnstats",
                    "se3et_gemm_bf16_gnapply", "se3et_gemm_bf16_gnapply_dual", "se3et_linear_gnstats_gram",
                    "se3et_gemm_grouped_bf16", "se3et_groupnorm_double",
                    "se3et_groupnorm_apply", "se3et_groupnorm_stats", "se3et_maxpool_nbr", "se3et_radius_neighbors", "se3et_grid_subsample",
@@ -410,6 +514,20 @@ def main():
         e2e_s = float(t.item())
     e2e_value = world * args.pairs * args.steps / e2e_s
 
+    extra = {}
+    if args.workload == "3dmatch" and not args.no_extra:
+        del model, dev_inputs, pinned
+        torch.cuda.empty_cache()
+        for name in ("kitti", "3dmatch-e"):
+            try:
+                extra[name] = measure_extra(name, args, world, rank, dev)
+            except Exception as e:  # the headline line must survive a failing secondary workload
+                extra[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+            torch.cuda.empty_cache()
+        model = create_model(cfg).to(dev).eval()
+        dev_inputs = [(torch.from_numpy(np.concatenate([c for pair in groups[0] for c in pair])).to(dev),
+                       torch.from_numpy(np.array([len(c) for pair in groups[0] for c in pair], dtype=np.int64)))]
+
     if rank == 0:
         peaks = load_peaks()
         # dominant entry point by summed device time inside the timed region
@@ -453,11 +571,12 @@ def main():
             "config": {"workload": "%s %s-shaped inference, batch of %d synthetic pairs per GPU per step "
                                    "(%s), random-init weights" % (model_name(), args.workload, args.pairs, shape_note),
                        "variant": VARIANT, "pairs_per_gpu_per_step": args.pairs, "pairs_per_launch": ppl,
-                       "distinct_pairs": len(distinct), "streams_per_gpu": args.streams, "parallelism": "pairs sharded over %d GPU(s), no collective" % world,
+                       "distinct_pairs": len(distinct), "neighbor_limits": list(cfg.neighbor_limits),
+                       "streams_per_gpu": args.streams, "parallelism": "pairs sharded over %d GPU(s), no collective" % world,
                        "l2": "working set per launch (activations of %d stacked pairs, > 1 GB) exceeds the 126 MB L2" % ppl},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes},
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "extra_workloads": extra,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

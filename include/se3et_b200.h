@@ -398,6 +398,43 @@ int se3et_log_optimal_transport(const float* scores, const uint8_t* row_masks, c
                                 const float* alpha, int64_t batch, int64_t num_row, int64_t num_col,
                                 int64_t num_iterations, float* out, se3et_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fine-stage registration: LocalGlobalRegistration.forward
+ * (geotransformer/modules/geotransformer/local_global_registration.py:49-235; call site
+ * experiments/se3eti.3dmatch/model.py:208-224) with weighted_procrustes
+ * (geotransformer/modules/registration/procrustes.py:6-73), for every patch correspondence of every pair
+ * of a launch sequence.  Two stages share one workspace (se3et_lgr_workspace_bytes); between them the host
+ * turns `counts` into `corr_offsets` (exclusive scan, a device-side cumsum: no sync).
+ * ------------------------------------------------------------------------------------------ */
+int se3et_lgr_workspace_bytes(int64_t num_patches, int64_t k_points, int64_t topk, size_t* bytes);
+
+/* Stage 1 (compute_correspondence_matrix, :49-84, mutual = True, no dustbin): log_scores fp32 [B, ld, ld], the
+ * top-left k_points x k_points block is the patch's log-likelihood matrix; exp, top-k along rows and columns with
+ * (score desc, index asc) order, confidence threshold, masks uint8 [B, k_points].  counts int32 [B]: correspondences
+ * per patch (kept, in torch.nonzero's row-major order, in workspace slots).  k_points <= 128, topk <= 4. */
+int se3et_lgr_correspondences(const float* log_scores, int64_t ld, const uint8_t* ref_masks, const uint8_t* src_masks,
+                              int64_t num_patches, int64_t k_points, int64_t topk, float confidence_threshold,
+                              void* workspace, size_t workspace_bytes, int32_t* counts, se3et_stream_t stream);
+
+/* Stage 2 (local_to_global_registration, :137-205): per patch with >= correspondence_threshold correspondences a
+ * weighted Procrustes transform and its support over all correspondences of the pair; per pair the first best
+ * transform starts num_refinement_steps rounds of inlier-weighted Procrustes (no patch qualifies: all correspondences
+ * start it).  knn points fp32 [B, k_points, 3]; patch_offsets int64 [num_pairs + 1]; corr_offsets int64 [B + 1].
+ * Outputs: compacted correspondences fp32 [sum counts, 3] x 2 and scores [sum counts] (capacity B * topk * k_points
+ * suffices), transforms fp32 [num_pairs, 4, 4]. */
+int se3et_lgr_register(const float* ref_knn_points, const float* src_knn_points, const int64_t* patch_offsets,
+                       int64_t num_pairs, int64_t num_patches, int64_t k_points, int64_t topk, float acceptance_radius,
+                       int64_t correspondence_threshold, int64_t num_refinement_steps, void* workspace,
+                       size_t workspace_bytes, const int32_t* counts, const int64_t* corr_offsets,
+                       float* out_ref_points, float* out_src_points, float* out_scores, float* out_transforms,
+                       se3et_stream_t stream);
+
+/* weighted_procrustes (procrustes.py:6-73) for `batch` point sets of n points: src / ref fp32 [batch, n, 3], weights
+ * fp32 [batch, n] or NULL; out fp32 [batch, 4, 4] mapping src onto ref.  The rotation is the proper rotation the
+ * reference builds from its SVD (V diag(1, 1, det) U^T), found from Horn's quaternion matrix in fp64. */
+int se3et_weighted_procrustes(const float* src_points, const float* ref_points, const float* weights, int64_t batch,
+                              int64_t n, float weight_thresh, float eps, float* out_transforms, se3et_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

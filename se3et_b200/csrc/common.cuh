@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/se3et_b200.h"
 
 namespace se3et {
@@ -22,6 +24,21 @@ void set_last_error(const char* what, cudaError_t err);
 #define SE3ET_LAUNCH_CHECK() SE3ET_CUDA_CHECK(cudaGetLastError())
 
 constexpr int kNumSMs = 148;  // B200
+constexpr int kMaxDevices = 32;
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: remembered per (call site, device) so that a
+// process driving several GPUs configures every one of them; host threads may race here (atomics, idempotent call).
+#define SE3ET_ENSURE_SMEM(kernel, bytes)                                                                            \
+  do {                                                                                                              \
+    static std::atomic<int> _cfg[::se3et::kMaxDevices];                                                             \
+    int _dev = 0;                                                                                                   \
+    SE3ET_CUDA_CHECK(cudaGetDevice(&_dev));                                                                         \
+    const bool _in = _dev >= 0 && _dev < ::se3et::kMaxDevices;                                                      \
+    if (!_in || _cfg[_dev].load(std::memory_order_relaxed) < (int)(bytes)) {                                        \
+      SE3ET_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));   \
+      if (_in) _cfg[_dev].store((int)(bytes), std::memory_order_relaxed);                                           \
+    }                                                                                                               \
+  } while (0)
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

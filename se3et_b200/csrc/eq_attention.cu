@@ -229,12 +229,7 @@ extern "C" int se3et_anchor_pair_stats(const void* q_bf16, int64_t q_pt, int64_t
 #define SE3ET_STATS(C)                                                                                              \
   {                                                                                                                 \
     const int smem = kStatBK * ((C) + 8) * 2;                                                                       \
-    static bool configured = false;                                                                                 \
-    if (!configured) {                                                                                              \
-      SE3ET_CUDA_CHECK(cudaFuncSetAttribute(anchor_pair_stats_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                            smem));                                                                 \
-      configured = true;                                                                                            \
-    }                                                                                                               \
+    SE3ET_ENSURE_SMEM(anchor_pair_stats_kernel<C>, smem);                                                           \
     anchor_pair_stats_kernel<C><<<grid, kStatWarps * 32, smem, st>>>(q, q_pt, q_an, k, k_pt, k_an, pr, (int)anchors, \
                                                                       scale, positive, g);                          \
   }

@@ -417,12 +417,7 @@ static int launch_gemm_variant(const CUtensorMap& ta, const CUtensorMap& tb, Gem
   shape.stages = kMulti ? kGemmMaxStages : (num_kb < kGemmMaxStages ? num_kb : kGemmMaxStages);
   while (shape.stages > (kMulti ? 2 : 1) && S::total(shape.stages, c_tile) > max_smem) --shape.stages;
   const int smem = S::total(shape.stages, c_tile);
-  static int configured = 0;
-  if (configured < smem) {
-    SE3ET_CUDA_CHECK(cudaFuncSetAttribute(gemm_tma_kernel<BN, kMulti>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          smem));
-    configured = smem;
-  }
+  SE3ET_ENSURE_SMEM((gemm_tma_kernel<BN, kMulti>), smem);
   const int64_t m_tiles = ceil_div(shape.M, kGemmBM);
   const int64_t n_tiles = shape.N / BN;
   int64_t tpc = 1;

@@ -225,12 +225,7 @@ static int launch_dual(const CUtensorMap& ta1, const CUtensorMap& tb1, const CUt
   // the staged output tile must fit the ring it aliases
   while (args.stages * S::kStageBytes < kDualBM * BN * 2) ++args.stages;
   const int smem = S::total(args.stages);
-  static int configured = 0;
-  if (configured < smem) {
-    SE3ET_CUDA_CHECK(cudaFuncSetAttribute(gemm_dual_gnapply_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          smem));
-    configured = smem;
-  }
+  SE3ET_ENSURE_SMEM(gemm_dual_gnapply_kernel<BN>, smem);
   dim3 grid((unsigned)ceil_div(args.M, kDualBM), (unsigned)(args.N / BN), 1);
   gemm_dual_gnapply_kernel<BN><<<grid, kDualThreads, smem, st>>>(ta1, tb1, ta2, tb2, args);
   SE3ET_LAUNCH_CHECK();

@@ -354,14 +354,8 @@ int gemm_stream_gnapply(const void* a1, int64_t lda1, const void* b1, int64_t ld
   gn_table_kernel<<<dim3((unsigned)ceil_div(n, 256), (unsigned)nseg), 256, 0, st>>>(
       n1, n2, dual ? 1 : 0, seg_off, (int)rpp, (int)n, (int)groups, eps, static_cast<float4*>(workspace));
   SE3ET_LAUNCH_CHECK();
-  static bool configured = false;
-  if (!configured) {
-    SE3ET_CUDA_CHECK(cudaFuncSetAttribute(gemm_stream_gnapply_kernel<false>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmem));
-    SE3ET_CUDA_CHECK(cudaFuncSetAttribute(gemm_stream_gnapply_kernel<true>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmem));
-    configured = true;
-  }
+  SE3ET_ENSURE_SMEM(gemm_stream_gnapply_kernel<false>, kSSmem);
+  SE3ET_ENSURE_SMEM(gemm_stream_gnapply_kernel<true>, kSSmem);
   const int64_t work = (int64_t)args.m_tiles * args.n_tiles;
   const unsigned grid = (unsigned)(work < 2 * kNumSMs ? work : 2 * kNumSMs);
   if (dual)
@@ -394,12 +388,7 @@ int gemm_stream_plain(const void* a, int64_t lda, const void* b, int64_t ldb, in
   args.slope = slope;
   args.plain_bias = bias;
   args.plain_alpha = alpha;
-  static bool configured = false;
-  if (!configured) {
-    SE3ET_CUDA_CHECK(cudaFuncSetAttribute(gemm_stream_gnapply_kernel<false>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSSmem));
-    configured = true;
-  }
+  SE3ET_ENSURE_SMEM(gemm_stream_gnapply_kernel<false>, kSSmem);
   const int64_t work = (int64_t)args.m_tiles * args.n_tiles;
   const unsigned grid = (unsigned)(work < 2 * kNumSMs ? work : 2 * kNumSMs);
   gemm_stream_gnapply_kernel<false><<<grid, kSThreads, kSSmem, st>>>(ta, tb, ta, tb, args);

@@ -255,11 +255,7 @@ template <int K>
 static int launch_gram(const __nv_bfloat16* a, int64_t lda, const int64_t* seg_off, int nseg, int rpp,
                        int64_t total_tiles, double* gram, cudaStream_t st) {
   using C = GramCfg<K>;
-  static bool configured = false;
-  if (!configured) {
-    SE3ET_CUDA_CHECK(cudaFuncSetAttribute(gram_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem));
-    configured = true;
-  }
+  SE3ET_ENSURE_SMEM(gram_kernel<K>, C::kSmem);
   const int64_t cap = (int64_t)C::kCtasPerSM * kNumSMs;
   const int64_t grid = total_tiles < cap ? total_tiles : cap;
   gram_kernel<K><<<(unsigned)grid, kGramThreads, C::kSmem, st>>>(a, lda, seg_off, nseg, rpp, total_tiles, gram);

@@ -336,12 +336,7 @@ static int launch_gather_mma(const float* q_pts, const float* s_pts, const int64
                              int h, const __nv_bfloat16* x, int cin, const float* kp, float inv_extent,
                              __nv_bfloat16* out, int kpad, cudaStream_t st) {
   using S = GatherSmem<KS>;
-  static bool configured = false;
-  if (!configured) {
-    SE3ET_CUDA_CHECK(cudaFuncSetAttribute(kpconv_gather_mma_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          S::kTotal));
-    configured = true;
-  }
+  SE3ET_ENSURE_SMEM(kpconv_gather_mma_kernel<KS>, S::kTotal);
   int64_t blocks = ceil_div(nq, kGatherWarps);
   if (blocks > (int64_t)kNumSMs * 4) blocks = (int64_t)kNumSMs * 4;
   kpconv_gather_mma_kernel<KS><<<(unsigned)blocks, kGatherWarps * 32, S::kTotal, st>>>(

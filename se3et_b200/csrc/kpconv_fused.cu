@@ -36,7 +36,11 @@ constexpr int kFXRow = 32;                    // bytes per gathered row: 16 chan
                                               // are swapped when (n / 4) is odd -> conflict-free ldmatrix
 constexpr int kFWMaxStages = 18;             // weight K-block ring: as many stages as fit (two chunks at most)
 constexpr int kFKS = 3;                       // neighbour k-steps of 16 (H <= 48)
-constexpr int kFW16Row = (kFKS * 16 + 8) * 2; // 112 bytes
+constexpr int kFW16Row = (kFKS * 16 + 8) * 2; // 112 bytes (one neighbour half per ring stage)
+// Neighbour columns beyond 48 (KITTI-calibrated limits, utils/data.py:212-252) are processed as NH = 2 halves of <= 48:
+// a ring stage holds one half, the products of both halves accumulate in registers before the operand stores, and
+// the second half's basis-weight fragments are parked in tensor-memory columns the accumulators leave free.
+__host__ __device__ constexpr int w16_pitch(int nh, int hr) { return nh == 1 ? kFW16Row : (2 * hr + 8) * 2; }
 
 __constant__ int8_t c_f_basis_target[16][6] = {
 #define SE3ET_BT(row) {(int8_t)basis_target(row, 0), (int8_t)basis_target(row, 1), (int8_t)basis_target(row, 2), \
@@ -56,7 +60,7 @@ struct FusedArgs {
   const float* kernel_points;
   float* out;                 // fp32 [nq * 6, cout]
   int64_t nq, ns;
-  int H, HR;                  // neighbour columns, rounded up to 8
+  int H, HR;                  // neighbour columns; rows per ring stage (one half, rounded up to 8)
   int cin, cout;
   int wstages;                // weight ring stages (<= kFWMaxStages)
   float inv_extent;
@@ -85,11 +89,13 @@ struct FusedSmem {
   }
 };
 
-template <int BN>
+template <int BN, int NH>
 __global__ void __launch_bounds__(kFThreads, 1)
 kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
   using S = FusedSmem<BN>;
-  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  constexpr uint32_t kAccCols = BN < 32 ? 32 : BN;
+  // NH = 2: 12 stash columns per producer warp (4 warps per lane quadrant) after the accumulators
+  constexpr uint32_t kTmemCols = NH == 1 ? kAccCols : (kAccCols + 48 <= 64 ? 64 : (kAccCols + 48 <= 128 ? 128 : 256));
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_tile = smem + S::kAOff;
@@ -175,8 +181,10 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
     }
     // per-tile state (registers): A fragments of this warp's point's basis weights, gather source pointers
     uint32_t afrag[kFKS][4];
-    const __nv_bfloat16* gsrc[3];
-    uint32_t gvalid = 0;  // bit u: the piece reads a real neighbour (else zero fill)
+    const __nv_bfloat16* gsrc[NH][3];
+    uint32_t gvalid = 0;  // bit 3 * half + u: the piece reads a real neighbour (else zero fill)
+    const uint32_t stash = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kAccCols + (uint32_t)((warp >> 2) * 12);
+    const int wpitch = w16_pitch(NH, HR);
 
     auto setup = [&](int64_t tile) {
       const int64_t p = tile * kFPts + warp;
@@ -185,50 +193,67 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
       const float qx = args.q_pts[3 * pc], qy = args.q_pts[3 * pc + 1], qz = args.q_pts[3 * pc + 2];
       gvalid = 0;
 #pragma unroll
-      for (int u = 0; u < 3; ++u) {
-        const int i = lane + 32 * u, n = i >> 1;
-        int64_t j = (pvalid && n < H) ? args.idx[pc * H + n] : -1;
-        const bool valid = j >= 0 && j < args.ns;
-        gsrc[u] = args.x + (valid ? j : 0) * (int64_t)(kA * cin) + (i & 1) * 8;
-        gvalid |= (valid ? 1u : 0u) << u;
-      }
-      // W16 scratch aliases the head of the gather ring: [16][kFW16Row]
-      for (int i = lane; i < 16 * kFW16Row / 16; i += 32) reinterpret_cast<uint4*>(xs)[i] = make_uint4(0, 0, 0, 0);
-      __syncwarp();
+      for (int hf = 0; hf < NH; ++hf)
 #pragma unroll
-      for (int it = 0; it < 2; ++it) {
-        const int n = lane + 32 * it;
-        if (it == 0 || n < H) {
-          int64_t j = (pvalid && n < H) ? args.idx[pc * H + n] : -1;
+        for (int u = 0; u < 3; ++u) {
+          const int i = lane + 32 * u, n = hf * HR + (i >> 1);
+          int64_t j = (pvalid && (i >> 1) < HR && n < H) ? args.idx[pc * H + n] : -1;
           const bool valid = j >= 0 && j < args.ns;
-          if (valid) {  // shadow / padding neighbours keep their zero weights
-            float row[16];
-            basis_weights(args.s_pts[3 * j] - qx, args.s_pts[3 * j + 1] - qy, args.s_pts[3 * j + 2] - qz, sh_kp,
-                          args.inv_extent, true, row);
-            uint8_t* dst = xs + n * 2;
+          gsrc[hf][u] = args.x + (valid ? j : 0) * (int64_t)(kA * cin) + (i & 1) * 8;
+          gvalid |= (valid ? 1u : 0u) << (3 * hf + u);
+        }
+      // W16 scratch aliases the head of the gather ring: [16][wpitch]
+      for (int i = lane; i < 16 * wpitch / 16; i += 32) reinterpret_cast<uint4*>(xs)[i] = make_uint4(0, 0, 0, 0);
+      __syncwarp();
+#pragma unroll 1
+      for (int n = lane; n < H; n += 32) {
+        int64_t j = pvalid ? args.idx[pc * H + n] : -1;
+        const bool valid = j >= 0 && j < args.ns;
+        if (valid) {  // shadow / padding neighbours keep their zero weights
+          float row[16];
+          basis_weights(args.s_pts[3 * j] - qx, args.s_pts[3 * j + 1] - qy, args.s_pts[3 * j + 2] - qz, sh_kp,
+                        args.inv_extent, true, row);
+          // column of neighbour n: half n / HR, position n % HR inside it
+          const int col = NH == 1 ? n : (n >= HR ? HR + (n - HR) : n);
+          uint8_t* dst = xs + col * 2;
 #pragma unroll
-            for (int r = 0; r < 16; ++r) *reinterpret_cast<__nv_bfloat16*>(dst + r * kFW16Row) = __float2bfloat16(row[r]);
-          }
+          for (int r = 0; r < 16; ++r) *reinterpret_cast<__nv_bfloat16*>(dst + r * wpitch) = __float2bfloat16(row[r]);
         }
       }
       __syncwarp();
+      if (NH == 2) {  // second half first: its fragments go to tensor memory
+        uint32_t t4[kFKS][4];
 #pragma unroll
-      for (int ks = 0; ks < kFKS; ++ks)
-        ldmatrix_x4(afrag[ks], xs_s + ld_row * kFW16Row + (ks * 16 + ld_half * 8) * 2);
+        for (int ks = 0; ks < kFKS; ++ks) {
+          if (ks * 16 < HR) ldmatrix_x4(t4[ks], xs_s + ld_row * wpitch + (HR + ks * 16 + ld_half * 8) * 2);
+          else { t4[ks][0] = t4[ks][1] = t4[ks][2] = t4[ks][3] = 0u; }
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stash + ks * 4), "r"(t4[ks][0]),
+                       "r"(t4[ks][1]), "r"(t4[ks][2]), "r"(t4[ks][3]) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+#pragma unroll
+      for (int ks = 0; ks < kFKS; ++ks) {
+        if (NH == 1 || ks * 16 < HR) ldmatrix_x4(afrag[ks], xs_s + ld_row * wpitch + (ks * 16 + ld_half * 8) * 2);
+        else { afrag[ks][0] = afrag[ks][1] = afrag[ks][2] = afrag[ks][3] = 0u; }
+      }
       __syncwarp();
       // gather rows >= H must read as zero again
-      for (int i = lane; i < 16 * kFW16Row / 16; i += 32) reinterpret_cast<uint4*>(xs)[i] = make_uint4(0, 0, 0, 0);
+      for (int i = lane; i < 16 * wpitch / 16; i += 32) reinterpret_cast<uint4*>(xs)[i] = make_uint4(0, 0, 0, 0);
       __syncwarp();
     };
 
-    auto issue = [&](int chunk, int a, int stage) {
+    // item = (chunk, input anchor a, neighbour half): idx = a * NH + half inside a chunk, ring stage idx % 3
+    auto issue = [&](int chunk, int idx, int stage) {
+      const int a = idx / NH, hf = idx % NH;
       const int off = a * cin + chunk * kChunk;
 #pragma unroll
       for (int u = 0; u < 3; ++u) {
-        if (lane + 32 * u < 2 * H) cp_async_16(gdst[u] + stage * xstage, gsrc[u] + off, (gvalid >> u) & 1u ? 16 : 0);
+        if (lane + 32 * u < 2 * HR)
+          cp_async_16(gdst[u] + stage * xstage, gsrc[hf][u] + off, (gvalid >> (3 * hf + u)) & 1u ? 16 : 0);
       }
     };
-    // item (chunk, a) occupies ring stage a % 3 (6 % 3 == 0); the ring runs two items ahead
+    // the ring runs two items ahead (6 * NH items per chunk, a multiple of the three stages)
     auto prologue = [&]() {
       issue(0, 0, 0);
       cp_async_commit();
@@ -247,26 +272,47 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
       for (int chunk = 0; chunk < nchunks; ++chunk) {
 #pragma unroll
         for (int a = 0; a < kA; ++a) {
-          {  // prefetch the item two ahead (possibly of the next chunk)
-            const int a2 = (a + 2) % kA;
-            const int chunk2 = chunk + (a + 2) / kA;
-            if (chunk2 < nchunks) issue(chunk2, a2, a2 % kFStages);
-            cp_async_commit();
-          }
-          cp_async_wait<2>();
-          __syncwarp();
-          if (a == 0) {
-            tc::mbar_wait_long(a_empty, (gc & 1) ^ 1);  // the MMA of the previous chunk has consumed the operand tile
-          }
           float d[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-          const uint32_t xsb = xs_s + (a % kFStages) * xstage;
 #pragma unroll
-          for (int ks = 0; ks < kFKS; ++ks) {
-            const int n = ks * 16 + ld_row;
-            uint32_t b[4];
-            ldmatrix_x4_trans(b, n < HR ? xsb + n * kFXRow + ((ld_half ^ ((n >> 2) & 1)) << 4) : zero_s);
-            mma_16816(d[0], afrag[ks], b[0], b[1]);
-            mma_16816(d[1], afrag[ks], b[2], b[3]);
+          for (int hf = 0; hf < NH; ++hf) {
+            constexpr int kItems = kA * NH;
+            const int idx = a * NH + hf;
+            {  // prefetch the item two ahead (possibly of the next chunk)
+              const int idx2 = (idx + 2) % kItems;
+              const int chunk2 = chunk + (idx + 2) / kItems;
+              if (chunk2 < nchunks) issue(chunk2, idx2, idx2 % kFStages);
+              cp_async_commit();
+            }
+            uint32_t bfrag[kFKS][4];
+            if (hf == 1) {
+#pragma unroll
+              for (int ks = 0; ks < kFKS; ++ks)
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(bfrag[ks][0]), "=r"(bfrag[ks][1]), "=r"(bfrag[ks][2]), "=r"(bfrag[ks][3])
+                             : "r"(stash + ks * 4)
+                             : "memory");
+            }
+            cp_async_wait<2>();
+            __syncwarp();
+            if (idx == 0) {
+              tc::mbar_wait_long(a_empty, (gc & 1) ^ 1);  // the MMA of the previous chunk has consumed the operand tile
+            }
+            if (hf == 1) tc::tmem_ld_wait();
+            const uint32_t xsb = xs_s + (idx % kFStages) * xstage;
+#pragma unroll
+            for (int ks = 0; ks < kFKS; ++ks) {
+              const int n = ks * 16 + ld_row;
+              uint32_t b[4];
+              ldmatrix_x4_trans(b, n < HR ? xsb + n * kFXRow + ((ld_half ^ ((n >> 2) & 1)) << 4) : zero_s);
+              if (hf == 0) {
+                mma_16816(d[0], afrag[ks], b[0], b[1]);
+                mma_16816(d[1], afrag[ks], b[2], b[3]);
+              } else {
+                mma_16816(d[0], bfrag[ks], b[0], b[1]);
+                mma_16816(d[1], bfrag[ks], b[2], b[3]);
+              }
+            }
+            if (hf + 1 < NH) __syncwarp();  // every lane is done with this ring stage
           }
           // accumulator rows g / g + 8 = basis rows; each is copied to its (r, kc) targets: operand row
           // m = warp * 6 + r, slot j = kc * 6 + ridx[a][r], K-block j / 4, 16-byte chunk (j % 4) * 2 + nt swizzled by
@@ -420,20 +466,16 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
 
 int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);  // gemm.cu
 
-template <int BN>
+template <int BN, int NH>
 static int launch_fused(const CUtensorMap& tw, FusedArgs args, cudaStream_t st) {
   using S = FusedSmem<BN>;
   args.wstages = S::max_wstages(args.HR);
   if (args.wstages < 2) return SE3ET_ERR_UNSUPPORTED;
   const int smem = S::total(args.HR, args.wstages);
-  static int configured = 0;
-  if (configured < smem) {
-    SE3ET_CUDA_CHECK(cudaFuncSetAttribute(kpconv_fused_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
-  }
+  SE3ET_ENSURE_SMEM((kpconv_fused_kernel<BN, NH>), smem);
   const int64_t ntiles = ceil_div(args.nq, kFPts);
   dim3 grid((unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs), (unsigned)(args.cout / BN));
-  kpconv_fused_kernel<BN><<<grid, kFThreads, smem, st>>>(tw, args);
+  kpconv_fused_kernel<BN, NH><<<grid, kFThreads, smem, st>>>(tw, args);
   SE3ET_LAUNCH_CHECK();
   return SE3ET_OK;
 }
@@ -448,7 +490,7 @@ extern "C" int se3et_kpconv_fused(const float* q_pts, const float* s_pts, const 
                                   double* stats, const int64_t* seg_offsets, int64_t nseg, int64_t groups,
                                   se3et_stream_t stream) {
   if (nq < 0 || ns <= 0 || h <= 0 || cin <= 0 || cout <= 0 || !(kp_extent > 0.f)) return SE3ET_ERR_ARG;
-  if (h > kFKS * 16 || cin % kChunk != 0 || cout % 16 != 0) return SE3ET_ERR_UNSUPPORTED;
+  if (h > 2 * kFKS * 16 || cin % kChunk != 0 || cout % 16 != 0) return SE3ET_ERR_UNSUPPORTED;
   int bn = 0;
   for (int c : {128, 64, 32, 16})
     if (cout % c == 0) { bn = c; break; }
@@ -457,7 +499,8 @@ extern "C" int se3et_kpconv_fused(const float* q_pts, const float* s_pts, const 
   FusedArgs a;
   a.q_pts = q_pts; a.s_pts = s_pts; a.idx = neighbors; a.x = static_cast<const __nv_bfloat16*>(x_bf16);
   a.kernel_points = kernel_points_15x3; a.out = out_f32; a.nq = nq; a.ns = ns; a.H = (int)h;
-  a.HR = ((int)h + 7) / 8 * 8;
+  const bool halves = h > kFKS * 16;   // two neighbour halves per (chunk, anchor)
+  a.HR = halves ? (((int)h + 1) / 2 + 7) / 8 * 8 : ((int)h + 7) / 8 * 8;
   if (a.HR < 16) a.HR = 16;  // the per-warp ring doubles as the W16 scratch (16 x 112 bytes)
   a.cin = (int)cin; a.cout = (int)cout; a.inv_extent = 1.f / kp_extent;
   a.gn_stats = nullptr; a.gn_seg_off = nullptr; a.gn_nseg = 0; a.gn_cpg = 1; a.gn_groups = 0;
@@ -474,11 +517,19 @@ extern "C" int se3et_kpconv_fused(const float* q_pts, const float* s_pts, const 
   CUtensorMap tw;
   int rc = make_tmap_bf16_2d(&tw, w_bf16, cout, 36 * cin, 36 * cin, bn);
   if (rc) return rc;
+  if (halves) {
+    switch (bn) {
+      case 128: return launch_fused<128, 2>(tw, a, st);
+      case 64: return launch_fused<64, 2>(tw, a, st);
+      case 32: return launch_fused<32, 2>(tw, a, st);
+      default: return launch_fused<16, 2>(tw, a, st);
+    }
+  }
   switch (bn) {
-    case 128: return launch_fused<128>(tw, a, st);
-    case 64: return launch_fused<64>(tw, a, st);
-    case 32: return launch_fused<32>(tw, a, st);
-    default: return launch_fused<16>(tw, a, st);
+    case 128: return launch_fused<128, 1>(tw, a, st);
+    case 64: return launch_fused<64, 1>(tw, a, st);
+    case 32: return launch_fused<32, 1>(tw, a, st);
+    default: return launch_fused<16, 1>(tw, a, st);
   }
 }
 
@@ -487,19 +538,19 @@ extern "C" int se3et_kpconv_fused_attrs(int bn, int* out5) {
   cudaFuncAttributes at;
   cudaError_t e;
   switch (bn) {
-    case 128: e = cudaFuncGetAttributes(&at, kpconv_fused_kernel<128>); break;
-    case 64: e = cudaFuncGetAttributes(&at, kpconv_fused_kernel<64>); break;
-    case 32: e = cudaFuncGetAttributes(&at, kpconv_fused_kernel<32>); break;
-    default: e = cudaFuncGetAttributes(&at, kpconv_fused_kernel<16>); break;
+    case 128: e = cudaFuncGetAttributes(&at, kpconv_fused_kernel<128, 1>); break;
+    case 64: e = cudaFuncGetAttributes(&at, kpconv_fused_kernel<64, 1>); break;
+    case 32: e = cudaFuncGetAttributes(&at, kpconv_fused_kernel<32, 1>); break;
+    default: e = cudaFuncGetAttributes(&at, kpconv_fused_kernel<16, 1>); break;
   }
   if (e != cudaSuccess) { set_last_error("cudaFuncGetAttributes", e); return SE3ET_ERR_CUDA; }
   out5[0] = at.numRegs; out5[1] = (int)at.sharedSizeBytes; out5[2] = at.maxThreadsPerBlock;
   out5[3] = (int)at.localSizeBytes; out5[4] = at.maxDynamicSharedSizeBytes;
   if (bn == 32) {  // occupancy probe for the common configuration (HR = 40)
     const int smem = FusedSmem<32>::total(40, FusedSmem<32>::max_wstages(40));
-    cudaFuncSetAttribute(kpconv_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(kpconv_fused_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int nb = -1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kpconv_fused_kernel<32>, kFThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kpconv_fused_kernel<32, 1>, kFThreads, smem);
     out5[3] = nb;
     out5[4] = smem;
     if (e != cudaSuccess) { set_last_error("occupancy", e); return SE3ET_ERR_CUDA; }

@@ -582,8 +582,7 @@ static int launch(const CUtensorMap& tw, Args args, cudaStream_t st) {
   args.wstages = S::max_wstages();
   if (args.wstages < 2) return SE3ET_ERR_UNSUPPORTED;
   const int smem = S::total(args.wstages);
-  SE3ET_CUDA_CHECK(cudaFuncSetAttribute(kpconv_rows_kernel<BN, KH, PPW, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        smem));
+  SE3ET_ENSURE_SMEM((kpconv_rows_kernel<BN, KH, PPW, TP>), smem);
   const int64_t ntiles = ceil_div(args.nq, 16 * PPW);
   dim3 grid((unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs), (unsigned)(args.cout / BN));
   kpconv_rows_kernel<BN, KH, PPW, TP><<<grid, kThreads, smem, st>>>(tw, args);

@@ -197,11 +197,7 @@ extern "C" int se3et_log_optimal_transport(const float* scores, const uint8_t* r
   const int R = (int)num_row + 1, C = (int)num_col + 1;
   const size_t smem = sizeof(float) * ((size_t)R * (C | 1) + 2 * (size_t)R + 2 * (size_t)C);
   if (smem > 227 * 1024) return SE3ET_ERR_UNSUPPORTED;
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    SE3ET_CUDA_CHECK(cudaFuncSetAttribute(log_sinkhorn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  if (smem > 48 * 1024) SE3ET_ENSURE_SMEM(log_sinkhorn_kernel, smem);
   log_sinkhorn_kernel<<<(unsigned)batch, kOtThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       scores, row_masks, col_masks, alpha, (int)num_row, (int)num_col, (int)num_iterations, out);
   SE3ET_LAUNCH_CHECK();

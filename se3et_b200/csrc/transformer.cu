@@ -276,12 +276,7 @@ template <int BN>
 static int launch_embed(const CUtensorMap& td, const CUtensorMap& ta, const float4* idx, int64_t rows, int C,
                         const float* bias_sum, __nv_bfloat16* out, cudaStream_t st) {
   using S = EmbedSmem<BN>;
-  static bool configured = false;
-  if (!configured) {
-    SE3ET_CUDA_CHECK(
-        cudaFuncSetAttribute(geo_embed_project_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    configured = true;
-  }
+  SE3ET_ENSURE_SMEM(geo_embed_project_kernel<BN>, S::kTotal);
   dim3 grid((unsigned)ceil_div(rows, 128), (unsigned)(C / BN));
   geo_embed_project_kernel<BN><<<grid, kEpThreads, S::kTotal, st>>>(td, ta, idx, rows, C, bias_sum, out);
   SE3ET_LAUNCH_CHECK();
@@ -407,11 +402,7 @@ extern "C" int se3et_geo_embed_indices(const float* points, const int64_t* cloud
   if (!points || !cloud_offsets || !emb_offsets || !out_idx4) return SE3ET_ERR_ARG;
   const size_t smem = sizeof(float) * 4 * (size_t)max_cloud;
   if (smem > 200 * 1024) return SE3ET_ERR_UNSUPPORTED;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    SE3ET_CUDA_CHECK(cudaFuncSetAttribute(geo_embed_indices_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  if (smem > 48 * 1024) SE3ET_ENSURE_SMEM(geo_embed_indices_kernel, smem);
   geo_embed_indices_kernel<<<(unsigned)total_points, kEmbThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       points, cloud_offsets, (int)nclouds, emb_offsets, 1.f / sigma_d, 180.f / (sigma_a * 3.14159265358979323846f),
       reinterpret_cast<float4*>(out_idx4));

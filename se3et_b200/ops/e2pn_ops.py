@@ -118,9 +118,12 @@ def upsample_concat(x_bf16, up_idx, y_bf16):
 
 def kpconv_fused_supported(cin, cout, h):
     """Shapes the fused kernel covers (mirrors se3et_kpconv_fused in csrc/kpconv_fused.cu)."""
-    if cin % 16 or cout % 16 or h > 48:
+    if cin % 16 or cout % 16 or h > 96:
         return False
-    return h <= 40 or cout % 128 != 0
+    # neighbour widths above 48 run as two halves of ceil(h / 2) rounded up to 8 rows per ring stage; 48-row stages
+    # leave too little shared memory for the weight ring of a 128-wide tile
+    stage_rows = (h + 7) // 8 * 8 if h <= 48 else ((h + 1) // 2 + 7) // 8 * 8
+    return stage_rows <= 40 or cout % 128 != 0
 
 
 def kpconv_fused(q_pts, s_pts, neighbors, x_bf16, w_fused, kernel_points, kp_extent, gn=None):

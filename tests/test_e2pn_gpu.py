@@ -130,6 +130,39 @@ def test_kpconv_rows_matches_oracle(pyramid, cin, cout, hcols):
         assert rel_err(got, want) < 5e-3
 
 
+@pytest.mark.parametrize("cin,cout,hcols", [(32, 64, 59), (64, 128, 73), (16, 32, 96), (128, 256, 67), (32, 128, 49)])
+def test_kpconv_wide_neighbourhoods_match_oracle(pyramid, cin, cout, hcols):
+    """Neighbour widths above 48 (KITTI-calibrated limits, utils/data.py:212-252): se3et_kpconv_fused runs them as two
+    neighbour halves per (chunk, anchor), the second half's basis fragments parked in tensor memory.  The wide
+    matrices repeat real neighbours (the convolution is a plain sum over columns) and keep shadow entries."""
+    t = oe.octahedral_tables()
+    p1 = torch.from_numpy(pyramid["points"][1])
+    p0 = torch.from_numpy(pyramid["points"][0])
+    for q, s, nb in ((p0, p0, pyramid["neighbors"][0]), (p1, p0, pyramid["subsampling"][0])):
+        nb = torch.from_numpy(nb)
+        while nb.shape[1] < hcols:
+            nb = torch.cat([nb, nb.flip(1)[:, :hcols - nb.shape[1]]], 1)
+        nb = nb.contiguous()
+        conv = M.KPConvInterSO3(15, 6, cin, cout, 0.05, 0.0625, non_sep_conv=True, rot_by_permute=True,
+                                quotient_factor=4)
+        with torch.no_grad():
+            conv.weights.copy_(helpers.seeded_tensor("conv.weights", (6, 6, cin, cout)))
+        x = helpers.seeded_tensor("conv.input", (s.shape[0], 6, cin)).bfloat16().float()
+        w = conv.weights.detach().bfloat16().float()
+        want = oe.kpconv_inter_so3(q, s, nb, x, w, conv.kernel_points.detach(), 0.05, t["kidx"], t["ridx"])
+        conv = conv.to(DEV)
+        assert conv._fused_ok(nb) and not conv._rows_ok(nb, s.shape[0])
+        L = __import__('se3et_b200._lib', fromlist=['x']).lib()
+        L.enabled = True
+        L.reset()
+        got = conv(q.to(DEV), s.to(DEV), nb.to(DEV), x.to(DEV)).cpu()
+        assert L.counts.get("se3et_kpconv_fused", 0) == 1, L.counts
+        L.enabled = False
+        assert torch.allclose(got, want, rtol=2e-2, atol=5e-3 * want.abs().max().item() + 1e-6), \
+            (got - want).abs().max().item()
+        assert rel_err(got, want) < 5e-3
+
+
 @pytest.mark.parametrize("cout", [32, 64])
 def test_kpconv_lifted_input_matches_oracle(pyramid, cout):
     """First backbone layer: the LiftBlockEPN output (an expand over the anchor axis) takes the anchor-constant kernel

@@ -145,6 +145,76 @@ def test_full_size_pair_matches_oracle():
     assert len(got & want) >= 0.85 * len(want), len(got & want) / len(want)
 
 
+def _compare_with_oracle(cfg, model, sd, ref, src, tag):
+    d, fl, r, s, ri, si, sc = oracle_forward(cfg, sd, ref, src)
+    res = model.forward_stacked(torch.from_numpy(np.concatenate([ref, src])).to(DEV), torch.tensor([len(ref), len(src)]))
+    for k in ("points", "neighbors", "subsampling", "upsampling"):
+        for a, b in zip(d[k], res["data_dict"][k]):
+            assert np.array_equal(a, b.cpu().numpy()), k
+    got = set(zip(res["ref_node_corr_indices"][0].tolist(), res["src_node_corr_indices"][0].tolist()))
+    want = set(zip(ri.tolist(), si.tolist()))
+    m = {"cos_f": min_cos(res["feats_f"], fl[0]), "cos_ref_c": min_cos(res["ref_feats_c"], r),
+         "cos_src_c": min_cos(res["src_feats_c"], s), "overlap": len(got & want) / max(1, len(want))}
+    print("PARITY %s level-0 points %d: %s" % (tag, d["points"][0].shape[0], {k: round(v, 5) for k, v in m.items()}))
+    return m
+
+
+def test_headline_config_full_size_pair_matches_oracle():
+    """BASELINE.json configs[1] model at full size: SE3ET-I (init_dim 64) on one full 3DMatch-shaped pair vs the fp32 CPU
+    oracle end to end.  Bars as in DESIGN.md section 2 (measured values are printed with -s)."""
+    cfg, model, sd = build("se3eti.3dmatch")
+    p = synthetic.make_3dmatch_pair(2)
+    assert len(p["ref_points"]) > 10000 and len(p["src_points"]) > 10000
+    m = _compare_with_oracle(cfg, model, sd, p["ref_points"], p["src_points"], "se3eti.3dmatch full size")
+    # measured on B200 (round 2): cos 0.99995 / 0.99993 / 0.99994, overlap 0.980; SURVEY 8c bar: cos >= 0.999
+    assert m["cos_f"] > 0.999 and m["cos_ref_c"] > 0.999 and m["cos_src_c"] > 0.999
+    assert m["overlap"] >= 0.95
+
+
+def test_kitti_30k_points_per_cloud_matches_oracle():
+    """BASELINE.json configs[3] shape: SE3ET-I KITTI (5 stages, voxel 0.3 m) at ~30k points per cloud vs the oracle."""
+    cfg, model, sd = build("se3eti.kitti")
+    p = synthetic.make_kitti_pair(3, target_points=30000)
+    assert min(len(p["ref_points"]), len(p["src_points"])) > 20000
+    m = _compare_with_oracle(cfg, model, sd, p["ref_points"], p["src_points"], "se3eti.kitti 30k")
+    # measured on B200 (round 2): cos 0.99994 / 0.99992 / 0.99992, overlap 0.977
+    assert m["cos_f"] > 0.999 and m["cos_ref_c"] > 0.999 and m["cos_src_c"] > 0.999
+    assert m["overlap"] >= 0.95
+
+
+def test_32_stacked_full_size_pairs_equal_single_pairs():
+    """The benchmarked launch shape: 32 full-size SE3ET-I pairs in one launch sequence (~900k level-0 points).  Every
+    per-pair output must equal what the same pair gives alone: GroupNorm statistics, attention and matching never mix
+    pairs, so only the summation order of the statistics (fp64 atomics) differs."""
+    cfg, model, _ = build("se3eti.3dmatch")
+    pairs = [synthetic.make_3dmatch_pair(100 + i) for i in range(32)]
+    clouds = [(p["ref_points"], p["src_points"]) for p in pairs]
+    lens = torch.tensor([len(c) for pair in clouds for c in pair])
+    pts = torch.from_numpy(np.concatenate([c for pair in clouds for c in pair])).to(DEV)
+    assert pts.shape[0] > 800000
+    res = model.forward_stacked(pts, lens)
+    together = model.forward_pairs(clouds)
+    lc = res["data_dict"]["lengths"][-1].cpu().numpy()
+    ref_off = np.concatenate([[0], np.cumsum(lc[0::2])])
+    src_off = np.concatenate([[0], np.cumsum(lc[1::2])])
+    worst_rel, worst_ov = 0.0, 1.0
+    for i in (0, 7, 19, 31):
+        alone = model.forward_stacked(torch.from_numpy(np.concatenate(clouds[i])).to(DEV),
+                                      torch.tensor([len(clouds[i][0]), len(clouds[i][1])]))
+        for key, off in (("ref_feats_c", ref_off), ("src_feats_c", src_off)):
+            a = alone[key].float()
+            b = res[key][off[i]:off[i + 1]].float()
+            assert a.shape == b.shape
+            worst_rel = max(worst_rel, ((a - b).norm() / a.norm()).item())
+        a = set(zip(alone["ref_node_corr_indices"][0].tolist(), alone["src_node_corr_indices"][0].tolist()))
+        b = set(zip(together[i][0].tolist(), together[i][1].tolist()))
+        worst_ov = min(worst_ov, len(a & b) / len(a))
+    print("PARITY 32 stacked pairs vs alone: worst rel err %.2e, worst top-256 overlap %.4f" % (worst_rel, worst_ov))
+    # measured on B200 (round 2): 7.6e-3 / 0.977 (bf16 activations: a different summation order of the per-pair
+    # statistics moves a few features by one bf16 ulp)
+    assert worst_rel < 1.5e-2 and worst_ov >= 0.95
+
+
 def test_fine_matching_scores_after_forward():
     """forward() (reference data_dict) -> point-to-node partition -> coarse matching -> fine_matching_scores: patch gather,
     batched score GEMM and log-domain optimal transport (model.py:184-205 of the reference), checked against the numpy

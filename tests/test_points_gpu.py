@@ -133,3 +133,19 @@ def test_rejects_bad_arguments():
         ext.grid_subsampling(pts.double(), torch.tensor([4]), pts, 0.1)
     with pytest.raises(RuntimeError, match="contiguous"):
         ext.radius_neighbors(torch.zeros(3, 4, device=DEV).t(), pts, torch.tensor([4]), torch.tensor([4]), 0.1)
+
+
+@pytest.mark.parametrize("name", ["tdm_small", "kitti_small"])
+def test_neighbor_limit_calibration_matches_oracle_and_reference(golden_dir, name):
+    """se3et_b200.calibrate (GPU pyramid + histograms) == oracle == the unmodified reference function's limits."""
+    import os
+    from oracle import calibrate as ocal
+    from se3et_b200.calibrate import calibrate_neighbors_stack_mode
+    from test_oracle_calibrate import clouds_of
+    gold = np.load(os.path.join(golden_dir, "calibrate_ref.npz"))
+    stages, voxel, radius, keep, thresh = gold[name + "_params"]
+    clouds = clouds_of(name)
+    got = calibrate_neighbors_stack_mode(clouds, int(stages), float(voxel), float(radius), float(keep), int(thresh))
+    assert np.array_equal(got, gold[name + "_limits"]), (got, gold[name + "_limits"])
+    assert np.array_equal(got, ocal.calibrate_neighbors_stack_mode(clouds, int(stages), float(voxel), float(radius),
+                                                                   float(keep), int(thresh)))
