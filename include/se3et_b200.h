@@ -142,6 +142,15 @@ int se3et_gemm_set_plain_tile_cap(int bn);
 /* Measurement switch: 0 keeps large bf16-output Linears of se3et_gemm_bf16 on the tile kernels (default: streaming kernel). */
 int se3et_gemm_set_stream_plain(int on);
 
+/* GroupNorm statistics of y = A W^T + bias as a STREAMING pass (UnaryBlockEPN / ResNet shortcut, blocks_epn.py:639-665,
+ * 833-852): persistent tcgen05 GEMM whose epilogue keeps per-thread running sums of y and y^2 across all row tiles of a
+ * pair and reduces them once per pair; y is never stored, A is read once.  Same `stats` layout as
+ * se3et_gemm_bf16_gnstats ([nseg, groups, 2] {sum, sum sq}, zeroed by the call).  Requires n % 32 == 0, k % 8 == 0 and
+ * n / groups a power of two <= 32 or a multiple of 32 (SE3ET_ERR_UNSUPPORTED otherwise). */
+int se3et_linear_gnstats_stream(const void* a, int64_t lda, int64_t m, int64_t k, const void* w_bf16, int64_t ldw,
+                                int64_t n, const float* bias, const int64_t* seg_offsets, int64_t nseg, int64_t groups,
+                                int64_t rows_per_point, double* stats, se3et_stream_t stream);
+
 /* GroupNorm statistics of y = A W^T + bias WITHOUT forming y (UnaryBlockEPN, blocks_epn.py:639-665, when the Linear
  * widens): one pass over A accumulates per pair the Gram matrix A^T A and the column sums (mma.sync, fp32 per CTA, fp64
  * across CTAs), then sum y_j = w_j.s + R b_j and sum y_j^2 = w_j^T G w_j + 2 b_j w_j.s + R b_j^2 per channel in fp64.

@@ -15,7 +15,7 @@ namespace se3et {
 __constant__ int c_ridx[6][6] = {{0, 3, 3, 3, 3, 5}, {1, 0, 4, 5, 2, 1}, {2, 2, 0, 4, 5, 4},
                                  {3, 5, 2, 0, 4, 3}, {4, 4, 5, 2, 0, 2}, {5, 1, 1, 1, 1, 0}};
 
-constexpr int kMaxH = 64;    // neighbour columns supported by the gather kernel
+constexpr int kMaxH = 96;    // neighbour columns supported by the gather / pooling kernels
 
 int kpconv_gather_mma(const float* q_pts, const float* s_pts, const int64_t* neighbors, int64_t nq, int64_t ns, int h,
                       const __nv_bfloat16* x, int cin, const float* kp, float inv_extent, __nv_bfloat16* out, int kpad,

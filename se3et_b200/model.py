@@ -16,6 +16,7 @@ from . import _lib
 from .modules.e2pn import E2PN
 from .modules.transformer import GeometricTransformer, SuperPointMatching
 from .ops import transformer_ops as T
+from .modules.registration import LocalGlobalRegistration
 from .modules.sinkhorn import LearnableLogOptimalTransport
 from .ops.gemm import bmm_bf16
 from .ops.partition_ops import point_to_node_partition_stacked
@@ -72,6 +73,10 @@ def make_cfg(variant='se3eti.3dmatch'):
     # config.py:177-178 (3DMatch) / se3eti.kitti/config.py:180-181
     c.model = Cfg(num_points_in_patch=128 if stages == 5 else 64, num_sinkhorn_iterations=100)
     c.coarse_matching = Cfg(num_targets=128, overlap_threshold=0.1, num_correspondences=256, dual_normalization=True)
+    # config.py:208-217 (3DMatch) / se3eti.kitti/config.py:212-221
+    c.fine_matching = Cfg(topk=2 if stages == 5 else 3, acceptance_radius=0.6 if stages == 5 else 0.1, mutual=True,
+                          confidence_threshold=0.05, use_dustbin=False, use_global_score=False,
+                          correspondence_threshold=3, correspondence_limit=None, num_refinement_steps=5)
     c.neighbor_limits = list(limits)  # demo.py:52 for 3DMatch; KITTI limits are calibrated per dataset (data.py:212-252)
     return c
 
@@ -93,6 +98,12 @@ class GeoTransformer(nn.Module):
         self.coarse_matching = SuperPointMatching(cfg.coarse_matching.num_correspondences,
                                                   cfg.coarse_matching.dual_normalization)
         self.optimal_transport = LearnableLogOptimalTransport(cfg.model.num_sinkhorn_iterations)  # model.py:76
+        f = cfg.fine_matching
+        self.fine_matching = LocalGlobalRegistration(                                              # model.py:63-73
+            f.topk, f.acceptance_radius, mutual=f.mutual, confidence_threshold=f.confidence_threshold,
+            use_dustbin=f.use_dustbin, use_global_score=f.use_global_score,
+            correspondence_threshold=f.correspondence_threshold, correspondence_limit=f.correspondence_limit,
+            num_refinement_steps=f.num_refinement_steps)
 
     @torch.no_grad()
     def fine_matching_scores(self, out):
@@ -113,6 +124,69 @@ class GeoTransformer(nn.Module):
                                     out['src_node_knn_masks'].index_select(0, si))
         out['matching_scores'] = ms
         return ms
+
+    @torch.no_grad()
+    def register(self, out, data_dict):
+        """Steps 7.2-9 of the reference forward (experiments/se3eti.3dmatch/model.py:175-224) after forward(): optimal
+        transport on the patch pairs, LocalGlobalRegistration.  Adds matching_scores, ref_corr_points, src_corr_points,
+        corr_scores and estimated_transform (4, 4) to `out`."""
+        ms = self.fine_matching_scores(out)
+        points_f = data_dict['points'][1]
+        ref_length_f = int(data_dict['lengths'][1][0])
+        ri, si = out['ref_node_corr_indices'], out['src_node_corr_indices']
+        knn_pts = []
+        for pts, knn, idx in ((points_f[:ref_length_f], out['ref_node_knn_indices'], ri),
+                              (points_f[ref_length_f:], out['src_node_knn_indices'], si)):
+            padded = torch.cat([pts, torch.zeros_like(pts[:1])], dim=0)            # model.py:117-118 (shadow point)
+            k_idx = knn.index_select(0, idx)
+            knn_pts.append(padded.index_select(0, k_idx.reshape(-1)).view(k_idx.shape[0], k_idx.shape[1], 3))
+        rp, sp, sc, t = self.fine_matching(knn_pts[0], knn_pts[1], out['ref_node_knn_masks'].index_select(0, ri),
+                                           out['src_node_knn_masks'].index_select(0, si), ms, out['node_corr_scores'])
+        out['ref_corr_points'], out['src_corr_points'], out['corr_scores'], out['estimated_transform'] = rp, sp, sc, t
+        return out
+
+    @torch.no_grad()
+    def register_stacked(self, res):
+        """Fine stage for the P pairs of forward_stacked(): patch gather + batched score GEMM + optimal transport +
+        LocalGlobalRegistration for all P x num_correspondences patch pairs in one launch sequence.
+        Adds 'estimated_transforms' (P, 4, 4), 'ref_corr_points' / 'src_corr_points' / 'corr_scores' (stacked) and
+        'corr_offsets' (P + 1,) to `res`."""
+        dd = res['data_dict']
+        dev = res['feats_f'].device
+        num_pairs = len(res['ref_sizes'])
+        k = self.cfg.model.num_points_in_patch
+        points_f, feats_f = dd['points'][1], res['feats_f']
+        len_f = dd['lengths'][1].to(dev)
+        len_c = dd['lengths'][-1].to(dev)
+        start_f = torch.cumsum(len_f, 0) - len_f                    # first fine point of every cloud (backbone order)
+        start_c = torch.cumsum(len_c, 0) - len_c
+        cnt = res['num_corr'].to(torch.int64)                       # correspondences per pair
+        ncor = res['ref_node_corr_indices'].shape[1]
+        slot = torch.arange(ncor, device=dev)[None, :].expand(num_pairs, -1)
+        live = slot < cnt[:, None]
+        pair_id = torch.arange(num_pairs, device=dev)[:, None].expand(-1, ncor)[live]
+        knn, knn_masks = res['node_knn_indices'], res['node_knn_masks']       # cloud-local point ids, backbone order
+        feats = feats_f.to(torch.bfloat16)
+        zf = torch.zeros_like(feats[:1])
+        zp = torch.zeros_like(points_f[:1])
+        g_feats, g_pts, g_masks = [], [], []
+        for side, corr in ((0, res['ref_node_corr_indices']), (1, res['src_node_corr_indices'])):
+            cloud = 2 * pair_id + side
+            node = start_c[cloud] + corr[live]                      # node row in backbone order
+            k_idx = knn.index_select(0, node)                       # (B, K) cloud-local, shadow = cloud length
+            m = knn_masks.index_select(0, node)
+            rows = torch.where(m, k_idx + start_f[cloud][:, None], torch.full_like(k_idx, feats.shape[0]))
+            g_feats.append(torch.cat([feats, zf]).index_select(0, rows.reshape(-1)).view(rows.shape[0], k, -1).contiguous())
+            g_pts.append(torch.cat([points_f, zp]).index_select(0, rows.reshape(-1)).view(rows.shape[0], k, 3))
+            g_masks.append(m)
+        c = g_feats[0].shape[-1]
+        scores, _ = bmm_bf16(g_feats[0], g_feats[1], alpha=1.0 / c ** 0.5)
+        ms = self.optimal_transport(scores, g_masks[0], g_masks[1])
+        patch_off = torch.cat([cnt.new_zeros(1), torch.cumsum(cnt, 0)])
+        rp, sp, sc, coff, tr = self.fine_matching.forward_pairs(g_pts[0], g_pts[1], g_masks[0], g_masks[1], ms, patch_off)
+        res.update(matching_scores=ms, ref_corr_points=rp, src_corr_points=sp, corr_scores=sc, corr_offsets=coff,
+                   estimated_transforms=tr)
+        return res
 
     # ---- one pair, reference data_dict -------------------------------------------------------------------------
     @torch.no_grad()

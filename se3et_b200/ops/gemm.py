@@ -111,8 +111,13 @@ def linear_gn_stats(a, w, bias, groups, seg_off, rows_per_point, store=True):
     _check_ab(a, w, bias)
     assert seg_off.dtype == torch.int64
     nseg = seg_off.numel() - 1
+    # measured on B200 (scratch/bench_stats.py): widening Linears with a small K are fastest from the Gram matrix of the
+    # input (one read of A whatever N is), everything else on the streaming tcgen05 pass (2x the GEMM-epilogue pass for
+    # narrowing Linears: 3.4-5.9 TB/s)
     if not store and gram_stats_supported(n, k) and a.stride(0) % 8 == 0:
         return None, linear_gn_stats_gram(a, w, bias, groups, seg_off, rows_per_point)
+    if not store and STATS_MODE['stream'] and stream_stats_supported(n, k, groups) and a.stride(0) % 8 == 0:
+        return None, linear_gn_stats_stream(a, w, bias, groups, seg_off, rows_per_point)
     y = torch.empty((m, n), dtype=torch.float32, device=a.device) if store else None
     stats = torch.empty((nseg, groups, 2), dtype=torch.float64, device=a.device)
     _lib.check(_lib.lib().se3et_gemm_bf16_gnstats(
@@ -181,6 +186,29 @@ def dual_apply_supported(n, k1, k2):
 
 
 _GRAM = {'on': True}
+
+
+# A/B switch (tests, measurements): the streaming statistics pass is the product path
+STATS_MODE = {'stream': True}
+
+
+def stream_stats_supported(n, k, groups):
+    cpg = n // groups
+    return n % 32 == 0 and k % 8 == 0 and n % groups == 0 and (((cpg & (cpg - 1)) == 0 and cpg <= 32) or cpg % 32 == 0)
+
+
+def linear_gn_stats_stream(a, w, bias, groups, seg_off, rows_per_point):
+    """GroupNorm statistics of a @ w.T + bias by the streaming pass (se3et_linear_gnstats_stream): y is never formed."""
+    _check_ab(a, w, bias)
+    m, k = a.shape
+    n = w.shape[0]
+    nseg = seg_off.numel() - 1
+    stats = torch.empty((nseg, groups, 2), dtype=torch.float64, device=a.device)
+    _lib.check(_lib.lib().se3et_linear_gnstats_stream(
+        _lib.ptr(a), _lib.i64(a.stride(0) if m > 1 else k), _lib.i64(m), _lib.i64(k), _lib.ptr(w),
+        _lib.i64(w.stride(0) if n > 1 else k), _lib.i64(n), _lib.ptr(bias), _lib.ptr(seg_off), _lib.i64(nseg),
+        _lib.i64(groups), _lib.i64(rows_per_point), _lib.ptr(stats), _lib.stream_ptr()), "linear_gnstats_stream")
+    return stats
 
 
 def gram_stats_supported(n, k):

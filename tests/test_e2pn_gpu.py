@@ -375,11 +375,47 @@ def test_linear_gnstats_gram(n_out, groups, k, rpp):
     assert float(((got[:, :, 1] - want[:, :, 1]).abs() / scale).max()) < 2e-5
     assert float(((got[:, :, 0] - want[:, :, 0]).abs() / scale).max()) < 2e-5
     G._GRAM['on'] = False
+    G.STATS_MODE['stream'] = False
     try:
         _, ep = G.linear_gn_stats(ad, wd, bd, groups, seg, rpp, store=False)
     finally:
         G._GRAM['on'] = True
+        G.STATS_MODE['stream'] = True
     assert float(((got - ep.cpu()).abs() / scale.unsqueeze(-1)).max()) < 1e-4
+
+
+@pytest.mark.parametrize("n_out,groups,k,rpp", [(32, 32, 64, 6), (32, 32, 128, 6), (64, 32, 256, 6), (128, 32, 32, 6),
+                                                 (256, 32, 1024, 6), (512, 32, 128, 1), (2048, 32, 64, 6),
+                                                 (64, 16, 40, 1)])
+def test_linear_gnstats_stream(n_out, groups, k, rpp):
+    """se3et_linear_gnstats_stream (persistent tcgen05 GEMM, per-thread running sums across the row tiles of a pair)
+    against fp64 torch: narrowing and widening Linears, a half-filled column tile (n = 32), groups wider than a warp's
+    columns, empty pairs, pairs shorter than a tile, pair ends inside tiles and inside warps."""
+    from se3et_b200.ops import gemm as G
+    g = torch.Generator().manual_seed(n_out + k)
+    pts = [150, 0, 333, 5, 4100, 1, 700]
+    seg = torch.tensor(np.concatenate([[0], np.cumsum(pts)]), dtype=torch.int64, device=DEV)
+    rows = rpp * sum(pts)
+    a = (torch.randn(rows, k, generator=g) + 0.3).to(torch.bfloat16)
+    w = (torch.randn(n_out, k, generator=g) / k ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(n_out, generator=g)
+    y = a.double() @ w.double().t() + bias.double()
+    want = torch.zeros(len(pts), groups, 2, dtype=torch.float64)
+    for i in range(len(pts)):
+        blk = y[rpp * int(seg[i]):rpp * int(seg[i + 1])].view(-1, groups, n_out // groups)
+        want[i, :, 0] = blk.sum(dim=(0, 2))
+        want[i, :, 1] = (blk * blk).sum(dim=(0, 2))
+    assert G.stream_stats_supported(n_out, k, groups)
+    got = G.linear_gn_stats_stream(a.to(DEV), w.to(DEV), bias.to(DEV), groups, seg, rpp).cpu()
+    scale = want[:, :, 1].abs().max(dim=1, keepdim=True)[0].clamp_min(1.0)
+    assert float(((got[:, :, 1] - want[:, :, 1]).abs() / scale).max()) < 2e-5
+    assert float(((got[:, :, 0] - want[:, :, 0]).abs() / scale).max()) < 2e-5
+    # and without a bias
+    got0 = G.linear_gn_stats_stream(a.to(DEV), w.to(DEV), None, groups, seg, rpp).cpu()
+    y0 = y - bias.double()
+    for i in (2, 4):
+        blk = y0[rpp * int(seg[i]):rpp * int(seg[i + 1])].view(-1, groups, n_out // groups)
+        assert float(((got0[i, :, 1] - (blk * blk).sum(dim=(0, 2))).abs() / scale[i]).max()) < 2e-5
 
 
 @pytest.mark.parametrize("c,G,rpp", [(32, 32, 6), (128, 32, 6), (1024, 32, 6), (256, 32, 1), (48, 16, 6), (2048, 32, 6)])

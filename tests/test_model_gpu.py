@@ -253,3 +253,55 @@ def test_fine_matching_scores_after_forward():
     live = want > -1e11
     assert np.array_equal(live, ms > -1e11)
     assert np.abs(ms[live] - want[live]).max() < 2e-3
+
+
+def test_registration_after_forward_matches_oracle():
+    """forward() -> register(): optimal transport + LocalGlobalRegistration (model.py:175-224 of the reference) on the GPU
+    against the numpy oracle applied to the same patch points / masks / optimal-transport scores; then the same pair
+    inside a three-pair launch sequence (register_stacked) must give the same correspondences and transform."""
+    from oracle import registration as oreg
+    from se3et_b200.precompute import precompute_data_stack_mode
+    cfg, model, sd = build("se3eti2.3dmatch")
+    pairs = [synthetic.make_3dmatch_pair(i, crop=0.9) for i in (13, 3, 5)]
+    p = pairs[0]
+    pts = torch.from_numpy(np.concatenate([p["ref_points"], p["src_points"]])).to(DEV)
+    lens = torch.tensor([len(p["ref_points"]), len(p["src_points"])], device=DEV)
+    b = cfg.backbone
+    dd = precompute_data_stack_mode(pts, lens, b.num_stages, b.init_voxel_size, b.init_radius, cfg.neighbor_limits)
+    dd['features'] = torch.ones((pts.shape[0], 1), dtype=torch.float32, device=DEV)
+    out = model.register(model(dd), dd)
+    T = out['estimated_transform'].cpu().numpy()
+    assert T.shape == (4, 4) and abs(np.linalg.det(T[:3, :3]) - 1) < 1e-4
+    # oracle on the GPU's own inputs of the stage
+    ri, si = out['ref_node_corr_indices'], out['src_node_corr_indices']
+    nf = int(dd['lengths'][1][0])
+    pf = dd['points'][1]
+    def patch(points, knn, idx):
+        padded = torch.cat([points, torch.zeros_like(points[:1])])
+        return padded[knn[idx]].cpu().numpy()
+    rp = patch(pf[:nf], out['ref_node_knn_indices'], ri)
+    sp = patch(pf[nf:], out['src_node_knn_indices'], si)
+    rm = out['ref_node_knn_masks'][ri].cpu().numpy()
+    sm = out['src_node_knn_masks'][si].cpu().numpy()
+    f = cfg.fine_matching
+    w_rp, w_sp, w_sc, w_T = oreg.local_global_registration(rp, sp, rm, sm, out['matching_scores'][:, :-1, :-1].cpu().numpy(),
+                                                           k=f.topk, acceptance_radius=f.acceptance_radius)
+    assert np.array_equal(out['ref_corr_points'].cpu().numpy(), w_rp)
+    assert np.array_equal(out['src_corr_points'].cpu().numpy(), w_sp)
+    assert np.allclose(out['corr_scores'].cpu().numpy(), w_sc, rtol=1e-5)
+    assert np.abs(T - w_T).max() < 1e-3, np.abs(T - w_T).max()
+    # stacked: three pairs, per-pair outputs
+    clouds = [(q["ref_points"], q["src_points"]) for q in pairs]
+    lens3 = torch.tensor([len(c) for pair in clouds for c in pair])
+    pts3 = torch.from_numpy(np.concatenate([c for pair in clouds for c in pair])).to(DEV)
+    res = model.register_stacked(model.forward_stacked(pts3, lens3))
+    assert res['estimated_transforms'].shape == (3, 4, 4)
+    coff = res['corr_offsets'].cpu().numpy()
+    n0 = coff[1] - coff[0]
+    # the pair alone (pair mode trims neighbour columns, stacked mode pads them: same maths, bf16 rounding order differs)
+    assert abs(n0 - len(w_sc)) <= 0.15 * len(w_sc) + 5
+    for i in range(3):
+        Ti = res['estimated_transforms'][i].cpu().numpy()
+        assert abs(np.linalg.det(Ti[:3, :3]) - 1) < 1e-4 and np.isfinite(Ti).all()
+    print("PARITY registration: %d correspondences, |T - oracle| max %.2e, stacked pair-0 count %d" % (
+        len(w_sc), np.abs(T - w_T).max(), n0))
