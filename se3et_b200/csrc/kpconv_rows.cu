@@ -114,6 +114,48 @@ __device__ __forceinline__ void basis_weights_fast(float dx, float dy, float dz,
   }
 }
 
+// ---- thread-block cluster helpers (CL > 1: the CTAs of a cluster share one tile of points, each accumulates its own
+// BN output columns and produces 1 / CL of the operand rows, which it copies to its peers through distributed shared
+// memory) ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t num_clusters_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr_cta, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr_cta), "r"(rank));
+  return r;
+}
+// local shared memory -> a peer CTA's shared memory, completing on the PEER's mbarrier (both cluster addresses)
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t mbar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(mbar_cluster)
+               : "memory");
+}
+// arrive on the same-offset mbarrier of every CTA in `mask` when all previously issued MMAs of this thread completed
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   tc::smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 // (r, kc) -> basis row, t = r * 6 + kc
 struct BetaTab {
   int8_t v[36];
@@ -157,10 +199,10 @@ struct Smem {
   static int total(int wstages) { return kWOff + wstages * kWStage + 1024; }
 };
 
-// BN: output columns per CTA; KH: neighbour columns / 8 rounded up (4, 5, 6); PPW: points per producer warp;
-// TP: points per warp whose basis fragments live in tensor memory
-template <int BN, int KH, int PPW, int TP>
-__global__ void __launch_bounds__(kThreads, 1)
+// BN: output columns per CTA; KH: neighbour columns / 8 rounded up (4, 5, 6); PPW: points per producer warp (of this
+// CTA); TP: points per warp whose basis fragments live in tensor memory; CL: CTAs per cluster sharing a tile (1: none)
+template <int BN, int KH, int PPW, int TP, int CL>
+__global__ void __launch_bounds__(kThreads + 32, 1)
 kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
   using S = Smem<BN, KH>;
   constexpr int FR = 2 * KH;              // fragment registers per point
@@ -169,7 +211,8 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
   constexpr int kAccCols = 6 * BN;
   static_assert(kAccCols + 4 * kStash <= 512, "tensor memory over-subscribed");
   static_assert(kW16Row * 16 <= kXStages * S::kXStage, "W16 scratch must fit the gather ring");
-  constexpr int kTilePts = 16 * PPW;
+  constexpr int kTilePts = 16 * PPW * CL;
+  static_assert(kTilePts <= 128 && (CL == 1 || kTilePts == 128), "a cluster shares one full 128-row tile");
   constexpr int kHR = S::kHR;
   constexpr int kXStage = S::kXStage;
   constexpr BetaTab kBeta = make_beta_tab();
@@ -182,13 +225,17 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
   uint64_t* b_empty = b_full + 2;                                     // [2]
   uint64_t* tmem_full = b_full + 4;
   uint64_t* tmem_empty = b_full + 5;
-  uint64_t* w_full = b_full + 6;
+  uint64_t* p_done = b_full + 6;                                      // [2] (CL > 1: this CTA's rows are stored)
+  uint64_t* w_full = b_full + 8;
   uint64_t* w_empty = w_full + kWMaxStages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_empty + kWMaxStages);
   float4* sh_kp = reinterpret_cast<float4*>(smem + S::kKpOff);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.y * BN;
+  const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
+  const int n0 = (CL > 1 ? (int)rank : (int)blockIdx.y) * BN;
+  const int64_t tile0 = CL > 1 ? (int64_t)cluster_id_x() : (int64_t)blockIdx.x;
+  const int64_t tile_stride = CL > 1 ? (int64_t)num_clusters_x() : (int64_t)gridDim.x;
   const int64_t ntiles = (args.nq + kTilePts - 1) / kTilePts;
   const int nsteps = args.cin / kChunk * kA;  // (chunk, a), a fastest
   const int wstages = args.wstages;
@@ -199,8 +246,9 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&tma_w);
     for (int s = 0; s < 2; ++s) {
-      tc::mbar_init(&b_full[s], kProdWarps);
-      tc::mbar_init(&b_empty[s], 1);
+      tc::mbar_init(&b_full[s], CL > 1 ? 1 : kProdWarps);
+      tc::mbar_init(&b_empty[s], CL);
+      tc::mbar_init(&p_done[s], kProdWarps);
     }
     for (int s = 0; s < wstages; ++s) {
       tc::mbar_init(&w_full[s], 1);
@@ -210,14 +258,14 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
     tc::mbar_init(tmem_empty, kProdWarps);
     tc::mbar_fence_init();
   }
-  if (PPW < 8) {
-    // rows 16 PPW .. 127 of the operand are never produced: keep them finite
-    for (int i = threadIdx.x; i < 2 * kBBuf / 16; i += kThreads) reinterpret_cast<uint4*>(b_tile)[i] = make_uint4(0, 0, 0, 0);
+  if (kTilePts < 128) {
+    // rows kTilePts .. 127 of the operand are never produced: keep them finite
+    for (int i = threadIdx.x; i < 2 * kBBuf / 16; i += blockDim.x) reinterpret_cast<uint4*>(b_tile)[i] = make_uint4(0, 0, 0, 0);
   }
   if (warp == kProdWarps) tc::tmem_alloc<512>(tmem_ptr);
   tc::fence_proxy_async_smem();
   tc::tcgen05_fence_before_sync();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // peers' mbarriers are initialised before anything remote
   tc::tcgen05_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -255,7 +303,7 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
       const int beta = (lane & 7) + 8 * ((lane >> 3) & 1), half = lane >> 4;
       const int sub = beta >> 2, slot = beta & 3;
       const int chunk = slot * 2 + (half ^ (sub & 1));
-      st_off = smem_addr(b_tile) + sub * kSubTile + warp * 128 + ((chunk ^ (warp & 7)) << 4);
+      st_off = smem_addr(b_tile) + sub * kSubTile + ((int)rank * PPW * 16 + warp) * 128 + ((chunk ^ (warp & 7)) << 4);
     }
     const uint32_t stash = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kAccCols + (warp >> 2) * kStash);
 
@@ -267,7 +315,7 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
     struct Ids { int j0, j1; };
     struct Rel { float x0, y0, z0, x1, y1, z1; };
     auto load_ids = [&](int64_t tile, int i) -> Ids {
-      const int64_t p = tile * kTilePts + i * 16 + warp;
+      const int64_t p = tile * kTilePts + ((int)rank * PPW + i) * 16 + warp;
       Ids r{-1, -1};
       if (p < args.nq) {
         const int64_t* row = args.idx + p * H;
@@ -277,7 +325,7 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
       return r;
     };
     auto load_rel = [&](int64_t tile, int i, Ids id) -> Rel {
-      int64_t p = tile * kTilePts + i * 16 + warp;
+      int64_t p = tile * kTilePts + ((int)rank * PPW + i) * 16 + warp;
       if (p >= args.nq) p = 0;
       const float qx = args.q_pts[3 * p], qy = args.q_pts[3 * p + 1], qz = args.q_pts[3 * p + 2];
       Rel r{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -321,7 +369,7 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
       // gather offsets: the neighbour of piece u is lane / 2 + 16 u
 #pragma unroll
       for (int i = 0; i < PPW; ++i) {
-        const int64_t p = tile * kTilePts + i * 16 + warp;
+        const int64_t p = tile * kTilePts + ((int)rank * PPW + i) * 16 + warp;
         const bool pvalid = p < args.nq;
         const int64_t pc = pvalid ? p : 0;
         int64_t j0 = (pvalid && lane < H) ? args.idx[pc * H + lane] : -1;
@@ -387,9 +435,9 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
 
     uint32_t gstep = 0;   // steps produced so far (all tiles)
     // rotated tile loop (one call site per phase): production(t), setup(t + 1), epilogue(t)
-    for (int64_t tile = (int64_t)blockIdx.x - gridDim.x, titer = -1;; tile += gridDim.x, ++titer) {
+    for (int64_t tile = tile0 - tile_stride, titer = -1;; tile += tile_stride, ++titer) {
       const bool have = titer >= 0;
-      const bool have_next = tile + gridDim.x < ntiles;
+      const bool have_next = tile + tile_stride < ntiles;
       if (have) {
       // items (step, point) in order; the ring runs two items ahead
       {
@@ -474,16 +522,16 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
 #endif
           __syncwarp();  // every lane is done with this ring stage
         }
-        tc::fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async proxy
+        tc::fence_proxy_async_smem();  // generic-proxy stores -> visible to the async proxy (tensor core, bulk copies)
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&b_full[buf]);
+        if (lane == 0) tc::mbar_arrive(CL > 1 ? &p_done[buf] : &b_full[buf]);
       }
       }
         cp_async_wait<0>();
         __syncwarp();
       }
       // the next tile's basis weights are built under this tile's last MMAs
-      if (have_next) setup(tile + gridDim.x);
+      if (have_next) setup(tile + tile_stride);
       if (have) {
         // ---- epilogue: TMEM lane quadrant warp % 4 (rows = points), column group warp / 4 -------------------
         tc::mbar_wait_long(tmem_full, (uint32_t)titer & 1u);
@@ -519,7 +567,7 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
       constexpr uint32_t idesc = tc::umma_idesc_bf16(128, BN);
       uint32_t gstep = 0, titer = 0, ws = 0, wphase = 0;
       const uint32_t b_s = tc::smem_u32(b_tile), w_s = tc::smem_u32(w_tile);
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++titer) {
+      for (int64_t tile = tile0; tile < ntiles; tile += tile_stride, ++titer) {
         tc::mbar_wait_long(tmem_empty, (titer & 1) ^ 1);  // the epilogue has drained the previous tile's accumulators
         tc::tcgen05_fence_after_sync();
         for (int step = 0; step < nsteps; ++step, ++gstep) {
@@ -546,16 +594,18 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
             tc::umma_commit(&w_empty[ws]);
             if (++ws == (uint32_t)wstages) { ws = 0; wphase ^= 1; }
           }
-          tc::umma_commit(&b_empty[buf]);
+          // every CTA of the cluster writes rows into this buffer: all of them learn that it is free again
+          if (CL > 1) umma_commit_multicast(&b_empty[buf], (uint16_t)((1u << CL) - 1u));
+          else tc::umma_commit(&b_empty[buf]);
         }
         tc::umma_commit(tmem_full);
       }
     }
-  } else {
+  } else if (warp == kProdWarps + 1) {
     // =========================================== weight TMA ==================================================
     if (lane == 0) {
       uint32_t ws = 0, wphase = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int64_t tile = tile0; tile < ntiles; tile += tile_stride) {
         for (int kbg = 0; kbg < nsteps * 9; ++kbg) {
           tc::mbar_wait_long(&w_empty[ws], wphase ^ 1);
           tc::mbar_arrive_expect_tx(&w_full[ws], BN * 128);
@@ -564,9 +614,35 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
         }
       }
     }
+  } else if (CL > 1) {
+    // ============================== operand exchange (CL > 1): this CTA's rows -> the peers ==========================
+    if (lane == 0) {
+      constexpr uint32_t kBlk = PPW * 16 * 128;                 // this CTA's rows of one sub-tile
+      const uint32_t b_s = tc::smem_u32(b_tile) + rank * kBlk;
+      uint32_t gstep = 0;
+      for (int64_t tile = tile0; tile < ntiles; tile += tile_stride) {
+        for (int step = 0; step < nsteps; ++step, ++gstep) {
+          const uint32_t buf = gstep & 1u;
+          tc::mbar_wait_long(&p_done[buf], (gstep >> 1) & 1u);  // the 16 producer warps stored (and fenced) their rows
+          // the one arrival of this CTA's b_full phase, expecting the peers' rows
+          tc::mbar_arrive_expect_tx(&b_full[buf], (CL - 1) * 4 * kBlk);
+          const uint32_t bar = tc::smem_u32(&b_full[buf]);
+#pragma unroll
+          for (int d = 1; d < CL; ++d) {
+            const uint32_t peer = (rank + d) % CL;
+            const uint32_t bar_peer = map_to_cta(bar, peer);
+#pragma unroll
+            for (int sub = 0; sub < 4; ++sub) {
+              const uint32_t src = b_s + buf * kBBuf + sub * kSubTile;
+              dsmem_bulk_copy(map_to_cta(src, peer), src, kBlk, bar_peer);
+            }
+          }
+        }
+      }
+    }
   }
   tc::tcgen05_fence_before_sync();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();   // no CTA leaves while a peer may still write to it
   if (warp == kProdWarps) tc::tmem_dealloc<512>(tmem_base);
 }
 
@@ -576,17 +652,36 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t 
 
 namespace rows {
 
-template <int BN, int KH, int PPW, int TP>
+template <int BN, int KH, int PPW, int TP, int CL>
 static int launch(const CUtensorMap& tw, Args args, cudaStream_t st) {
   using S = Smem<BN, KH>;
   args.wstages = S::max_wstages();
   if (args.wstages < 2) return SE3ET_ERR_UNSUPPORTED;
   const int smem = S::total(args.wstages);
-  SE3ET_ENSURE_SMEM((kpconv_rows_kernel<BN, KH, PPW, TP>), smem);
-  const int64_t ntiles = ceil_div(args.nq, 16 * PPW);
-  dim3 grid((unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs), (unsigned)(args.cout / BN));
-  kpconv_rows_kernel<BN, KH, PPW, TP><<<grid, kThreads, smem, st>>>(tw, args);
-  SE3ET_LAUNCH_CHECK();
+  auto kernel = kpconv_rows_kernel<BN, KH, PPW, TP, CL>;
+  SE3ET_ENSURE_SMEM(kernel, smem);
+  const int64_t ntiles = ceil_div(args.nq, 16 * PPW * CL);
+  if (CL == 1) {
+    dim3 grid((unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs), (unsigned)(args.cout / BN));
+    kernel<<<grid, kThreads + 32, smem, st>>>(tw, args);
+    SE3ET_LAUNCH_CHECK();
+    return SE3ET_OK;
+  }
+  // one cluster of CL CTAs per tile of 128 points; CTA rank = column block of BN outputs (cout == CL * BN)
+  const int64_t max_clusters = kNumSMs / CL;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)((ntiles < max_clusters ? ntiles : max_clusters) * CL), 1, 1);
+  cfg.blockDim = dim3(kThreads + 32, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SE3ET_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tw, args));
   return SE3ET_OK;
 }
 
@@ -623,21 +718,39 @@ extern "C" int se3et_kpconv_rows(const float* q_pts, const float* s_pts, const i
   CUtensorMap tw;
   int rc = make_tmap_bf16_2d(&tw, w_rows_bf16, cout, 216 * cin, 216 * cin, bn);
   if (rc) return rc;
+  // cout 128 / 256: clusters of 2 / 4 CTAs share a tile of 128 points (each CTA 64 output columns and 1 / CL of the
+  // operand rows, exchanged through distributed shared memory).  Other widths: one CTA per (tile, column block).
 #ifdef SE3ET_ROWS_DEV
   if (kh != 5) return SE3ET_ERR_UNSUPPORTED;
-  return bn == 32 ? rows::launch<32, 5, 8, 8>(tw, a, st) : rows::launch<64, 5, 6, 3>(tw, a, st);
+  if (cout == 128) return rows::launch<64, 5, 4, 3, 2>(tw, a, st);
+  if (cout == 256) return rows::launch<64, 5, 2, 2, 4>(tw, a, st);
+  return bn == 32 ? rows::launch<32, 5, 8, 8, 1>(tw, a, st) : rows::launch<64, 5, 6, 3, 1>(tw, a, st);
 #else
+  if (cout == 128 || cout == 256) {
+    if (cout == 128) {
+      switch (kh) {
+        case 4: return rows::launch<64, 4, 4, 4, 2>(tw, a, st);
+        case 5: return rows::launch<64, 5, 4, 3, 2>(tw, a, st);
+        default: return rows::launch<64, 6, 4, 2, 2>(tw, a, st);
+      }
+    }
+    switch (kh) {
+      case 4: return rows::launch<64, 4, 2, 2, 4>(tw, a, st);
+      case 5: return rows::launch<64, 5, 2, 2, 4>(tw, a, st);
+      default: return rows::launch<64, 6, 2, 2, 4>(tw, a, st);
+    }
+  }
   if (bn == 32) {
     switch (kh) {
-      case 4: return rows::launch<32, 4, 8, 8>(tw, a, st);
-      case 5: return rows::launch<32, 5, 8, 8>(tw, a, st);
-      default: return rows::launch<32, 6, 8, 6>(tw, a, st);
+      case 4: return rows::launch<32, 4, 8, 8, 1>(tw, a, st);
+      case 5: return rows::launch<32, 5, 8, 8, 1>(tw, a, st);
+      default: return rows::launch<32, 6, 8, 6, 1>(tw, a, st);
     }
   }
   switch (kh) {
-    case 4: return rows::launch<64, 4, 6, 4>(tw, a, st);
-    case 5: return rows::launch<64, 5, 6, 3>(tw, a, st);
-    default: return rows::launch<64, 6, 6, 2>(tw, a, st);
+    case 4: return rows::launch<64, 4, 6, 4, 1>(tw, a, st);
+    case 5: return rows::launch<64, 5, 6, 3, 1>(tw, a, st);
+    default: return rows::launch<64, 6, 6, 2, 1>(tw, a, st);
   }
 #endif
 }

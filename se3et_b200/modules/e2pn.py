@@ -26,7 +26,7 @@ from . import octahedral
 # 'cin1_kernel': the CUDA-core first-layer kernel (csrc/kpconv.cu) measures slower than gather + GEMM on B200
 # (9.6 vs 8.4 ms per 64 pairs), so it is off by default and only exercised by the tests
 _GFLAGS = {'fused_kpconv': True, 'two_pass_unary': True, 'double_norm': True, 'cin1_kernel': False, 'dual_apply': True, 'lifted_kernel': True, 'conv_stats_stream': True,
-           'rows_kpconv': True, 'rows_max_cout': 64}
+           'rows_kpconv': True, 'rows_max_cout': 128}
 
 
 def _gn_fusable_fused(cout, groups):

@@ -91,7 +91,7 @@ def test_kpconv_matches_oracle(pyramid, cin, cout):
 
 
 @pytest.mark.parametrize("cin,cout,hcols", [(32, 32, 38), (64, 64, 36), (16, 64, 30), (32, 32, 44), (48, 96, 38),
-                                            (64, 64, 46)])
+                                            (64, 64, 46), (128, 128, 36), (64, 256, 38), (32, 128, 30), (16, 256, 44)])
 def test_kpconv_rows_matches_oracle(pyramid, cin, cout, hcols):
     """se3et_kpconv_rows (UMMA rows = points, basis weights parked in TMEM) against the oracle: self and strided
     convolution, ragged last tile, neighbour widths that select every fragment variant (<= 32, <= 40, <= 48 columns;
@@ -113,6 +113,7 @@ def test_kpconv_rows_matches_oracle(pyramid, cin, cout, hcols):
         w = conv.weights.detach().bfloat16().float()
         want = oe.kpconv_inter_so3(q, s, nb, x, w, conv.kernel_points.detach(), 0.05, t["kidx"], t["ridx"])
         conv = conv.to(DEV)
+        old_cap = M._GFLAGS['rows_max_cout']
         M._GFLAGS['rows_max_cout'] = 1 << 20
         try:
             assert conv._fused_ok(nb) and conv._rows_ok(nb, s.shape[0])
@@ -123,7 +124,7 @@ def test_kpconv_rows_matches_oracle(pyramid, cin, cout, hcols):
             assert L.counts.get("se3et_kpconv_rows", 0) == 1, L.counts
             L.enabled = False
         finally:
-            M._GFLAGS['rows_max_cout'] = 64
+            M._GFLAGS['rows_max_cout'] = old_cap
         assert torch.isfinite(got).all()
         assert torch.allclose(got, want, rtol=2e-2, atol=5e-3 * want.abs().max().item() + 1e-6), \
             (got - want).abs().max().item()
@@ -151,7 +152,10 @@ def test_kpconv_wide_neighbourhoods_match_oracle(pyramid, cin, cout, hcols):
         w = conv.weights.detach().bfloat16().float()
         want = oe.kpconv_inter_so3(q, s, nb, x, w, conv.kernel_points.detach(), 0.05, t["kidx"], t["ridx"])
         conv = conv.to(DEV)
-        assert conv._fused_ok(nb) and not conv._rows_ok(nb, s.shape[0])
+        M._GFLAGS['rows_max_cout'], old_cap = 1 << 20, M._GFLAGS['rows_max_cout']
+        rows_ok = conv._rows_ok(nb, s.shape[0])
+        M._GFLAGS['rows_max_cout'] = old_cap
+        assert conv._fused_ok(nb) and not rows_ok   # > 48 columns: the fused kernel's halves
         L = __import__('se3et_b200._lib', fromlist=['x']).lib()
         L.enabled = True
         L.reset()
