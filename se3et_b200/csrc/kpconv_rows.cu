@@ -148,6 +148,15 @@ __device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster, uint32_t s
                "r"(src_cta), "r"(bytes), "r"(mbar_cluster)
                : "memory");
 }
+// TMA tile -> the same shared-memory offset of every CTA in `mask`, completing bytes on each CTA's own mbarrier
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                      uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(tc::smem_u32(smem_dst)),
+      "l"(m), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
 // arrive on the same-offset mbarrier of every CTA in `mask` when all previously issued MMAs of this thread completed
 __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -200,8 +209,10 @@ struct Smem {
 };
 
 // BN: output columns per CTA; KH: neighbour columns / 8 rounded up (4, 5, 6); PPW: points per producer warp (of this
-// CTA); TP: points per warp whose basis fragments live in tensor memory; CL: CTAs per cluster sharing a tile (1: none)
-template <int BN, int KH, int PPW, int TP, int CL>
+// CTA); TP: points per warp whose basis fragments live in tensor memory; CL: CTAs per cluster sharing a tile (1: none);
+// WM: CTAs per cluster that work on DIFFERENT tiles but consume the same weight stream: every CTA loads 1 / WM of each
+// weight K-block and TMA-multicasts it to the cluster (L2 reads and bytes in flight per CTA divided by WM)
+template <int BN, int KH, int PPW, int TP, int CL, int WM>
 __global__ void __launch_bounds__(kThreads + 32, 1)
 kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
   using S = Smem<BN, KH>;
@@ -213,6 +224,9 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
   static_assert(kW16Row * 16 <= kXStages * S::kXStage, "W16 scratch must fit the gather ring");
   constexpr int kTilePts = 16 * PPW * CL;
   static_assert(kTilePts <= 128 && (CL == 1 || kTilePts == 128), "a cluster shares one full 128-row tile");
+  static_assert(CL == 1 || WM == 1, "one kind of cluster at a time");
+  static_assert((BN / WM) % 8 == 0, "weight slices are whole swizzle atoms");
+  constexpr bool kCluster = CL > 1 || WM > 1;
   constexpr int kHR = S::kHR;
   constexpr int kXStage = S::kXStage;
   constexpr BetaTab kBeta = make_beta_tab();
@@ -237,6 +251,10 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
   const int64_t tile0 = CL > 1 ? (int64_t)cluster_id_x() : (int64_t)blockIdx.x;
   const int64_t tile_stride = CL > 1 ? (int64_t)num_clusters_x() : (int64_t)gridDim.x;
   const int64_t ntiles = (args.nq + kTilePts - 1) / kTilePts;
+  // WM > 1: the CTAs of a cluster advance through the weight stream in lockstep, so all of them run the same number of
+  // rounds; a CTA whose tile index passes the end works on a dummy tile (no valid point)
+  const int64_t nrounds = (ntiles + tile_stride - 1) / tile_stride;
+  const uint32_t wrank = WM > 1 ? cluster_ctarank() : 0u;
   const int nsteps = args.cin / kChunk * kA;  // (chunk, a), a fastest
   const int wstages = args.wstages;
 
@@ -252,7 +270,7 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
     }
     for (int s = 0; s < wstages; ++s) {
       tc::mbar_init(&w_full[s], 1);
-      tc::mbar_init(&w_empty[s], 1);
+      tc::mbar_init(&w_empty[s], WM);
     }
     tc::mbar_init(tmem_full, 1);
     tc::mbar_init(tmem_empty, kProdWarps);
@@ -265,7 +283,7 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
   if (warp == kProdWarps) tc::tmem_alloc<512>(tmem_ptr);
   tc::fence_proxy_async_smem();
   tc::tcgen05_fence_before_sync();
-  if (CL > 1) cluster_sync_all(); else __syncthreads();   // peers' mbarriers are initialised before anything remote
+  if (kCluster) cluster_sync_all(); else __syncthreads();   // peers' mbarriers are initialised before anything remote
   tc::tcgen05_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -437,7 +455,7 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
     // rotated tile loop (one call site per phase): production(t), setup(t + 1), epilogue(t)
     for (int64_t tile = tile0 - tile_stride, titer = -1;; tile += tile_stride, ++titer) {
       const bool have = titer >= 0;
-      const bool have_next = tile + tile_stride < ntiles;
+      const bool have_next = WM > 1 ? titer + 1 < nrounds : tile + tile_stride < ntiles;
       if (have) {
       // items (step, point) in order; the ring runs two items ahead
       {
@@ -567,7 +585,7 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
       constexpr uint32_t idesc = tc::umma_idesc_bf16(128, BN);
       uint32_t gstep = 0, titer = 0, ws = 0, wphase = 0;
       const uint32_t b_s = tc::smem_u32(b_tile), w_s = tc::smem_u32(w_tile);
-      for (int64_t tile = tile0; tile < ntiles; tile += tile_stride, ++titer) {
+      for (int64_t tile = tile0; WM > 1 ? (int64_t)titer < nrounds : tile < ntiles; tile += tile_stride, ++titer) {
         tc::mbar_wait_long(tmem_empty, (titer & 1) ^ 1);  // the epilogue has drained the previous tile's accumulators
         tc::tcgen05_fence_after_sync();
         for (int step = 0; step < nsteps; ++step, ++gstep) {
@@ -591,7 +609,8 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
                             (step | kc) != 0);
 #endif
             }
-            tc::umma_commit(&w_empty[ws]);
+            if (WM > 1) umma_commit_multicast(&w_empty[ws], (uint16_t)((1u << WM) - 1u));
+            else tc::umma_commit(&w_empty[ws]);
             if (++ws == (uint32_t)wstages) { ws = 0; wphase ^= 1; }
           }
           // every CTA of the cluster writes rows into this buffer: all of them learn that it is free again
@@ -605,11 +624,18 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
     // =========================================== weight TMA ==================================================
     if (lane == 0) {
       uint32_t ws = 0, wphase = 0;
-      for (int64_t tile = tile0; tile < ntiles; tile += tile_stride) {
+      int64_t round = 0;
+      for (int64_t tile = tile0; WM > 1 ? round < nrounds : tile < ntiles; tile += tile_stride, ++round) {
         for (int kbg = 0; kbg < nsteps * 9; ++kbg) {
-          tc::mbar_wait_long(&w_empty[ws], wphase ^ 1);
+          tc::mbar_wait_long(&w_empty[ws], wphase ^ 1);     // WM > 1: every CTA of the cluster has consumed the stage
           tc::mbar_arrive_expect_tx(&w_full[ws], BN * 128);
-          tc::tma_load_2d(w_tile + ws * S::kWStage, &tma_w, &w_full[ws], kbg * 64, n0);
+          if (WM > 1) {
+            constexpr int kSliceRows = BN / WM;
+            tma_load_2d_multicast(w_tile + ws * S::kWStage + wrank * (kSliceRows * 128), &tma_w, &w_full[ws], kbg * 64,
+                                  n0 + (int)wrank * kSliceRows, (uint16_t)((1u << WM) - 1u));
+          } else {
+            tc::tma_load_2d(w_tile + ws * S::kWStage, &tma_w, &w_full[ws], kbg * 64, n0);
+          }
           if (++ws == (uint32_t)wstages) { ws = 0; wphase ^= 1; }
         }
       }
@@ -642,7 +668,7 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
     }
   }
   tc::tcgen05_fence_before_sync();
-  if (CL > 1) cluster_sync_all(); else __syncthreads();   // no CTA leaves while a peer may still write to it
+  if (kCluster) cluster_sync_all(); else __syncthreads();   // no CTA leaves while a peer may still write to it
   if (warp == kProdWarps) tc::tmem_dealloc<512>(tmem_base);
 }
 
@@ -652,31 +678,41 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, int64_t rows, int64_t 
 
 namespace rows {
 
-template <int BN, int KH, int PPW, int TP, int CL>
-static int launch(const CUtensorMap& tw, Args args, cudaStream_t st) {
+template <int BN, int KH, int PPW, int TP, int CL, int WM>
+static int launch(const void* w, Args args, cudaStream_t st) {
   using S = Smem<BN, KH>;
   args.wstages = S::max_wstages();
   if (args.wstages < 2) return SE3ET_ERR_UNSUPPORTED;
   const int smem = S::total(args.wstages);
-  auto kernel = kpconv_rows_kernel<BN, KH, PPW, TP, CL>;
+  CUtensorMap tw;
+  int rc = make_tmap_bf16_2d(&tw, w, args.cout, 216 * (int64_t)args.cin, 216 * (int64_t)args.cin, BN / WM);
+  if (rc) return rc;
+  auto kernel = kpconv_rows_kernel<BN, KH, PPW, TP, CL, WM>;
   SE3ET_ENSURE_SMEM(kernel, smem);
   const int64_t ntiles = ceil_div(args.nq, 16 * PPW * CL);
-  if (CL == 1) {
+  if (CL == 1 && WM == 1) {
     dim3 grid((unsigned)(ntiles < kNumSMs ? ntiles : kNumSMs), (unsigned)(args.cout / BN));
     kernel<<<grid, kThreads + 32, smem, st>>>(tw, args);
     SE3ET_LAUNCH_CHECK();
     return SE3ET_OK;
   }
-  // one cluster of CL CTAs per tile of 128 points; CTA rank = column block of BN outputs (cout == CL * BN)
-  const int64_t max_clusters = kNumSMs / CL;
+  constexpr int kC = CL * WM;   // cluster size (one of the two is 1)
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)((ntiles < max_clusters ? ntiles : max_clusters) * CL), 1, 1);
+  if (CL > 1) {
+    // one cluster of CL CTAs per tile of 128 points; CTA rank = column block of BN outputs (cout == CL * BN)
+    const int64_t max_clusters = kNumSMs / CL;
+    cfg.gridDim = dim3((unsigned)((ntiles < max_clusters ? ntiles : max_clusters) * CL), 1, 1);
+  } else {
+    // clusters of WM CTAs on consecutive tiles, same column block (blockIdx.y)
+    const int64_t want = ceil_div(ntiles, WM) * WM, cap = kNumSMs / WM * WM;
+    cfg.gridDim = dim3((unsigned)(want < cap ? want : cap), (unsigned)(args.cout / BN), 1);
+  }
   cfg.blockDim = dim3(kThreads + 32, 1, 1);
   cfg.dynamicSmemBytes = (size_t)smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.x = kC;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
@@ -715,42 +751,45 @@ extern "C" int se3et_kpconv_rows(const float* q_pts, const float* s_pts, const i
   a.q_pts = q_pts; a.s_pts = s_pts; a.idx = neighbors; a.x = static_cast<const __nv_bfloat16*>(x_bf16);
   a.kernel_points = kernel_points_15x3; a.out = out_f32; a.nq = nq; a.ns = ns; a.H = (int)h;
   a.cin = (int)cin; a.cout = (int)cout; a.inv_extent = 1.f / kp_extent; a.wstages = 0;
-  CUtensorMap tw;
-  int rc = make_tmap_bf16_2d(&tw, w_rows_bf16, cout, 216 * cin, 216 * cin, bn);
-  if (rc) return rc;
+  const void* w = w_rows_bf16;
+#ifndef SE3ET_ROWS_WM
+#define SE3ET_ROWS_WM 1   // measured on B200: 2 and 4 are 2x SLOWER (lockstep on a 4-stage ring: any skew between the CTAs stalls all)
+#endif
+  constexpr int WM = SE3ET_ROWS_WM;   // weight-multicast cluster size of the 64-column kernels
   // cout 128 / 256: clusters of 2 / 4 CTAs share a tile of 128 points (each CTA 64 output columns and 1 / CL of the
-  // operand rows, exchanged through distributed shared memory).  Other widths: one CTA per (tile, column block).
+  // operand rows, exchanged through distributed shared memory).  Other widths: one CTA per (tile, column block); the
+  // 64-column kernels run in clusters of WM CTAs that share the weight stream by TMA multicast.
 #ifdef SE3ET_ROWS_DEV
   if (kh != 5) return SE3ET_ERR_UNSUPPORTED;
-  if (cout == 128) return rows::launch<64, 5, 4, 3, 2>(tw, a, st);
-  if (cout == 256) return rows::launch<64, 5, 2, 2, 4>(tw, a, st);
-  return bn == 32 ? rows::launch<32, 5, 8, 8, 1>(tw, a, st) : rows::launch<64, 5, 6, 3, 1>(tw, a, st);
+  if (cout == 128) return rows::launch<64, 5, 4, 3, 2, 1>(w, a, st);
+  if (cout == 256) return rows::launch<64, 5, 2, 2, 4, 1>(w, a, st);
+  return bn == 32 ? rows::launch<32, 5, 8, 8, 1, 1>(w, a, st) : rows::launch<64, 5, 6, 3, 1, WM>(w, a, st);
 #else
   if (cout == 128 || cout == 256) {
     if (cout == 128) {
       switch (kh) {
-        case 4: return rows::launch<64, 4, 4, 4, 2>(tw, a, st);
-        case 5: return rows::launch<64, 5, 4, 3, 2>(tw, a, st);
-        default: return rows::launch<64, 6, 4, 2, 2>(tw, a, st);
+        case 4: return rows::launch<64, 4, 4, 4, 2, 1>(w, a, st);
+        case 5: return rows::launch<64, 5, 4, 3, 2, 1>(w, a, st);
+        default: return rows::launch<64, 6, 4, 2, 2, 1>(w, a, st);
       }
     }
     switch (kh) {
-      case 4: return rows::launch<64, 4, 2, 2, 4>(tw, a, st);
-      case 5: return rows::launch<64, 5, 2, 2, 4>(tw, a, st);
-      default: return rows::launch<64, 6, 2, 2, 4>(tw, a, st);
+      case 4: return rows::launch<64, 4, 2, 2, 4, 1>(w, a, st);
+      case 5: return rows::launch<64, 5, 2, 2, 4, 1>(w, a, st);
+      default: return rows::launch<64, 6, 2, 2, 4, 1>(w, a, st);
     }
   }
   if (bn == 32) {
     switch (kh) {
-      case 4: return rows::launch<32, 4, 8, 8, 1>(tw, a, st);
-      case 5: return rows::launch<32, 5, 8, 8, 1>(tw, a, st);
-      default: return rows::launch<32, 6, 8, 6, 1>(tw, a, st);
+      case 4: return rows::launch<32, 4, 8, 8, 1, 1>(w, a, st);
+      case 5: return rows::launch<32, 5, 8, 8, 1, 1>(w, a, st);
+      default: return rows::launch<32, 6, 8, 6, 1, 1>(w, a, st);
     }
   }
   switch (kh) {
-    case 4: return rows::launch<64, 4, 6, 4, 1>(tw, a, st);
-    case 5: return rows::launch<64, 5, 6, 3, 1>(tw, a, st);
-    default: return rows::launch<64, 6, 6, 2, 1>(tw, a, st);
+    case 4: return rows::launch<64, 4, 6, 4, 1, WM>(w, a, st);
+    case 5: return rows::launch<64, 5, 6, 3, 1, WM>(w, a, st);
+    default: return rows::launch<64, 6, 6, 2, 1, WM>(w, a, st);
   }
 #endif
 }

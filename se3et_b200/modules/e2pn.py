@@ -190,8 +190,10 @@ class KPConvInterSO3(nn.Module):
         return y
 
     def _fused_ok(self, neighb_inds):
-        return _GFLAGS['fused_kpconv'] and neighb_inds.shape[0] > 0 and K.kpconv_fused_supported(
-            self.in_channels, self.out_channels, neighb_inds.shape[1])
+        """One of the one-kernel paths (se3et_kpconv_rows / se3et_kpconv_fused) covers this shape."""
+        return _GFLAGS['fused_kpconv'] and neighb_inds.shape[0] > 0 and (
+            self._rows_ok(neighb_inds, 0) or
+            K.kpconv_fused_supported(self.in_channels, self.out_channels, neighb_inds.shape[1]))
 
     def forward(self, q_pts, s_pts, neighb_inds, x):
         """-> fp32 (Nq, A, Cout), pre-norm (blocks_epn.py:454-546)."""
