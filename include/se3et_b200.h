@@ -369,14 +369,18 @@ int se3et_l2_normalize_rows(const float* x, int64_t rows, int64_t channels, floa
 
 /* SuperPointMatching.forward (superpoint_matching.py:13-55) for num_pairs pairs at once.
  * problems: int64 [num_pairs][5] {ref_start, n_ref, src_start, n_src, e_off}; masks uint8 (1 = keep) or NULL.
- * e_workspace: fp32, sum of n_ref*n_src; row_sums / col_sums: fp32 per ref / src superpoint.
+ * e_workspace: fp32, 16-byte aligned, se3et_superpoint_matching_workspace_floats(...) floats: the score matrices
+ * (e_total = sum of n_ref*n_src floats) followed by the candidate lists of the selection (eight CTAs per pair each
+ * select their slice's top-k, one CTA per pair merges them); row_sums / col_sums: fp32 per ref / src superpoint.
  * Outputs per pair: num_correspondences (ref index, src index, score) sorted by (score desc, flat index asc),
  * indices local to the pair, -1 padded; counts[p] = min(num_correspondences, #unmasked entries). */
+int se3et_superpoint_matching_workspace_floats(int64_t num_pairs, int64_t num_correspondences, int64_t e_total,
+                                               int64_t* floats);
 int se3et_superpoint_matching(const float* ref_feats, const float* src_feats, int64_t channels,
                               const uint8_t* ref_masks, const uint8_t* src_masks, const int64_t* problems,
                               int64_t num_pairs, int64_t max_ref, int64_t max_src, int64_t num_correspondences,
-                              int dual_normalization, float* e_workspace, float* row_sums, float* col_sums,
-                              int64_t* ref_idx, int64_t* src_idx, float* scores, int32_t* counts,
+                              int dual_normalization, float* e_workspace, int64_t e_total, float* row_sums,
+                              float* col_sums, int64_t* ref_idx, int64_t* src_idx, float* scores, int32_t* counts,
                               se3et_stream_t stream);
 
 /* point_to_node_partition -- geotransformer/modules/ops/pointcloud_partition.py:60-107 (called twice per pair from

@@ -92,54 +92,53 @@ __device__ __forceinline__ int block_prefix(int flag, int* sh_warp, int& total) 
   return off + in_warp;
 }
 
-// one CTA per pair: exact k-th largest by 3-pass radix select on the float bits, ordered collection, bitonic sort
+constexpr int kSelSlices = 8;  // CTAs per pair in the selection (a pair alone would leave most of the 148 SMs idle)
+
+// one CTA per (slice, pair): the slice's top-k by the canonical order (exact k-th largest by 3-pass radix select on the
+// float bits, ordered collection, bitonic sort) as 64-bit keys (~score bits, flat index); the global top-k is a subset
+// of the union of the slices' top-k lists, spm_merge_kernel picks it
 __global__ void __launch_bounds__(kSelThreads) spm_topk_kernel(const float* __restrict__ e,
                                                                 const float* __restrict__ row_sum,
                                                                 const float* __restrict__ col_sum,
                                                                 const uint8_t* __restrict__ ref_mask,
                                                                 const uint8_t* __restrict__ src_mask,
                                                                 const MatchProblem* __restrict__ problems, int k_req,
-                                                                int dual, int64_t* __restrict__ ref_idx,
-                                                                int64_t* __restrict__ src_idx,
-                                                                float* __restrict__ scores, int32_t* __restrict__ counts) {
+                                                                int dual, unsigned long long* __restrict__ slice_keys,
+                                                                int32_t* __restrict__ slice_counts) {
   __shared__ unsigned int hist[2048];
   __shared__ int sh_warp[kSelThreads / 32];
   __shared__ unsigned long long cand[kSelMaxK];
   __shared__ unsigned int sh_prefix, sh_remaining;
   __shared__ int sh_valid;
-  const MatchProblem pr = problems[blockIdx.x];
+  const MatchProblem pr = problems[blockIdx.y];
   const int n_src = (int)pr.n_src;
-  const int64_t total = pr.n_ref * pr.n_src;
+  const int64_t all = pr.n_ref * pr.n_src;
+  const int64_t i_begin = all * blockIdx.x / gridDim.x, i_end = all * (blockIdx.x + 1) / gridDim.x;
   const float* ep = e + pr.e_off;
   const float* rs = row_sum + pr.ref_start;
   const float* cs = col_sum + pr.src_start;
-  int64_t* out_r = ref_idx + (int64_t)blockIdx.x * k_req;
-  int64_t* out_s = src_idx + (int64_t)blockIdx.x * k_req;
-  float* out_v = scores + (int64_t)blockIdx.x * k_req;
+  unsigned long long* out_k = slice_keys + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * k_req;
 
-  // number of unmasked entries = (#valid rows) * (#valid cols)
+  // number of unmasked entries of the slice
   if (threadIdx.x == 0) sh_valid = 0;
   __syncthreads();
   {
-    int vr = 0, vc = 0;
-    for (int i = threadIdx.x; i < pr.n_ref; i += kSelThreads) vr += (!ref_mask || ref_mask[pr.ref_start + i]) ? 1 : 0;
-    for (int i = threadIdx.x; i < pr.n_src; i += kSelThreads) vc += (!src_mask || src_mask[pr.src_start + i]) ? 1 : 0;
-    // pack both counts into one atomic word (each < 65536 is not guaranteed: use two passes)
-    atomicAdd(&sh_valid, vr);
+    int v = 0;
+    for (int64_t i = i_begin + threadIdx.x; i < i_end; i += kSelThreads) {
+      const int n = (int)(i / n_src), m = (int)(i - (int64_t)n * n_src);
+      v += ((ref_mask && !ref_mask[pr.ref_start + n]) || (src_mask && !src_mask[pr.src_start + m])) ? 0 : 1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&sh_valid, v);
     __syncthreads();
-    const int rows_valid = sh_valid;
+    const int nvalid = sh_valid;
     __syncthreads();
-    if (threadIdx.x == 0) sh_valid = 0;
-    __syncthreads();
-    atomicAdd(&sh_valid, vc);
-    __syncthreads();
-    const long long nvalid = (long long)rows_valid * sh_valid;
-    __syncthreads();
-    if (threadIdx.x == 0) sh_valid = (int)(nvalid < k_req ? nvalid : k_req);
+    if (threadIdx.x == 0) sh_valid = nvalid < k_req ? nvalid : k_req;
     __syncthreads();
   }
-  const int k = sh_valid;  // min(num_correspondences, numel) (superpoint_matching.py:43)
-  if (threadIdx.x == 0) counts[blockIdx.x] = k;
+  const int k = sh_valid;  // this slice contributes at most min(num_correspondences, its unmasked entries) candidates
+  if (threadIdx.x == 0) slice_counts[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = k;
   if (k == 0) return;
 
   // ---- radix select: bits of a non-negative float order like unsigned integers
@@ -151,7 +150,7 @@ __global__ void __launch_bounds__(kSelThreads) spm_topk_kernel(const float* __re
     const int shift = shifts[pass], nb = 1 << widths[pass];
     for (int i = threadIdx.x; i < nb; i += kSelThreads) hist[i] = 0;
     __syncthreads();
-    for (int64_t i = threadIdx.x; i < total; i += kSelThreads) {
+    for (int64_t i = i_begin + threadIdx.x; i < i_end; i += kSelThreads) {
       const int n = (int)(i / n_src), m = (int)(i - (int64_t)n * n_src);
       if ((ref_mask && !ref_mask[pr.ref_start + n]) || (src_mask && !src_mask[pr.src_start + m])) continue;
       const unsigned int bits = __float_as_uint(spm_score(ep, rs, cs, i, n_src, dual));
@@ -178,11 +177,11 @@ __global__ void __launch_bounds__(kSelThreads) spm_topk_kernel(const float* __re
 
   // ---- ordered collection (ascending flat index): everything above the threshold, then the first ties
   int n_above = 0, n_tie = 0;
-  for (int64_t base = 0; base < total; base += kSelThreads) {
+  for (int64_t base = i_begin; base < i_end; base += kSelThreads) {
     const int64_t i = base + threadIdx.x;
     unsigned int bits = 0;
     bool valid = false;
-    if (i < total) {
+    if (i < i_end) {
       const int n = (int)(i / n_src), m = (int)(i - (int64_t)n * n_src);
       valid = !((ref_mask && !ref_mask[pr.ref_start + n]) || (src_mask && !src_mask[pr.src_start + m]));
       if (valid) bits = __float_as_uint(spm_score(ep, rs, cs, i, n_src, dual));
@@ -218,9 +217,51 @@ __global__ void __launch_bounds__(kSelThreads) spm_topk_kernel(const float* __re
       __syncthreads();
     }
   }
+  for (int i = threadIdx.x; i < k; i += kSelThreads) out_k[i] = cand[i];
+}
+
+// one CTA per pair: the sorted candidate lists of its slices -> the pair's top-k in the canonical order
+__global__ void __launch_bounds__(kSelThreads) spm_merge_kernel(const unsigned long long* __restrict__ slice_keys,
+                                                                 const int32_t* __restrict__ slice_counts, int nslices,
+                                                                 const MatchProblem* __restrict__ problems, int k_req,
+                                                                 int64_t* __restrict__ ref_idx,
+                                                                 int64_t* __restrict__ src_idx, float* __restrict__ scores,
+                                                                 int32_t* __restrict__ counts) {
+  extern __shared__ unsigned long long keys[];  // [nslices * k_req rounded up to a power of two]
+  const MatchProblem pr = problems[blockIdx.x];
+  const int n_src = (int)pr.n_src;
+  int n = 0;
+  for (int sl = 0; sl < nslices; ++sl) {
+    const int c = slice_counts[(int64_t)blockIdx.x * nslices + sl];
+    const unsigned long long* src = slice_keys + ((int64_t)blockIdx.x * nslices + sl) * k_req;
+    for (int i = threadIdx.x; i < c; i += kSelThreads) keys[n + i] = src[i];
+    n += c;
+  }
+  int n2 = 1;
+  while (n2 < n) n2 <<= 1;
+  for (int i = n + threadIdx.x; i < n2; i += kSelThreads) keys[i] = ~0ull;
+  __syncthreads();
+  for (int kk = 2; kk <= n2; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n2; i += kSelThreads) {
+        const int p = i ^ j;
+        if (p > i) {
+          const unsigned long long x = keys[i], y = keys[p];
+          const bool up = (i & kk) == 0;
+          if ((x > y) == up) { keys[i] = y; keys[p] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const int k = n < k_req ? n : k_req;  // min(num_correspondences, #unmasked entries) (superpoint_matching.py:43)
+  if (threadIdx.x == 0) counts[blockIdx.x] = k;
+  int64_t* out_r = ref_idx + (int64_t)blockIdx.x * k_req;
+  int64_t* out_s = src_idx + (int64_t)blockIdx.x * k_req;
+  float* out_v = scores + (int64_t)blockIdx.x * k_req;
   for (int i = threadIdx.x; i < k_req; i += kSelThreads) {
     if (i < k) {
-      const unsigned long long c = cand[i];
+      const unsigned long long c = keys[i];
       const unsigned int flat = (unsigned int)(c & 0xffffffffull);
       out_r[i] = flat / n_src;
       out_s[i] = flat % n_src;
@@ -237,11 +278,19 @@ __global__ void __launch_bounds__(kSelThreads) spm_topk_kernel(const float* __re
 
 using namespace se3et;
 
+extern "C" int se3et_superpoint_matching_workspace_floats(int64_t num_pairs, int64_t num_correspondences, int64_t e_total,
+                                                          int64_t* floats) {
+  if (!floats || num_pairs < 0 || num_correspondences <= 0 || e_total < 0) return SE3ET_ERR_ARG;
+  // score matrices, then per (pair, slice): k 64-bit candidate keys; then the slice counts
+  *floats = (e_total + 3) / 4 * 4 + num_pairs * kSelSlices * (2 * num_correspondences + 1) + 4;
+  return SE3ET_OK;
+}
+
 extern "C" int se3et_superpoint_matching(const float* ref_feats, const float* src_feats, int64_t channels,
                                          const uint8_t* ref_masks, const uint8_t* src_masks, const int64_t* problems,
                                          int64_t num_pairs, int64_t max_ref, int64_t max_src,
                                          int64_t num_correspondences, int dual_normalization, float* e_workspace,
-                                         float* row_sums, float* col_sums, int64_t* ref_idx, int64_t* src_idx,
+                                         int64_t e_total, float* row_sums, float* col_sums, int64_t* ref_idx, int64_t* src_idx,
                                          float* scores, int32_t* counts, se3et_stream_t stream) {
   if (num_pairs < 0 || channels <= 0 || max_ref < 0 || max_src < 0 || num_correspondences <= 0 ||
       num_correspondences > kSelMaxK || num_pairs > 65535)
@@ -262,9 +311,20 @@ extern "C" int se3et_superpoint_matching(const float* ref_feats, const float* sr
     spm_col_sums_kernel<<<g2, 128, 0, st>>>(e_workspace, pr, col_sums);
     SE3ET_LAUNCH_CHECK();
   }
-  spm_topk_kernel<<<(unsigned)num_pairs, kSelThreads, 0, st>>>(e_workspace, row_sums, col_sums, ref_masks, src_masks, pr,
-                                                              (int)num_correspondences, dual_normalization, ref_idx,
-                                                              src_idx, scores, counts);
+  if ((reinterpret_cast<uintptr_t>(e_workspace) & 15) || e_total < 0) return SE3ET_ERR_ARG;
+  unsigned long long* slice_keys = reinterpret_cast<unsigned long long*>(e_workspace + (e_total + 3) / 4 * 4);
+  int32_t* slice_counts = reinterpret_cast<int32_t*>(slice_keys + num_pairs * kSelSlices * num_correspondences);
+  spm_topk_kernel<<<dim3(kSelSlices, (unsigned)num_pairs), kSelThreads, 0, st>>>(
+      e_workspace, row_sums, col_sums, ref_masks, src_masks, pr, (int)num_correspondences, dual_normalization,
+      slice_keys, slice_counts);
+  SE3ET_LAUNCH_CHECK();
+  int n2 = 1;
+  while (n2 < kSelSlices * num_correspondences) n2 <<= 1;
+  const size_t msmem = sizeof(unsigned long long) * (size_t)n2;
+  if (msmem > 48 * 1024) SE3ET_ENSURE_SMEM(spm_merge_kernel, msmem);
+  spm_merge_kernel<<<(unsigned)num_pairs, kSelThreads, msmem, st>>>(slice_keys, slice_counts, kSelSlices, pr,
+                                                                   (int)num_correspondences, ref_idx, src_idx, scores,
+                                                                   counts);
   SE3ET_LAUNCH_CHECK();
   return SE3ET_OK;
 }

@@ -240,6 +240,11 @@ class GeoTransformer(nn.Module):
         feats_list = self.backbone(feats, dd)
         feats_c, feats_f = feats_list[-1], feats_list[0]
         len_c = dd['lengths'][-1].cpu().numpy()  # already synchronised by the subsampling that produced it
+        if num_pairs > 1 and int(len_c.max(initial=0)) > 2000:
+            # the reference keeps at most 2000 superpoints per cloud (utils/data.py:34-43, applied in pair mode by
+            # precompute_data_stack_mode); a stacked launch would silently differ from the pair run alone
+            raise RuntimeError("forward_stacked: a cloud has %d superpoints (> 2000); run it through forward()" %
+                               int(len_c.max()))
         ref_sizes, src_sizes = len_c[0::2], len_c[1::2]
         points_c = dd['points'][-1]
         if num_pairs > 1:

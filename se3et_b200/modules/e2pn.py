@@ -9,6 +9,7 @@ offsets into the stacked point axis; None = the whole tensor is one pair, exactl
 fp32 inputs are accepted everywhere and rounded to bf16 once.
 """
 import math
+import threading
 
 import numpy as np
 import torch
@@ -49,19 +50,41 @@ def _seg(seg, n_points, device):
 
 
 class _Bf16Cache:
-    """bf16 copy of an fp32 parameter, refreshed when the parameter changes (in-place updates bump _version)."""
+    """bf16 copy of an fp32 parameter, refreshed when the parameter changes (in-place updates bump _version).
+
+    Launch sequences run on several host threads, one CUDA stream each (GeoTransformer.forward_stacked_concurrent): the
+    conversion is enqueued once, under a lock, on the stream of whichever thread gets there first; every other stream
+    waits on the conversion's event the first time it reads the copy."""
 
     def __init__(self):
-        self._key, self._val = None, None
+        self._key, self._val, self._event, self._synced = None, None, None, set()
+        self._lock = threading.Lock()
 
     def get(self, p, transform=None):
         key = (p.data_ptr(), p._version, p.device)
         if key != self._key:
-            with torch.no_grad():
-                v = p.detach() if transform is None else transform(p.detach())
-                self._val = v.to(torch.bfloat16).contiguous()
-            self._key = key
-        return self._val
+            with self._lock:
+                if key != self._key:
+                    with torch.no_grad():
+                        v = p.detach() if transform is None else transform(p.detach())
+                        val = v.to(torch.bfloat16).contiguous()
+                    ev, synced = None, set()
+                    if val.is_cuda:
+                        st = torch.cuda.current_stream(val.device)
+                        ev = torch.cuda.Event()
+                        ev.record(st)
+                        synced.add(st.cuda_stream)
+                    self._val, self._event, self._synced = val, ev, synced
+                    self._key = key  # last: whoever sees the key sees the value and its event
+        val = self._val
+        if val.is_cuda:
+            st = torch.cuda.current_stream(val.device)
+            if st.cuda_stream not in self._synced:
+                with self._lock:
+                    if self._event is not None:
+                        st.wait_event(self._event)
+                    self._synced.add(st.cuda_stream)
+        return val
 
 
 class GroupNormEPN(nn.Module):

@@ -19,6 +19,8 @@ states as bf16 (T*A, C) rows in (point, anchor) order.  The (N, N, C) geometric 
 """
 import functools
 
+import threading
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -129,6 +131,7 @@ class GeometricStructureEmbedding(nn.Module):
                 nn.Parameter(torch.ones(kanchor, 1, 1), requires_grad=False),
                 nn.Parameter(anchors.transpose(1, 2).contiguous(), requires_grad=False)])
         self._wd, self._wa = _Bf16Cache(), _Bf16Cache()
+        self._table_lock, self._table_state, self._table_retired = threading.Lock(), None, []
 
     def anchors_matrix(self):
         """(A, 3, 3) fp32 anchors (the transpose of the stored l = 1 Wigner-D matrices)."""
@@ -141,21 +144,36 @@ class GeometricStructureEmbedding(nn.Module):
         sinusoids and an fp32 matmul, once per weight version and size bucket (parameter preprocessing like the bf16
         weight copies, not part of the per-pair path)."""
         nd = 1 << int(np.ceil(np.log2(max(u_max, 1.0) / self.TABLE_STEP + 2)))
-        key = (self.proj_d.weight._version, self.proj_a.weight._version, self.proj_d.bias._version,
-               self.proj_a.bias._version, self.proj_d.weight.data_ptr(), str(device), nd)
-        if getattr(self, '_table_key', None) != key:
-            with torch.no_grad():
-                div = self.embedding.div_term.to(device).float()
+        wkey = (self.proj_d.weight._version, self.proj_a.weight._version, self.proj_d.bias._version,
+                self.proj_a.bias._version, self.proj_d.weight.data_ptr(), str(device))
+        # shared by the host threads / streams of concurrent launch sequences: built under a lock, the LARGEST table is
+        # kept (a smaller request reuses it: same step, more rows), other streams wait on the build's event once
+        with self._table_lock:
+            cur = self._table_state
+            if cur is None or cur['wkey'] != wkey or cur['nd'] < nd:
+                with torch.no_grad():
+                    div = self.embedding.div_term.to(device).float()
 
-                def table(n, lin):
-                    u = torch.arange(n, device=device, dtype=torch.float32) * self.TABLE_STEP
-                    om = u[:, None] * div[None, :]
-                    e = torch.stack([torch.sin(om), torch.cos(om)], dim=2).reshape(n, -1)
-                    return torch.addmm(lin.bias.float(), e, lin.weight.float().t()).to(torch.bfloat16).contiguous()
-                na = int(180.0 / self.sigma_a / self.TABLE_STEP) + 2
-                self._table_d, self._table_a = table(nd, self.proj_d), table(na, self.proj_a)
-            self._table_key = key
-        return self._table_d, self._table_a
+                    def table(n, lin):
+                        u = torch.arange(n, device=device, dtype=torch.float32) * self.TABLE_STEP
+                        om = u[:, None] * div[None, :]
+                        e = torch.stack([torch.sin(om), torch.cos(om)], dim=2).reshape(n, -1)
+                        return torch.addmm(lin.bias.float(), e, lin.weight.float().t()).to(torch.bfloat16).contiguous()
+                    na = int(180.0 / self.sigma_a / self.TABLE_STEP) + 2
+                    st = torch.cuda.current_stream(device)
+                    ev = torch.cuda.Event()
+                    cur = {'wkey': wkey, 'nd': nd, 'd': table(nd, self.proj_d), 'a': table(na, self.proj_a), 'event': ev,
+                           'synced': {st.cuda_stream}}
+                    ev.record(st)
+                if self._table_state is not None:
+                    # another stream may still be reading the smaller tables: keep them alive (sizes only double)
+                    self._table_retired.append(self._table_state)
+                self._table_state = cur
+            st = torch.cuda.current_stream(device)
+            if st.cuda_stream not in cur['synced']:
+                st.wait_event(cur['event'])
+                cur['synced'].add(st.cuda_stream)
+            return cur['d'], cur['a']
 
     def embed(self, points_flat, ctx):
         """-> bf16 (sum n_b^2, C): row eoff[b] + n*n_b + m is the embedding of the pair (n, m) of cloud b."""

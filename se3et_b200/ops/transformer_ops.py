@@ -1,4 +1,6 @@
 """Host wrappers of the superpoint-transformer and matching kernels (include/se3et_b200.h)."""
+import ctypes
+
 import torch
 
 from .. import _lib
@@ -103,7 +105,11 @@ def superpoint_matching(ref_feats, src_feats, ref_masks, src_masks, problems, ma
         return mk.view(torch.uint8) if mk.dtype == torch.bool else mk.to(torch.uint8)
 
     rm, sm = mask8(ref_masks), mask8(src_masks)
-    e = torch.empty((max(e_total, 1),), dtype=torch.float32, device=dev)
+    nfloats = ctypes.c_int64(0)
+    _lib.check(_lib.lib().se3et_superpoint_matching_workspace_floats(_lib.i64(p), _lib.i64(k), _lib.i64(e_total),
+                                                                    ctypes.byref(nfloats)),
+               "superpoint_matching_workspace_floats")
+    e = torch.empty((max(nfloats.value, 1),), dtype=torch.float32, device=dev)
     rs = torch.empty((max(ref_feats.shape[0], 1),), dtype=torch.float32, device=dev)
     cs = torch.empty((max(src_feats.shape[0], 1),), dtype=torch.float32, device=dev)
     ri = torch.empty((p, k), dtype=torch.int64, device=dev)
@@ -113,9 +119,9 @@ def superpoint_matching(ref_feats, src_feats, ref_masks, src_masks, problems, ma
     _lib.check(_lib.lib().se3et_superpoint_matching(
         _lib.ptr(ref_feats), _lib.ptr(src_feats), _lib.i64(ref_feats.shape[1]), _lib.ptr(rm), _lib.ptr(sm),
         _lib.ptr(problems), _lib.i64(p), _lib.i64(max_ref), _lib.i64(max_src), _lib.i64(k),
-        int(bool(dual_normalization)), _lib.ptr(e), _lib.ptr(rs), _lib.ptr(cs), _lib.ptr(ri), _lib.ptr(si), _lib.ptr(sc),
-        _lib.ptr(cnt), _lib.stream_ptr()), "superpoint_matching")
-    return ri, si, sc, cnt, e
+        int(bool(dual_normalization)), _lib.ptr(e), _lib.i64(e_total), _lib.ptr(rs), _lib.ptr(cs), _lib.ptr(ri),
+        _lib.ptr(si), _lib.ptr(sc), _lib.ptr(cnt), _lib.stream_ptr()), "superpoint_matching")
+    return ri, si, sc, cnt, e[:max(e_total, 1)]
 
 
 # ---- SE3ET-E -----------------------------------------------------------------------------------------------------
