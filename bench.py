@@ -36,6 +36,10 @@ WORKLOADS = {
     # BASELINE.json configs[2]: SE3ET-E on ~5k-point pairs (a 1.5 m crop of the 3DMatch-shaped fragments)
     "3dmatch-e": ("se3ete.3dmatch", "3dmatch_5k_shape_pairs_per_sec", "make_3dmatch_pair_5k",
                   "~5k pts/cloud, voxel 0.025 m, 4 stages, SE3ET-E"),
+    # BASELINE.json configs[4]: SE3ET-I training step (forward + backward), one pair per GPU per iteration as the
+    # reference trains (batch_size 1), gradients averaged over the ranks by one NCCL all-reduce
+    "train": ("se3eti.3dmatch", "3dmatch_shape_training_pairs_per_sec", "make_3dmatch_pair",
+              "~15k pts/cloud, voxel 0.025 m, 4 stages, forward + backward + gradient all-reduce + Adam"),
 }
 
 
@@ -369,6 +373,59 @@ def measure_extra(name, args, world, rank, dev, steps=3, warmup=2):
             "top_entry_points_ms": {k: round(v, 3) for k, v in top}, "serial_step_ms": round(s0.elapsed_time(s1), 3)}
 
 
+def measure_train(args, world, rank, dev, steps=None, warmup=None):
+    """configs[4]: training iterations of SE3ET-I on synthetic 3DMatch-shaped pairs, one pair per rank per iteration
+    (se3et_b200/training.py: CUDA forward, ATen-recompute backward, reference losses, one flattened gradient all-reduce
+    over NCCL, Adam).  pairs/s = world pairs per iteration / iteration time (device events, max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    from se3et_b200 import training as TR
+    from se3et_b200.model import create_model, make_cfg
+    steps = steps or max(2, min(args.steps, 5))
+    warmup = warmup if warmup is not None else 2
+    cfg = make_cfg("se3eti.3dmatch")
+    torch.manual_seed(0)
+    model = create_model(cfg).to(dev).train()
+    params = TR.trainable_parameters(model)
+    opt = torch.optim.Adam(params, lr=1e-4)
+    from se3et_b200 import synthetic
+    mine = [synthetic.make_3dmatch_pair(100 + rank * 16 + i) for i in range(4)]
+    rng = np.random.default_rng(rank)
+
+    def step(i):
+        p = mine[i % len(mine)]
+        return TR.training_step(model, p["ref_points"], p["src_points"], p["transform"], optimizer=opt, world_size=world,
+                                rng=rng)
+    for i in range(warmup):
+        step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    last = None
+    for i in range(steps):
+        last = step(warmup + i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    nparam = sum(p.numel() for p in params)
+    return {"metric": WORKLOADS["train"][1], "value": world * steps / (ms / 1e3), "unit": "pairs/s",
+            "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+            "config": {"workload": "SE3ET-I 3dmatch-shaped training step (%s)" % WORKLOADS["train"][3],
+                       "variant": "se3eti.3dmatch", "pairs_per_gpu_per_step": 1,
+                       "parallelism": "data parallel over %d GPU(s), one flattened gradient all-reduce per step" % world,
+                       "backward": "recompute through ATen (se3et_b200/training.py); forward on the CUDA path"},
+            "grad_allreduce_bytes_per_step": int(last["grad_bytes"]) if last else 0, "parameters": int(nparam),
+            "last_loss": last["loss"] if last else None}
+
+
 # ------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -518,9 +575,10 @@ def main():
     if args.workload == "3dmatch" and not args.no_extra:
         del model, dev_inputs, pinned
         torch.cuda.empty_cache()
-        for name in ("kitti", "3dmatch-e"):
+        for name in ("kitti", "3dmatch-e", "train"):
             try:
-                extra[name] = measure_extra(name, args, world, rank, dev)
+                extra[name] = (measure_train(args, world, rank, dev) if name == "train"
+                               else measure_extra(name, args, world, rank, dev))
             except Exception as e:  # the headline line must survive a failing secondary workload
                 extra[name] = {"error": "%s: %s" % (type(e).__name__, e)}
             torch.cuda.empty_cache()
