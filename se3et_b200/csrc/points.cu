@@ -534,7 +534,16 @@ __global__ void __launch_bounds__(kQueryWarps * 32) radius_query_kernel(
   }
   if (!out || width <= 0) return;
   int64_t* row = out + qi * width;
-  if (nhit <= 64) {
+  if (nhit <= 32) {
+    // at most one key per lane: rank it against all others (keys are unique, the rank is the sorted position)
+    __syncwarp();
+    const unsigned long long mine = lane < nhit ? keys[lane] : ~0ull;
+    int rank = 0;
+#pragma unroll 4
+    for (int f = 0; f < nhit; ++f) rank += keys[f] < mine ? 1 : 0;
+    if (lane < nhit && rank < width) row[rank] = (int64_t)(mine & 0xffffffffull);
+    for (int k = nhit + lane; k < width; k += 32) row[k] = ns_total;
+  } else if (nhit <= 64) {
     // the common case (neighbour limits are <= 40): rank every key against all others -- keys are unique, so the rank
     // is its sorted position -- instead of a shared-memory bitonic network (21 synchronised passes for 64 keys)
     __syncwarp();

@@ -440,4 +440,5 @@ def training_step(model, ref_points, src_points, transform, optimizer=None, worl
     nbytes = allreduce_gradients(params, world_size)
     if optimizer is not None:
         optimizer.step()
-    return {'loss': float(loss), 'c_loss': float(c_loss), 'f_loss': float(f_loss), 'grad_bytes': nbytes}
+    return {'loss': float(loss.detach()), 'c_loss': float(c_loss.detach()), 'f_loss': float(f_loss.detach()),
+            'grad_bytes': nbytes}
