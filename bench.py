@@ -386,6 +386,7 @@ def measure_train(args, world, rank, dev, steps=None, warmup=None):
     steps = steps or max(2, min(args.steps, 5))
     warmup = warmup if warmup is not None else 2
     cfg = make_cfg("se3eti.3dmatch")
+    TR.RECOMPUTE['autocast'] = torch.bfloat16   # configs[4]: bf16 (operands; statistics, losses and the optimizer stay fp32)
     torch.manual_seed(0)
     model = create_model(cfg).to(dev).train()
     params = TR.trainable_parameters(model)
@@ -423,7 +424,7 @@ def measure_train(args, world, rank, dev, steps=None, warmup=None):
             "config": {"workload": "SE3ET-I 3dmatch-shaped training step (%s)" % WORKLOADS["train"][3],
                        "variant": "se3eti.3dmatch", "pairs_per_gpu_per_step": 1,
                        "parallelism": "data parallel over %d GPU(s), one flattened gradient all-reduce per step" % world,
-                       "backward": "recompute through ATen (se3et_b200/training.py); forward on the CUDA path"},
+                       "backward": "recompute through ATen under bf16 autocast (se3et_b200/training.py); forward on the CUDA path"},
             "grad_allreduce_bytes_per_step": int(last["grad_bytes"]) if last else 0, "parameters": int(nparam),
             "last_loss": last["loss"] if last else None}
 

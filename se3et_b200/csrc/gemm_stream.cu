@@ -190,8 +190,8 @@ gemm_stream_gnapply_kernel(const __grid_constant__ CUtensorMap tma_a1, const __g
       const int64_t wfirst = (int64_t)mt * kSBM + lg * 32;
       const int64_t row = wfirst + lane;
       const bool row_ok = row < args.M;
-      const bool warp_ok = wfirst < args.M;
       const int n0 = nt * kSBN + ch * 32;
+      const bool warp_ok = wfirst < args.M && n0 < args.N;
       bool uniform = true;
       const float4* row_tab = args.tab;
       if (warp_ok) {
@@ -310,7 +310,9 @@ static bool g_stream_enabled = true;
 static bool g_stream_plain = true;
 
 bool gemm_stream_supported(int64_t n, int64_t k1, int64_t k2, int64_t ldc) {
-  return g_stream_enabled && n % kSBN == 0 && k1 % 8 == 0 && k2 % 8 == 0 && ldc % 8 == 0;
+  // n = 32 (mod 64): the last column tile is half empty (TMA zero-fills the missing weight rows, its second four
+  // epilogue warps idle) -- still far better than the one-tile-per-CTA kernel for the 64 -> 32 / 128 -> 32 unary blocks
+  return g_stream_enabled && n % 32 == 0 && k1 % 8 == 0 && k2 % 8 == 0 && ldc % 8 == 0;
 }
 
 size_t gemm_stream_workspace_bytes(int64_t n, int64_t nseg) { return sizeof(float4) * (size_t)n * (size_t)nseg; }
@@ -323,7 +325,7 @@ int gemm_stream_gnapply(const void* a1, int64_t lda1, const void* b1, int64_t ld
   if (!workspace || workspace_bytes < gemm_stream_workspace_bytes(n, nseg) ||
       (reinterpret_cast<uintptr_t>(workspace) & 15) || nseg > 65535)
     return SE3ET_ERR_WORKSPACE;
-  if ((int64_t)ceil_div(m, kSBM) * (n / kSBN) > INT32_MAX) return SE3ET_ERR_UNSUPPORTED;
+  if ((int64_t)ceil_div(m, kSBM) * ceil_div(n, kSBN) > INT32_MAX) return SE3ET_ERR_UNSUPPORTED;
   const bool dual = k2 > 0;
   CUtensorMap ta1, tb1, ta2, tb2;
   int rc = make_tmap_bf16_2d(&ta1, a1, m, k1, lda1, kSBM);
@@ -341,7 +343,7 @@ int gemm_stream_gnapply(const void* a1, int64_t lda1, const void* b1, int64_t ld
   StreamArgs args;
   args.M = (int)m; args.N = (int)n; args.K1 = (int)k1; args.K2 = (int)k2;
   args.m_tiles = (int)ceil_div(m, kSBM);
-  args.n_tiles = (int)(n / kSBN);
+  args.n_tiles = (int)ceil_div(n, kSBN);
   args.out = static_cast<__nv_bfloat16*>(out);
   args.resid = static_cast<const __nv_bfloat16*>(resid);
   args.ldc = ldc;
@@ -378,7 +380,7 @@ int gemm_stream_plain(const void* a, int64_t lda, const void* b, int64_t ldb, in
   StreamArgs args;
   args.M = (int)m; args.N = (int)n; args.K1 = (int)k; args.K2 = 0;
   args.m_tiles = (int)ceil_div(m, kSBM);
-  args.n_tiles = (int)(n / kSBN);
+  args.n_tiles = (int)ceil_div(n, kSBN);
   args.out = static_cast<__nv_bfloat16*>(out);
   args.resid = nullptr;
   args.ldc = ldc;

@@ -35,14 +35,43 @@ def _leaky(x):
     return F.leaky_relu(x, 0.1)
 
 
+# dtype of the matrix products of the backward recomputation: None = fp32 (what the gradient-parity test checks);
+# torch.bfloat16 = the precision the CUDA forward runs in (bf16 operands, fp32 accumulation; statistics stay fp32)
+RECOMPUTE = {'autocast': None}
+
+
 def _group_norm(x, gn):
     """GroupNormEPN / GroupNorm (blocks_epn.py:684-701): statistics over all rows (points x anchors) of a group."""
+    x = x.float()
     shape, c, g = x.shape, x.shape[-1], gn.num_groups
     y = x.reshape(-1, g, c // g)
     mean = y.mean(dim=(0, 2), keepdim=True)
     var = y.var(dim=(0, 2), unbiased=False, keepdim=True)
     y = ((y - mean) * torch.rsqrt(var + gn.eps)).reshape(shape)
     return y * gn.weight + gn.bias
+
+
+class _GatherRows(torch.autograd.Function):
+    """x[idx] with an atomic scatter-add backward (index_add_): autograd's own backward of advanced indexing sorts the
+    indices and serialises duplicates -- with ~38 references per support row it took 90 % of the first version's step."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        ctx.save_for_backward(idx)
+        ctx.rows = x.shape[0]
+        return x[idx]
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        flat = g.reshape((idx.numel(),) + g.shape[idx.dim():])
+        out = flat.new_zeros((ctx.rows,) + flat.shape[1:])
+        out.index_add_(0, idx.reshape(-1), flat)
+        return out, None
+
+
+def gather_rows(x, idx):
+    return _GatherRows.apply(x, idx)
 
 
 def _kpconv(conv, q_pts, s_pts, idx, x):
@@ -52,7 +81,7 @@ def _kpconv(conv, q_pts, s_pts, idx, x):
     rel = s_pad[idx] - q_pts[:, None, :]                                                     # (P, H, 3)
     dist = torch.sqrt(((rel[:, :, None, :] - conv.kernel_points[None, None]) ** 2).sum(-1))   # (P, H, K)
     infl = torch.clamp(1.0 - dist / conv.KP_extent, min=0.0)
-    wf = torch.einsum("pnac,pnk->kpac", x_pad[idx], infl)                                     # (K, P, A, Cin)
+    wf = torch.einsum("pnac,pnk->kpac", gather_rows(x_pad, idx), infl)                        # (K, P, A, Cin)
     kidx, ridx = conv.kidx_rot[:, 0, :], conv.ridx_rot[0]                                     # (K, R), (A, R)
     w_eff = conv.weights[kidx[:, None, :], ridx[None, :, :]]                                  # (K, A, R, Cin, Cout)
     return torch.einsum("kpac,karcd->prd", wf, w_eff)
@@ -77,7 +106,7 @@ def _resnet(m, x, q_pts, s_pts, idx):
     y = _leaky(_group_norm(_interso3(m.interso3, y, q_pts, s_pts, idx), m.norm.norm))
     y = _unary_epn(m.unary2, y, relu=False)
     if 'strided' in m.block_name:
-        skip = torch.cat([skip, torch.zeros_like(skip[:1])], 0)[idx].amax(dim=1)
+        skip = gather_rows(torch.cat([skip, torch.zeros_like(skip[:1])], 0), idx).amax(dim=1)
     if isinstance(m.skip_conv, ME.UnaryBlockEPN):
         skip = _unary_epn(m.skip_conv, skip, relu=False)
     return _leaky(y + skip)
@@ -100,7 +129,7 @@ def aten_backbone(bb, feats, dd):
     latent = inv[bb.num_stages]
     for s in range(bb.num_stages - 1, 1, -1):
         lat_pad = torch.cat([latent, torch.zeros_like(latent[:1])], 0)
-        latent = torch.cat([lat_pad[up[s - 1][:, 0]], inv[s]], dim=1)
+        latent = torch.cat([gather_rows(lat_pad, up[s - 1][:, 0].contiguous()), inv[s]], dim=1)
         dec = getattr(bb, 'decoder%d' % s)
         latent = F.linear(latent, dec.mlp.weight, dec.mlp.bias)
         if hasattr(dec, 'norm'):
@@ -238,12 +267,13 @@ class _CoarsePath(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_ref, g_src, g_f):
         model, dd, n_ref = ctx.model, ctx.dd, ctx.n_ref
-        with torch.enable_grad():
+        ac = RECOMPUTE['autocast']
+        with torch.enable_grad(), torch.autocast('cuda', dtype=ac or torch.bfloat16, enabled=ac is not None):
             feats = torch.ones((dd['points'][0].shape[0], 1), dtype=torch.float32, device=g_ref.device)
             fl = aten_backbone(model.backbone, feats, dd)
             both = aten_transformer(model.transformer, dd['points'][-1], fl[-1], n_ref)
-            normed = F.normalize(both, p=2, dim=1)
-            outs = [normed[:n_ref], normed[n_ref:], fl[0]]
+            normed = F.normalize(both.float(), p=2, dim=1)
+            outs = [normed[:n_ref], normed[n_ref:], fl[0].float()]
             grads_out = [g_ref, g_src, g_f]
             live = [p for p in ctx.params if p.requires_grad]
             grads = torch.autograd.grad(outs, live, grads_out, allow_unused=True)
@@ -428,7 +458,8 @@ def training_step(model, ref_points, src_points, transform, optimizer=None, worl
     # fine stage on the ground-truth patch pairs (model.py:175-205 of the reference, training branch)
     ref_ff = torch.cat([feats_f[:n_ref_f], torch.zeros_like(feats_f[:1])])
     src_ff = torch.cat([feats_f[n_ref_f:], torch.zeros_like(feats_f[:1])])
-    scores = torch.einsum('bnd,bmd->bnm', ref_ff[rk[t_ref]], src_ff[sk[t_src]]) / feats_f.shape[1] ** 0.5
+    scores = torch.einsum('bnd,bmd->bnm', gather_rows(ref_ff, rk[t_ref]), gather_rows(src_ff, sk[t_src])) / \
+        feats_f.shape[1] ** 0.5
     ms = _OptimalTransport.apply(scores, model.optimal_transport.alpha, model.optimal_transport.num_iterations,
                                  rkm[t_ref], skm[t_src])
     f_loss = fine_matching_loss(ms, ref_f_pad[rk[t_ref]], src_f_pad[sk[t_src]], rkm[t_ref], skm[t_src], tr, cfg)
