@@ -213,7 +213,8 @@ int se3et_kpconv_gather(const float* q_pts, const float* s_pts, const int64_t* n
  * The gathered operand is built per 16-point tile in shared memory (mma.sync on the 16-row basis of the
  * octahedral index tables) and contracted by tcgen05 tensor cores with fp32 accumulation in TMEM; it never
  * touches global memory.
- *   x_bf16  [ns, 6, cin] bf16;  out_f32 [nq * 6, cout] fp32 (pre-norm, as KPConvInterSO3 returns it)
+ *   x_bf16  [ns, 6, cin] bf16;  out [nq * 6, cout] fp32 (pre-norm, as KPConvInterSO3 returns it), or bf16 when
+ *           out_bf16 != 0 (the model's inference path: the GroupNorm passes that follow read half the bytes)
  *   w_bf16  [cout, 36 * cin] bf16, K-major, K index = (chunk * 36 + kc * 6 + a') * 16 + c for input channel
  *           chunk * 16 + c of weights[kc][a'][.][d]  (se3et_b200/modules/e2pn.py:KPConvInterSO3._w_fused)
  *   stats   optional double [nseg, groups, 2]: GroupNorm sums of the output per pair (zeroed by the call)
@@ -221,7 +222,7 @@ int se3et_kpconv_gather(const float* q_pts, const float* s_pts, const int64_t* n
  * SE3ET_ERR_UNSUPPORTED and the host uses se3et_kpconv_gather + se3et_gemm_bf16(_gnstats). */
 int se3et_kpconv_fused(const float* q_pts, const float* s_pts, const int64_t* neighbors, int64_t nq, int64_t ns,
                        int64_t h, const void* x_bf16, int64_t cin, const void* w_bf16, int64_t cout,
-                       const float* kernel_points_15x3, float kp_extent, float* out_f32, double* stats,
+                       const float* kernel_points_15x3, float kp_extent, void* out, int out_bf16, double* stats,
                        const int64_t* seg_offsets, int64_t nseg, int64_t groups, se3et_stream_t stream);
 
 /* kpconv_rows -- the whole KPConvInterSO3.forward (blocks_epn.py:454-546, 334-390) in one kernel, UMMA rows = query
@@ -229,7 +230,7 @@ int se3et_kpconv_fused(const float* q_pts, const float* s_pts, const int64_t* ne
  * points are stored once in shared memory and the 36 (output anchor r, class kc) K = 16 tcgen05.mma pick their basis
  * slab and their weight slice W[kc][ridx[a][r]] by descriptor; accumulators: 6 x 32 / 64 fp32 columns of TMEM per point,
  * the basis weights of the tile's points are parked in the remaining TMEM columns.
- *   x_bf16  [ns, 6, cin] bf16;  out_f32 [nq * 6, cout] fp32 (pre-norm, as KPConvInterSO3 returns it)
+ *   x_bf16  [ns, 6, cin] bf16;  out [nq * 6, cout] fp32 (pre-norm, as KPConvInterSO3 returns it) or bf16 (out_bf16 != 0)
  *   w_rows_bf16 [cout, 216 * cin] bf16, K-major, K index = (((chunk * 6 + a) * 36 + r * 6 + kc) * 16 + c'),
  *           value weights[kc][ridx[a][r]][chunk * 16 + (c' ^ 8 * flip[r * 6 + kc])][d]; the slot / flip tables come
  *           from se3et_kpconv_rows_layout (se3et_b200/modules/e2pn.py:KPConvInterSO3._w_rows)
@@ -238,7 +239,7 @@ int se3et_kpconv_fused(const float* q_pts, const float* s_pts, const int64_t* ne
  * row is row 0, which must be finite). */
 int se3et_kpconv_rows(const float* q_pts, const float* s_pts, const int64_t* neighbors, int64_t nq, int64_t ns,
                       int64_t h, const void* x_bf16, int64_t cin, const void* w_rows_bf16, int64_t cout,
-                      const float* kernel_points_15x3, float kp_extent, float* out_f32, se3et_stream_t stream);
+                      const float* kernel_points_15x3, float kp_extent, void* out, int out_bf16, se3et_stream_t stream);
 
 /* Weight layout tables of se3et_kpconv_rows: src_slot[a][r * 6 + kc] = kc * 6 + ridx[a][r] (the weights[kc][a'] slice
  * step a needs for (r, kc)); flip[r * 6 + kc] = 1 when that slice's two 8-channel halves are stored swapped. */
@@ -254,6 +255,21 @@ int se3et_kpconv_cin1(const float* q_pts, const float* s_pts, const int64_t* nei
                       int64_t h, const void* x_bf16, const float* w_36xcout, int64_t cout,
                       const float* kernel_points_15x3, float kp_extent, float* out_f32, double* stats,
                       const int64_t* seg_offsets, int64_t nseg, int64_t groups, int lifted, se3et_stream_t stream);
+
+/* kpconv_lift -- the lifted first layer (se3et_kpconv_cin1 with lifted = 1) rebuilt around a thread per query point:
+ * KPConvInterSO3.forward (blocks_epn.py:454-546, 334-390) on the LiftBlockEPN output (blocks_epn.py:993-1004), whose
+ * value f[ns] (bf16) is the same for the six anchors.  16 basis products per point in registers, then
+ * out[p][(r, d)] = D[p][0..15] x Bm[16][6 * cout] on mma.sync (bf16 hi + lo operands, fp32-grade result).
+ *   out       [nq * 6, cout] fp32, or bf16 when out_bf16 != 0 (the statistics are taken before the rounding)
+ *   stats     optional double [nseg, groups, 2] as for se3et_kpconv_fused
+ *   workspace se3et_kpconv_lift_workspace_bytes(ns): the support points packed as {x, y, z, f}
+ * cout 32 or 64, h <= 48, ns < 2^31; otherwise SE3ET_ERR_UNSUPPORTED (the host uses se3et_kpconv_cin1). */
+int64_t se3et_kpconv_lift_workspace_bytes(int64_t ns);
+int se3et_kpconv_lift(const float* q_pts, const float* s_pts, const int64_t* neighbors, int64_t nq, int64_t ns,
+                      int64_t h, const void* f_bf16, const float* w_36xcout, int64_t cout,
+                      const float* kernel_points_15x3, float kp_extent, void* out, int out_bf16, double* stats,
+                      const int64_t* seg_offsets, int64_t nseg, int64_t groups, void* workspace,
+                      int64_t workspace_bytes, se3et_stream_t stream);
 
 /* Diagnostics: {registers, static smem bytes, max threads per block, local bytes, max dynamic smem} of the fused
  * kernel instantiation for output tile width bn (16, 32, 64 or 128). */
@@ -275,8 +291,9 @@ int se3et_groupnorm_apply(const float* ya, const double* stats_a, const float* g
  *   f = LeakyReLU(GN_1(y)), out = LeakyReLU(GN_2(f)).   apply = 0: accumulate the statistics of f into stats2
  * (zeroed by the call); apply = 1: recompute f and write out_bf16 using stats2; apply = 2: accumulate the statistics of
  * y itself into stats2 (stats1 / gamma / beta unused) -- the first norm's statistics as a streaming pass.
+ * y is fp32 [rows, channels], or bf16 when y_bf16 != 0 (what the conv kernels write with out_bf16).
  * channels / 4 a power of two <= 256. */
-int se3et_groupnorm_double(const float* y, const double* stats1, const float* gamma1, const float* beta1,
+int se3et_groupnorm_double(const void* y, int y_bf16, const double* stats1, const float* gamma1, const float* beta1,
                            double* stats2, const float* gamma2, const float* beta2, int64_t rows, int64_t channels,
                            int64_t groups, const int64_t* seg_offsets, int64_t nseg, int64_t rows_per_point, float eps,
                            float leaky_slope, int apply, void* out_bf16, se3et_stream_t stream);

@@ -307,8 +307,29 @@ __global__ void __launch_bounds__(256) groupnorm_apply_rows_kernel(NormSide a, N
 // kMode 1 (pass B): recomputes f and writes out (bf16)
 // kMode 2         : statistics of y itself into stats2 (the first norm's statistics, for producers whose epilogue
 //                   does not deliver them: cheaper here, as a streaming pass, than on the fused KPConv's critical path)
-template <int kMode>
-__global__ void __launch_bounds__(256) groupnorm_double_kernel(NormSide a, NormSide b2, double* __restrict__ stats2_acc,
+// kBf16: y is bf16 (the inference path's conv kernels write their pre-norm output in bf16: half the bytes of all three
+// passes); a thread then owns eight columns, so that every load stays 16 bytes wide.
+// Per-thread constants of one GroupNorm for N columns in the folded form  y * s + t  (t = beta - mean * s).
+template <int N>
+struct NormColsN {
+  float s[N], t[N];
+};
+template <int N>
+__device__ __forceinline__ void load_norm_cols_n(const NormSide& n, int seg, int G, int cpg, int c0, double cnt,
+                                                 float eps, NormColsN<N>& o) {
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const int g = (c0 + j) / cpg;
+    const double mean = n.stats[((int64_t)seg * G + g) * 2] / cnt;
+    const double var = n.stats[((int64_t)seg * G + g) * 2 + 1] / cnt - mean * mean;
+    const float rstd = rsqrtf((float)fmax(var, 0.0) + eps);
+    o.s[j] = rstd * n.gamma[c0 + j];
+    o.t[j] = (float)((double)n.beta[c0 + j] - mean * (double)o.s[j]);
+  }
+}
+
+template <int kMode, bool kBf16>
+__global__ void __launch_bounds__(256, 3) groupnorm_double_kernel(NormSide a, NormSide b2, double* __restrict__ stats2_acc,
                                                                 int64_t rows, int C, int cpg,
                                                                 const int64_t* __restrict__ seg_off, int nseg,
                                                                 int rows_per_point, float eps, float slope,
@@ -316,9 +337,10 @@ __global__ void __launch_bounds__(256) groupnorm_double_kernel(NormSide a, NormS
   // every CTA owns a contiguous range of rows and walks the pairs it intersects one after the other, so the
   // statistics of a pair are reduced inside the CTA (shared-memory atomics) before one set of fp64 atomics
   __shared__ float sh_acc[2 * 256];  // [group][sum, sum sq], G <= 256
-  const int V = C >> 2;
+  constexpr int N = kBf16 ? 8 : 4;   // columns per thread
+  const int V = C / N;
   const int G = C / cpg;
-  const int c0 = (threadIdx.x % V) * 4;
+  const int c0 = (threadIdx.x % V) * N;
   const int rsub = threadIdx.x / V, rstep = blockDim.x / V;
   const int64_t per_cta = (rows + gridDim.x - 1) / gridDim.x;
   const int64_t r0 = (int64_t)blockIdx.x * per_cta, r1 = min(rows, r0 + per_cta);
@@ -331,61 +353,97 @@ __global__ void __launch_bounds__(256) groupnorm_double_kernel(NormSide a, NormS
     const int64_t row1 = min(r1, seg_end);
     const double cnt = (double)(seg_off[seg + 1] - seg_off[seg]) * rows_per_point * cpg;
     constexpr bool kApply = kMode == 1;
-    NormCols n1, n2;
-    if (kMode != 2) load_norm_cols(a, seg, G, cpg, c0, cnt, eps, n1);
-    if (kApply) load_norm_cols(b2, seg, G, cpg, c0, cnt, eps, n2);
-    float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+    NormColsN<N> n1, n2;
+    if (kMode != 2) load_norm_cols_n<N>(a, seg, G, cpg, c0, cnt, eps, n1);
+    float s2b[N];
+    if (kApply) {
+      load_norm_cols_n<N>(b2, seg, G, cpg, c0, cnt, eps, n2);
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        s2b[j] = n2.s[j] * (0.5f * (1.f - slope));
+        n2.s[j] *= 0.5f * (1.f + slope);
+      }
+    }
+    float s[N], ss[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) s[j] = ss[j] = 0.f;
     // four rows per thread and iteration: the loads are issued together (bytes in flight, this kernel is pure streaming)
     constexpr int kU = 4;
     for (int64_t rowb = row0 + rsub; rowb < row1; rowb += (int64_t)kU * rstep) {
-      float4 yv[kU];
+      uint4 yv[kU];
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int64_t row = rowb + (int64_t)u * rstep;
-        if (row < row1) yv[u] = __ldcs(reinterpret_cast<const float4*>(a.y + row * C + c0));
+        if (row < row1) {
+          if (kBf16)
+            yv[u] = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.y) + row * C + c0));
+          else
+            yv[u] = __ldcs(reinterpret_cast<const uint4*>(a.y + row * C + c0));
+        }
       }
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int64_t row = rowb + (int64_t)u * rstep;
         if (row >= row1) continue;
-        const float4 ya = yv[u];
-        float v[4] = {ya.x, ya.y, ya.z, ya.w};
-        if (kMode != 2) {
-          v[0] = (ya.x - n1.mean[0]) * n1.s[0] + n1.beta[0];
-          v[1] = (ya.y - n1.mean[1]) * n1.s[1] + n1.beta[1];
-          v[2] = (ya.z - n1.mean[2]) * n1.s[2] + n1.beta[2];
-          v[3] = (ya.w - n1.mean[3]) * n1.s[3] + n1.beta[3];
+        float v[N];
+        if (kBf16) {
+          v[0] = bf_lo(yv[u].x); v[1] = bf_hi(yv[u].x); v[2] = bf_lo(yv[u].y); v[3] = bf_hi(yv[u].y);
+          v[N - 4] = bf_lo(yv[u].z); v[N - 3] = bf_hi(yv[u].z); v[N - 2] = bf_lo(yv[u].w); v[N - 1] = bf_hi(yv[u].w);
+        } else {
+          v[0] = __uint_as_float(yv[u].x); v[1] = __uint_as_float(yv[u].y);
+          v[2] = __uint_as_float(yv[u].z); v[3] = __uint_as_float(yv[u].w);
+        }
+        // the instruction count per element decides the speed of the bf16 form (half the bytes per element):
+        // LeakyReLU(w) = max(w, slope w) for 0 <= slope <= 1 (checked by the host), and in the apply pass the first
+        // activation is folded into the second norm:  GN_2(LeakyReLU(w)) = s2 (a w + b |w|) + t2,  a, b = (1 +- slope) / 2
+        if (kMode == 0) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) v[j] = v[j] >= 0.f ? v[j] : v[j] * slope;
+          for (int j = 0; j < N; ++j) {
+            const float w = fmaf(v[j], n1.s[j], n1.t[j]);
+            v[j] = fmaxf(w, w * slope);
+          }
         }
         if (!kApply) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < N; ++j) {
             s[j] += v[j];
             ss[j] = fmaf(v[j], v[j], ss[j]);
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float w = (v[j] - n2.mean[j]) * n2.s[j] + n2.beta[j];
-            v[j] = w >= 0.f ? w : w * slope;
+          for (int j = 0; j < N; ++j) {
+            const float w = fmaf(v[j], n1.s[j], n1.t[j]);
+            const float z = fmaf(w, n2.s[j], fmaf(fabsf(w), s2b[j], n2.t[j]));
+            v[j] = fmaxf(z, z * slope);
           }
-          uint2 o;
-          o.x = pack_bf16(v[0], v[1]);
-          o.y = pack_bf16(v[2], v[3]);
-          *reinterpret_cast<uint2*>(out_bf16 + row * C + c0) = o;
+          if (kBf16) {
+            *reinterpret_cast<uint4*>(out_bf16 + row * C + c0) =
+                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[N - 4], v[N - 3]),
+                           pack_bf16(v[N - 2], v[N - 1]));
+          } else {
+            uint2 o;
+            o.x = pack_bf16(v[0], v[1]);
+            o.y = pack_bf16(v[2], v[3]);
+            *reinterpret_cast<uint2*>(out_bf16 + row * C + c0) = o;
+          }
         }
       }
     }
     if (kMode != 1) {
       for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh_acc[i] = 0.f;
       __syncthreads();
-      if (cpg >= 4) {  // the four columns share one group
-        atomicAdd(&sh_acc[2 * (c0 / cpg)], (s[0] + s[1]) + (s[2] + s[3]));
-        atomicAdd(&sh_acc[2 * (c0 / cpg) + 1], (ss[0] + ss[1]) + (ss[2] + ss[3]));
+      if (cpg >= N) {  // the thread's columns share one group
+        float ts = 0.f, tss = 0.f;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          ts += s[j];
+          tss += ss[j];
+        }
+        atomicAdd(&sh_acc[2 * (c0 / cpg)], ts);
+        atomicAdd(&sh_acc[2 * (c0 / cpg) + 1], tss);
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < N; ++j) {
           atomicAdd(&sh_acc[2 * ((c0 + j) / cpg)], s[j]);
           atomicAdd(&sh_acc[2 * ((c0 + j) / cpg) + 1], ss[j]);
         }
@@ -697,7 +755,7 @@ extern "C" int se3et_upsample_concat(const void* x_bf16, int64_t nx, int64_t c1,
   return SE3ET_OK;
 }
 
-extern "C" int se3et_groupnorm_double(const float* y, const double* stats1, const float* gamma1, const float* beta1,
+extern "C" int se3et_groupnorm_double(const void* y_in, int y_bf16, const double* stats1, const float* gamma1, const float* beta1,
                                       double* stats2, const float* gamma2, const float* beta2, int64_t rows,
                                       int64_t channels, int64_t groups, const int64_t* seg_offsets, int64_t nseg,
                                       int64_t rows_per_point, float eps, float leaky_slope, int apply, void* out_bf16,
@@ -707,28 +765,37 @@ extern "C" int se3et_groupnorm_double(const float* y, const double* stats1, cons
     return SE3ET_ERR_ARG;
   const int64_t vecs = channels / 4;
   if (vecs > 256 || (vecs & (vecs - 1)) != 0 || groups > 256) return SE3ET_ERR_UNSUPPORTED;
+  const float* y = static_cast<const float*>(y_in);   // reinterpreted by the kernel when y_bf16
+  if (y_bf16 && (channels % 8 || vecs < 2)) return SE3ET_ERR_UNSUPPORTED;
+  if (!(leaky_slope >= 0.f && leaky_slope <= 1.f)) return SE3ET_ERR_UNSUPPORTED;   // max(w, slope * w) form
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (apply != 1) SE3ET_CUDA_CHECK(cudaMemsetAsync(stats2, 0, sizeof(double) * 2 * nseg * groups, st));
   if (rows == 0) return SE3ET_OK;
   if (apply < 0 || apply > 2) return SE3ET_ERR_ARG;
   if (!y || (apply != 2 && (!stats1 || !gamma1 || !beta1)) || (apply == 1 && (!gamma2 || !beta2 || !out_bf16)))
     return SE3ET_ERR_ARG;
-  int64_t blocks = ceil_div(rows * vecs, 256);
+  int64_t blocks = ceil_div(rows * (y_bf16 ? vecs / 2 : vecs), 256);
   const int64_t cap = (int64_t)kNumSMs * 8;
   if (blocks > cap) blocks = cap;
   NormSide a{y, stats1, gamma1, beta1};
   NormSide b{nullptr, stats2, gamma2, beta2};
   const int cpg = (int)(channels / groups);
+#define SE3ET_GND(MODE, OUT)                                                                                          \
+  do {                                                                                                                \
+    if (y_bf16)                                                                                                       \
+      groupnorm_double_kernel<MODE, true><<<(unsigned)blocks, 256, 0, st>>>(                                          \
+          a, b, stats2, rows, (int)channels, cpg, seg_offsets, (int)nseg, (int)rows_per_point, eps, leaky_slope, OUT); \
+    else                                                                                                              \
+      groupnorm_double_kernel<MODE, false><<<(unsigned)blocks, 256, 0, st>>>(                                         \
+          a, b, stats2, rows, (int)channels, cpg, seg_offsets, (int)nseg, (int)rows_per_point, eps, leaky_slope, OUT); \
+  } while (0)
   if (apply == 1)
-    groupnorm_double_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(
-        a, b, stats2, rows, (int)channels, cpg, seg_offsets, (int)nseg, (int)rows_per_point, eps, leaky_slope,
-        static_cast<__nv_bfloat16*>(out_bf16));
+    SE3ET_GND(1, static_cast<__nv_bfloat16*>(out_bf16));
   else if (apply == 0)
-    groupnorm_double_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(
-        a, b, stats2, rows, (int)channels, cpg, seg_offsets, (int)nseg, (int)rows_per_point, eps, leaky_slope, nullptr);
+    SE3ET_GND(0, nullptr);
   else
-    groupnorm_double_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(
-        a, b, stats2, rows, (int)channels, cpg, seg_offsets, (int)nseg, (int)rows_per_point, eps, leaky_slope, nullptr);
+    SE3ET_GND(2, nullptr);
+#undef SE3ET_GND
   SE3ET_LAUNCH_CHECK();
   return SE3ET_OK;
 }

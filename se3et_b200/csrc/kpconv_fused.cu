@@ -59,6 +59,7 @@ struct FusedArgs {
   const __nv_bfloat16* x;
   const float* kernel_points;
   float* out;                 // fp32 [nq * 6, cout]
+  __nv_bfloat16* out_bf16;    // or bf16, same shape (exactly one of the two is set)
   int64_t nq, ns;
   int H, HR;                  // neighbour columns; rows per ring stage (one half, rounded up to 8)
   int cin, cout;
@@ -392,10 +393,18 @@ kpconv_fused_kernel(const __grid_constant__ CUtensorMap tma_w, FusedArgs args) {
             gn_accumulate_chunk<kCols>(cpg, v, row_ok, gn_uniform, lane, warp_acc, g_loc, gn_row_stats, g_glob);
           }
           if (row_ok) {
-            float4* dst = reinterpret_cast<float4*>(args.out + grow * args.cout + n0 + c0);
+            if (args.out_bf16) {
+              uint4* dst = reinterpret_cast<uint4*>(args.out_bf16 + grow * args.cout + n0 + c0);
 #pragma unroll
-            for (int jj = 0; jj < kCols / 4; ++jj)
-              dst[jj] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+              for (int jj = 0; jj < kCols / 8; ++jj)
+                dst[jj] = make_uint4(kpm::pack2(v[8 * jj], v[8 * jj + 1]), kpm::pack2(v[8 * jj + 2], v[8 * jj + 3]),
+                                     kpm::pack2(v[8 * jj + 4], v[8 * jj + 5]), kpm::pack2(v[8 * jj + 6], v[8 * jj + 7]));
+            } else {
+              float4* dst = reinterpret_cast<float4*>(args.out + grow * args.cout + n0 + c0);
+#pragma unroll
+              for (int jj = 0; jj < kCols / 4; ++jj)
+                dst[jj] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+            }
           }
         }
         tc::tcgen05_fence_before_sync();
@@ -486,19 +495,22 @@ using namespace se3et;
 
 extern "C" int se3et_kpconv_fused(const float* q_pts, const float* s_pts, const int64_t* neighbors, int64_t nq,
                                   int64_t ns, int64_t h, const void* x_bf16, int64_t cin, const void* w_bf16,
-                                  int64_t cout, const float* kernel_points_15x3, float kp_extent, float* out_f32,
-                                  double* stats, const int64_t* seg_offsets, int64_t nseg, int64_t groups,
-                                  se3et_stream_t stream) {
+                                  int64_t cout, const float* kernel_points_15x3, float kp_extent, void* out,
+                                  int out_bf16, double* stats, const int64_t* seg_offsets, int64_t nseg,
+                                  int64_t groups, se3et_stream_t stream) {
   if (nq < 0 || ns <= 0 || h <= 0 || cin <= 0 || cout <= 0 || !(kp_extent > 0.f)) return SE3ET_ERR_ARG;
   if (h > 2 * kFKS * 16 || cin % kChunk != 0 || cout % 16 != 0) return SE3ET_ERR_UNSUPPORTED;
   int bn = 0;
   for (int c : {128, 64, 32, 16})
     if (cout % c == 0) { bn = c; break; }
-  if (!q_pts || !s_pts || !neighbors || !x_bf16 || !w_bf16 || !kernel_points_15x3 || !out_f32) return SE3ET_ERR_ARG;
+  if (!q_pts || !s_pts || !neighbors || !x_bf16 || !w_bf16 || !kernel_points_15x3 || !out) return SE3ET_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   FusedArgs a;
   a.q_pts = q_pts; a.s_pts = s_pts; a.idx = neighbors; a.x = static_cast<const __nv_bfloat16*>(x_bf16);
-  a.kernel_points = kernel_points_15x3; a.out = out_f32; a.nq = nq; a.ns = ns; a.H = (int)h;
+  a.kernel_points = kernel_points_15x3; a.nq = nq;
+  a.out = out_bf16 ? nullptr : static_cast<float*>(out);
+  a.out_bf16 = out_bf16 ? static_cast<__nv_bfloat16*>(out) : nullptr;
+  a.ns = ns; a.H = (int)h;
   const bool halves = h > kFKS * 16;   // two neighbour halves per (chunk, anchor)
   a.HR = halves ? (((int)h + 1) / 2 + 7) / 8 * 8 : ((int)h + 7) / 8 * 8;
   if (a.HR < 16) a.HR = 16;  // the per-warp ring doubles as the W16 scratch (16 x 112 bytes)

@@ -36,7 +36,12 @@ constexpr int kThreads = (kProdWarps + 2) * 32;
 constexpr int kSubTile = 128 * 128;      // [128 rows][4 basis rows x 16 channels] bf16
 constexpr int kBBuf = 4 * kSubTile;      // operand of one step
 constexpr int kXRow = 32;                // bytes per gathered row (16 channels)
-constexpr int kXStages = 3;
+#ifndef SE3ET_ROWS_XS32
+#define SE3ET_ROWS_XS32 3   // measured on B200: a fourth gather stage changes nothing (1.538 vs 1.532 ms at level 0)
+#endif
+#ifndef SE3ET_ROWS_FRAG_PREFETCH
+#define SE3ET_ROWS_FRAG_PREFETCH 1
+#endif
 constexpr int kWMaxStages = 12;
 constexpr int kW16Row = 112;             // scratch row pitch (bytes): 48 neighbours + 8 pad, conflict-free ldmatrix
 
@@ -183,6 +188,7 @@ struct Args {
   const __nv_bfloat16* x;
   const float* kernel_points;
   float* out;  // fp32 [nq * 6, cout]
+  __nv_bfloat16* out_bf16;  // or bf16, same shape (exactly one of the two is set)
   int64_t nq, ns;
   int H;
   int cin, cout;
@@ -196,7 +202,9 @@ struct Smem {
   static constexpr int kXStage = kHR * kXRow;
   static constexpr int kBOff = 0;
   static constexpr int kXOff = 2 * kBBuf;
-  static constexpr int kXBytes = kProdWarps * kXStages * kXStage;
+  // gather ring stages per producer warp: the 32-column kernels have the shared memory for a fourth one
+  static constexpr int kXS = BN == 32 ? SE3ET_ROWS_XS32 : 3;
+  static constexpr int kXBytes = kProdWarps * kXS * kXStage;
   static constexpr int kBarOff = kXOff + kXBytes;                       // 512 B of barriers
   static constexpr int kKpOff = kBarOff + 512;                          // 15 x float4
   static constexpr int kWOff = (kKpOff + 256 + 1023) / 1024 * 1024;
@@ -221,7 +229,9 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
   constexpr int kStash = TP * FR;         // stash columns per producer warp
   constexpr int kAccCols = 6 * BN;
   static_assert(kAccCols + 4 * kStash <= 512, "tensor memory over-subscribed");
-  static_assert(kW16Row * 16 <= kXStages * S::kXStage, "W16 scratch must fit the gather ring");
+  constexpr int XS = S::kXS, PF = XS - 1;   // ring stages, items the gather runs ahead
+  static_assert(kW16Row * 16 <= XS * S::kXStage, "W16 scratch must fit the gather ring");
+  static_assert((3 * PPW) % XS == 0 && PPW >= PF, "ring stage of item (step, i) must be a compile-time constant");
   constexpr int kTilePts = 16 * PPW * CL;
   static_assert(kTilePts <= 128 && (CL == 1 || kTilePts == 128), "a cluster shares one full 128-row tile");
   static_assert(CL == 1 || WM == 1, "one kind of cluster at a time");
@@ -289,7 +299,7 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
 
   if (warp < kProdWarps) {
     // =========================================== producers ===================================================
-    uint8_t* xs = smem + S::kXOff + warp * kXStages * kXStage;
+    uint8_t* xs = smem + S::kXOff + warp * XS * kXStage;
     const uint32_t xs_s = smem_addr(xs);
     const int H = args.H;
     const uint32_t row_chunks = (uint32_t)(kA * args.cin / 8);  // 16-byte units per support row
@@ -451,19 +461,34 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
       }
     };
 
+    uint32_t frag_a[FR], frag_b[FR];
+    auto load_stash = [&](int i, uint32_t (&dst)[FR]) {
+      const uint32_t ta = stash + (uint32_t)((i - RP) * FR);
+      if (FR >= 8) {
+        tmem_ld8(ta, dst);
+        if (FR == 12) tmem_ld4(ta + 8, dst + 8);
+        if (FR == 10) tmem_ld2(ta + 8, dst[8], dst[9]);
+      } else {
+        tmem_ld4(ta, dst);
+        tmem_ld4(ta + 4, dst + 4);
+      }
+    };
+
     uint32_t gstep = 0;   // steps produced so far (all tiles)
     // rotated tile loop (one call site per phase): production(t), setup(t + 1), epilogue(t)
     for (int64_t tile = tile0 - tile_stride, titer = -1;; tile += tile_stride, ++titer) {
       const bool have = titer >= 0;
       const bool have_next = WM > 1 ? titer + 1 < nrounds : tile + tile_stride < ntiles;
       if (have) {
-      // items (step, point) in order; the ring runs two items ahead
+      if (SE3ET_ROWS_FRAG_PREFETCH && RP == 0) load_stash(0, frag_a);   // point 0's fragments (later ones: one item ahead)
+      // items (step, point) in order; the ring runs PF items ahead
       {
         const uint8_t* b0 = step_base(0);
-        issue(b0, 0, 0);
-        cp_async_commit();
-        issue(b0, 1, 1);
-        cp_async_commit();
+#pragma unroll
+        for (int j = 0; j < PF; ++j) {
+          issue(b0, j, j);
+          cp_async_commit();
+        }
       }
       // three steps per trip: the ring stage of item (step, i) is then a compile-time constant (nsteps = 6 chunks)
 #pragma unroll 1
@@ -477,43 +502,34 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
         const uint32_t st_base = st_off + buf * kBBuf;
 #pragma unroll
         for (int i = 0; i < PPW; ++i) {
-          {  // prefetch the item two ahead
-            const int i2 = (i + 2) % PPW;
-            const uint8_t* b2 = i + 2 < PPW ? base : base_next;
-            const int stage = (s3 * PPW + i) % kXStages;
-            const int st2 = (stage + 2) % kXStages;
+          {  // prefetch the item PF ahead
+            const int i2 = (i + PF) % PPW;
+            const uint8_t* b2 = i + PF < PPW ? base : base_next;
+            const int stage = (s3 * PPW + i) % XS;
+            const int st2 = (stage + PF) % XS;
             if (b2) issue(b2, i2, st2);
             cp_async_commit();
           }
-          uint32_t fr[FR];
+          // basis fragments of point i: registers, or the tensor-memory stash -- loaded one item ahead into the other
+          // of two register sets (PPW is even, so the parity of i names the set in every step)
+          uint32_t (&fr)[FR] = (i & 1) ? frag_b : frag_a;
+          uint32_t (&fr_next)[FR] = (i & 1) ? frag_a : frag_b;
           if (i < RP) {
 #pragma unroll
             for (int f = 0; f < FR; ++f) fr[f] = afrag[i < RP ? i : 0][f];
-          } else {
-            const uint32_t ta = stash + (uint32_t)((i - RP) * FR);
-#ifdef SE3ET_ROWS_NOSTASH
-#pragma unroll
-            for (int f = 0; f < FR; ++f) fr[f] = goff[i][f % NU];
-#else
-            if (FR >= 8) {
-              tmem_ld8(ta, fr);
-              if (FR == 12) tmem_ld4(ta + 8, fr + 8);
-              if (FR == 10) tmem_ld2(ta + 8, fr[8], fr[9]);
-            } else {
-              tmem_ld4(ta, fr);
-              tmem_ld4(ta + 4, fr + 4);
-            }
-#endif
+          } else if (!SE3ET_ROWS_FRAG_PREFETCH) {
+            load_stash(i, fr);
           }
-          cp_async_wait<2>();
+          if (i >= RP) tc::tmem_ld_wait();
+          if (SE3ET_ROWS_FRAG_PREFETCH && (i + 1) % PPW >= RP) load_stash((i + 1) % PPW, fr_next);
+          cp_async_wait<PF>();
           __syncwarp();
           if (i == 0) {
             // the MMAs of the step before last have consumed this operand buffer
             tc::mbar_wait_long(&b_empty[buf], ((gstep >> 1) & 1u) ^ 1u);
           }
-          if (i >= RP) tc::tmem_ld_wait();
           float d[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-          const uint32_t xsb = xs_s + ((s3 * PPW + i) % kXStages) * kXStage;
+          const uint32_t xsb = xs_s + ((s3 * PPW + i) % XS) * kXStage;
 #ifndef SE3ET_ROWS_NOLDSM
 #pragma unroll
           for (int ks = 0; ks < KH / 2; ++ks) {
@@ -546,6 +562,7 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
       }
       }
         cp_async_wait<0>();
+        if (TP > 0) tc::tmem_ld_wait();   // the last prefetched fragments: the stash is rewritten by the next tile's setup
         __syncwarp();
       }
       // the next tile's basis weights are built under this tile's last MMAs
@@ -566,11 +583,22 @@ kpconv_rows_kernel(const __grid_constant__ CUtensorMap tma_w, Args args) {
           tc::tmem_ld_wait();
           if (row_ok) {
             const int r = c0 / BN, dcol = c0 - r * BN;
-            float4* dst = reinterpret_cast<float4*>(args.out + (p * kA + r) * args.cout + n0 + dcol);
+            const int64_t o = (p * kA + r) * args.cout + n0 + dcol;
+            if (args.out_bf16) {
+              uint32_t pk[8];
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-              dst[jj] = make_float4(__uint_as_float(rr[4 * jj]), __uint_as_float(rr[4 * jj + 1]),
-                                    __uint_as_float(rr[4 * jj + 2]), __uint_as_float(rr[4 * jj + 3]));
+              for (int jj = 0; jj < 8; ++jj)
+                pk[jj] = kpm::pack2(__uint_as_float(rr[2 * jj]), __uint_as_float(rr[2 * jj + 1]));
+              uint4* dst = reinterpret_cast<uint4*>(args.out_bf16 + o);
+              dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            } else {
+              float4* dst = reinterpret_cast<float4*>(args.out + o);
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                dst[jj] = make_float4(__uint_as_float(rr[4 * jj]), __uint_as_float(rr[4 * jj + 1]),
+                                      __uint_as_float(rr[4 * jj + 2]), __uint_as_float(rr[4 * jj + 3]));
+            }
           }
         }
         tc::tcgen05_fence_before_sync();
@@ -737,19 +765,22 @@ extern "C" int se3et_kpconv_rows_layout(int32_t* src_slot_6x36, int32_t* flip_36
 
 extern "C" int se3et_kpconv_rows(const float* q_pts, const float* s_pts, const int64_t* neighbors, int64_t nq,
                                  int64_t ns, int64_t h, const void* x_bf16, int64_t cin, const void* w_rows_bf16,
-                                 int64_t cout, const float* kernel_points_15x3, float kp_extent, float* out_f32,
-                                 se3et_stream_t stream) {
+                                 int64_t cout, const float* kernel_points_15x3, float kp_extent, void* out,
+                                 int out_bf16, se3et_stream_t stream) {
   if (nq < 0 || ns <= 0 || h <= 0 || cin <= 0 || cout <= 0 || !(kp_extent > 0.f)) return SE3ET_ERR_ARG;
   if (h > 48 || cin % kpm::kChunk != 0 || cout % 32 != 0) return SE3ET_ERR_UNSUPPORTED;
   if (ns * kA * cin / 8 >= ((int64_t)1 << 32)) return SE3ET_ERR_UNSUPPORTED;  // 32-bit gather offsets (16-byte units)
-  if (!q_pts || !s_pts || !neighbors || !x_bf16 || !w_rows_bf16 || !kernel_points_15x3 || !out_f32) return SE3ET_ERR_ARG;
+  if (!q_pts || !s_pts || !neighbors || !x_bf16 || !w_rows_bf16 || !kernel_points_15x3 || !out) return SE3ET_ERR_ARG;
   if (nq == 0) return SE3ET_OK;
   const int bn = cout % 64 == 0 ? 64 : 32;
   const int kh = h <= 32 ? 4 : (h <= 40 ? 5 : 6);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   rows::Args a;
   a.q_pts = q_pts; a.s_pts = s_pts; a.idx = neighbors; a.x = static_cast<const __nv_bfloat16*>(x_bf16);
-  a.kernel_points = kernel_points_15x3; a.out = out_f32; a.nq = nq; a.ns = ns; a.H = (int)h;
+  a.kernel_points = kernel_points_15x3; a.nq = nq;
+  a.out = out_bf16 ? nullptr : static_cast<float*>(out);
+  a.out_bf16 = out_bf16 ? static_cast<__nv_bfloat16*>(out) : nullptr;
+  a.ns = ns; a.H = (int)h;
   a.cin = (int)cin; a.cout = (int)cout; a.inv_extent = 1.f / kp_extent; a.wstages = 0;
   const void* w = w_rows_bf16;
 #ifndef SE3ET_ROWS_WM

@@ -27,7 +27,11 @@ from . import octahedral
 # 'cin1_kernel': the CUDA-core first-layer kernel (csrc/kpconv.cu) measures slower than gather + GEMM on B200
 # (9.6 vs 8.4 ms per 64 pairs), so it is off by default and only exercised by the tests
 _GFLAGS = {'fused_kpconv': True, 'two_pass_unary': True, 'double_norm': True, 'cin1_kernel': False, 'dual_apply': True, 'lifted_kernel': True, 'conv_stats_stream': True,
-           'rows_kpconv': True, 'rows_max_cout': 128}
+           'rows_kpconv': True, 'rows_max_cout': 128,
+           # pre-norm conv outputs in bf16 between the conv kernel and the double GroupNorm (inference path only)
+           'conv_bf16': True,
+           # the lifted first layer on se3et_kpconv_lift (thread per point + mma.sync) instead of se3et_kpconv_cin1
+           'lift_kernel': True}
 
 
 def _gn_fusable_fused(cout, groups):
@@ -203,13 +207,13 @@ class KPConvInterSO3(nn.Module):
         return _GFLAGS['rows_kpconv'] and neighb_inds.shape[0] > 0 and self.out_channels <= _GFLAGS['rows_max_cout'] \
             and K.kpconv_rows_supported(self.in_channels, self.out_channels, neighb_inds.shape[1], ns)
 
-    def _conv(self, q_pts, s_pts, neighb_inds, x):
-        """fp32 (Nq*6, Cout) by the fused kernels (caller checked _fused_ok)."""
+    def _conv(self, q_pts, s_pts, neighb_inds, x, out_bf16=False):
+        """fp32 (bf16 with out_bf16) (Nq*6, Cout) by the fused kernels (caller checked _fused_ok)."""
         if self._rows_ok(neighb_inds, s_pts.shape[0]):
             return K.kpconv_rows(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), self._w_rows(),
-                                 self.kernel_points, self.KP_extent)
+                                 self.kernel_points, self.KP_extent, out_bf16=out_bf16)
         y, _ = K.kpconv_fused(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), self._w_fused(),
-                              self.kernel_points, self.KP_extent)
+                              self.kernel_points, self.KP_extent, out_bf16=out_bf16)
         return y
 
     def _fused_ok(self, neighb_inds):
@@ -228,14 +232,21 @@ class KPConvInterSO3(nn.Module):
         y, _ = linear_bf16(a, self._w_flat())
         return y.view(-1, self.kanchor, self.out_channels)
 
-    def forward_stats(self, q_pts, s_pts, neighb_inds, x, groups, seg):
-        """forward() plus the per-pair GroupNorm statistics of its output (accumulated in the GEMM epilogue)."""
+    def forward_stats(self, q_pts, s_pts, neighb_inds, x, groups, seg, allow_bf16=False):
+        """forward() plus the per-pair GroupNorm statistics of its output (accumulated in the GEMM epilogue).
+        allow_bf16: the caller (the two back-to-back norms, _conv_double_norm) also reads a bf16 pre-norm tensor; the
+        one-kernel convolutions then write bf16 and the three streaming passes that follow move half the bytes."""
         self._check_tables()
         cin1_ok = neighb_inds.shape[0] > 0 and s_pts.shape[0] > 0 and K.kpconv_cin1_supported(
             self.in_channels, self.out_channels, neighb_inds.shape[1])
         if cin1_ok and _GFLAGS['lifted_kernel'] and x.dim() == 3 and x.stride(1) == 0:
             # LiftBlockEPN output (an expand over the anchor axis): anchor-constant input, 16 products per point
             w36 = self.weights.detach().reshape(36, self.out_channels).float().contiguous()
+            if _GFLAGS['lift_kernel'] and K.kpconv_lift_supported(self.out_channels, neighb_inds.shape[1], s_pts.shape[0]):
+                # round 2: a thread per point + mma.sync for the 16 -> 6 * Cout product (csrc/kpconv_lift.cu)
+                return K.kpconv_lift(q_pts, s_pts, neighb_inds.contiguous(), _act(x[:, 0, 0]).contiguous(), w36,
+                                     self.kernel_points, self.KP_extent, gn=(groups, seg),
+                                     out_bf16=allow_bf16 and _GFLAGS['conv_bf16'])
             return K.kpconv_cin1(q_pts, s_pts, neighb_inds.contiguous(), _act(x[:, 0, 0]).contiguous(), w36,
                                  self.kernel_points, self.KP_extent, gn=(groups, seg), lifted=True)
         if _GFLAGS['cin1_kernel'] and cin1_ok:
@@ -246,7 +257,7 @@ class KPConvInterSO3(nn.Module):
             if _GFLAGS['conv_stats_stream'] and K.groupnorm_double_supported(self.out_channels):
                 # the statistics as a streaming pass over the (small) conv output: in the fused kernel's epilogue they
                 # sit on the producers' critical path (4-10 % of that kernel), here they cost one read of y
-                y = self._conv(q_pts, s_pts, neighb_inds, x)
+                y = self._conv(q_pts, s_pts, neighb_inds, x, out_bf16=allow_bf16 and _GFLAGS['conv_bf16'])
                 return y, K.groupnorm_stats_stream(y, groups, seg, self.kanchor)
             return K.kpconv_fused(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), self._w_fused(),
                                   self.kernel_points, self.KP_extent, gn=(groups, seg))
@@ -348,7 +359,7 @@ def _conv_double_norm(interso3, norm2, x, q_pts, s_pts, neighb_inds, seg):
     c = interso3.out_dim
     if _GFLAGS['double_norm'] and K.groupnorm_double_supported(c) and n1.num_groups == norm2.num_groups and \
             n1.norm.eps == norm2.norm.eps and q_pts.shape[0] > 0:
-        y, stats = interso3.conv.forward_stats(q_pts, s_pts, neighb_inds, x, n1.num_groups, seg)
+        y, stats = interso3.conv.forward_stats(q_pts, s_pts, neighb_inds, x, n1.num_groups, seg, allow_bf16=True)
         return K.groupnorm_double(y.view(-1, c), stats, n1.norm.weight, n1.norm.bias, norm2.norm.weight,
                                   norm2.norm.bias, n1.num_groups, seg, 6, slope=0.1, eps=n1.norm.eps)
     f, _ = interso3.fused(x, q_pts, s_pts, neighb_inds, seg, out_f32=True)

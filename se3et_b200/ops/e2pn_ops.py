@@ -126,10 +126,10 @@ def kpconv_fused_supported(cin, cout, h):
     return stage_rows <= 40 or cout % 128 != 0
 
 
-def kpconv_fused(q_pts, s_pts, neighbors, x_bf16, w_fused, kernel_points, kp_extent, gn=None):
+def kpconv_fused(q_pts, s_pts, neighbors, x_bf16, w_fused, kernel_points, kp_extent, gn=None, out_bf16=False):
     """KPConvInterSO3.forward in one kernel. x (Ns, 6, Cin) bf16, w_fused (Cout, 36*Cin) bf16 in the fused K order.
     gn = (groups, seg_off) additionally returns the per-pair GroupNorm statistics (double (nseg, groups, 2)).
-    -> (fp32 (Nq*6, Cout), stats or None)."""
+    -> (fp32 -- bf16 with out_bf16 -- (Nq*6, Cout), stats or None)."""
     _lib.require_cuda(q_pts, s_pts, neighbors, x_bf16, w_fused, kernel_points)
     assert x_bf16.dtype == torch.bfloat16 and x_bf16.is_contiguous() and x_bf16.dim() == 3 and x_bf16.shape[1] == 6
     assert w_fused.dtype == torch.bfloat16 and w_fused.is_contiguous()
@@ -140,7 +140,7 @@ def kpconv_fused(q_pts, s_pts, neighbors, x_bf16, w_fused, kernel_points, kp_ext
     ns, _, cin = x_bf16.shape
     cout = w_fused.shape[0]
     assert w_fused.shape[1] == 36 * cin and s_pts.shape[0] == ns and q_pts.shape[0] == nq
-    out = torch.empty((nq * 6, cout), dtype=torch.float32, device=x_bf16.device)
+    out = torch.empty((nq * 6, cout), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x_bf16.device)
     stats, seg_off, groups, nseg = None, None, 0, 0
     if gn is not None:
         groups, seg_off = gn
@@ -150,8 +150,8 @@ def kpconv_fused(q_pts, s_pts, neighbors, x_bf16, w_fused, kernel_points, kp_ext
     _lib.check(_lib.lib().se3et_kpconv_fused(
         _lib.ptr(q_pts), _lib.ptr(s_pts), _lib.ptr(neighbors), _lib.i64(nq), _lib.i64(ns), _lib.i64(h),
         _lib.ptr(x_bf16), _lib.i64(cin), _lib.ptr(w_fused), _lib.i64(cout), _lib.ptr(kernel_points),
-        _lib.f32(kp_extent), _lib.ptr(out), _lib.ptr(stats), _lib.ptr(seg_off), _lib.i64(nseg), _lib.i64(groups),
-        _lib.stream_ptr()), "kpconv_fused")
+        _lib.f32(kp_extent), _lib.ptr(out), ctypes.c_int(1 if out_bf16 else 0), _lib.ptr(stats), _lib.ptr(seg_off),
+        _lib.i64(nseg), _lib.i64(groups), _lib.stream_ptr()), "kpconv_fused")
     return out, stats
 
 
@@ -168,9 +168,9 @@ def kpconv_rows_supported(cin, cout, h, ns=0):
     return cin % 16 == 0 and cout % 32 == 0 and h <= 48 and ns * 6 * cin // 8 < (1 << 32)
 
 
-def kpconv_rows(q_pts, s_pts, neighbors, x_bf16, w_rows, kernel_points, kp_extent):
+def kpconv_rows(q_pts, s_pts, neighbors, x_bf16, w_rows, kernel_points, kp_extent, out_bf16=False):
     """KPConvInterSO3.forward in one kernel, UMMA rows = points. x (Ns, 6, Cin) bf16, w_rows (Cout, 216*Cin) bf16 in
-    step order (KPConvInterSO3._w_rows). -> fp32 (Nq*6, Cout)."""
+    step order (KPConvInterSO3._w_rows). -> fp32 (bf16 with out_bf16) (Nq*6, Cout)."""
     _lib.require_cuda(q_pts, s_pts, neighbors, x_bf16, w_rows, kernel_points)
     assert x_bf16.dtype == torch.bfloat16 and x_bf16.is_contiguous() and x_bf16.dim() == 3 and x_bf16.shape[1] == 6
     assert w_rows.dtype == torch.bfloat16 and w_rows.is_contiguous()
@@ -181,11 +181,11 @@ def kpconv_rows(q_pts, s_pts, neighbors, x_bf16, w_rows, kernel_points, kp_exten
     ns, _, cin = x_bf16.shape
     cout = w_rows.shape[0]
     assert w_rows.shape[1] == 216 * cin and s_pts.shape[0] == ns and q_pts.shape[0] == nq
-    out = torch.empty((nq * 6, cout), dtype=torch.float32, device=x_bf16.device)
+    out = torch.empty((nq * 6, cout), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x_bf16.device)
     _lib.check(_lib.lib().se3et_kpconv_rows(
         _lib.ptr(q_pts), _lib.ptr(s_pts), _lib.ptr(neighbors), _lib.i64(nq), _lib.i64(ns), _lib.i64(h),
         _lib.ptr(x_bf16), _lib.i64(cin), _lib.ptr(w_rows), _lib.i64(cout), _lib.ptr(kernel_points),
-        _lib.f32(kp_extent), _lib.ptr(out), _lib.stream_ptr()), "kpconv_rows")
+        _lib.f32(kp_extent), _lib.ptr(out), ctypes.c_int(1 if out_bf16 else 0), _lib.stream_ptr()), "kpconv_rows")
     return out
 
 
@@ -202,9 +202,10 @@ def groupnorm_double(y, stats1, gamma1, beta1, gamma2, beta2, groups, seg_off, r
     stats2 = torch.empty((nseg, groups, 2), dtype=torch.float64, device=y.device)
     out = torch.empty((rows, c), dtype=torch.bfloat16, device=y.device)
     L = _lib.lib()
+    assert y.is_contiguous() and y.dtype in (torch.float32, torch.bfloat16)
     for apply in (0, 1):
         _lib.check(L.se3et_groupnorm_double(
-            _lib.ptr(y), _lib.ptr(stats1), _lib.ptr(gamma1), _lib.ptr(beta1), _lib.ptr(stats2), _lib.ptr(gamma2),
+            _lib.ptr(y), ctypes.c_int(1 if y.dtype == torch.bfloat16 else 0), _lib.ptr(stats1), _lib.ptr(gamma1), _lib.ptr(beta1), _lib.ptr(stats2), _lib.ptr(gamma2),
             _lib.ptr(beta2), _lib.i64(rows), _lib.i64(c), _lib.i64(groups), _lib.ptr(seg_off), _lib.i64(nseg),
             _lib.i64(rows_per_point), _lib.f32(eps), _lib.f32(slope), apply, _lib.ptr(out), _lib.stream_ptr()),
             "groupnorm_double")
@@ -212,13 +213,14 @@ def groupnorm_double(y, stats1, gamma1, beta1, gamma2, beta2, groups, seg_off, r
 
 
 def groupnorm_stats_stream(y, groups, seg_off, rows_per_point):
-    """Per-pair GroupNorm statistics (double (nseg, groups, 2)) of fp32 y (rows, C) by the streaming kernel
+    """Per-pair GroupNorm statistics (double (nseg, groups, 2)) of fp32 / bf16 y (rows, C) by the streaming kernel
     (se3et_groupnorm_double, apply = 2).  Requires groupnorm_double_supported(C)."""
     rows, c = y.shape
     nseg = seg_off.numel() - 1
     stats = torch.empty((nseg, groups, 2), dtype=torch.float64, device=y.device)
+    assert y.is_contiguous() and y.dtype in (torch.float32, torch.bfloat16)
     _lib.check(_lib.lib().se3et_groupnorm_double(
-        _lib.ptr(y), _lib.ptr(None), _lib.ptr(None), _lib.ptr(None), _lib.ptr(stats), _lib.ptr(None), _lib.ptr(None),
+        _lib.ptr(y), ctypes.c_int(1 if y.dtype == torch.bfloat16 else 0), _lib.ptr(None), _lib.ptr(None), _lib.ptr(None), _lib.ptr(stats), _lib.ptr(None), _lib.ptr(None),
         _lib.i64(rows), _lib.i64(c), _lib.i64(groups), _lib.ptr(seg_off), _lib.i64(nseg), _lib.i64(rows_per_point),
         _lib.f32(1e-5), _lib.f32(1.0), 2, _lib.ptr(None), _lib.stream_ptr()), "groupnorm_double(stats)")
     return stats
@@ -249,4 +251,35 @@ def kpconv_cin1(q_pts, s_pts, neighbors, x_bf16, w36, kernel_points, kp_extent, 
         _lib.ptr(x_bf16), _lib.ptr(w36), _lib.i64(cout), _lib.ptr(kernel_points), _lib.f32(kp_extent), _lib.ptr(out),
         _lib.ptr(stats), _lib.ptr(seg_off), _lib.i64(nseg), _lib.i64(groups), ctypes.c_int(1 if lifted else 0),
         _lib.stream_ptr()), "kpconv_cin1")
+    return out, stats
+
+
+def kpconv_lift_supported(cout, h, ns):
+    return cout in (32, 64) and h <= 48 and ns < (1 << 31)
+
+
+def kpconv_lift(q_pts, s_pts, neighbors, f_bf16, w36, kernel_points, kp_extent, gn=None, out_bf16=False):
+    """First-layer KPConvInterSO3 on the lifted input (se3et_kpconv_lift): f (Ns,) bf16 = the LiftBlockEPN value of
+    every support point, w36 fp32 (36, Cout).  -> (fp32 / bf16 (Nq*6, Cout), stats or None)."""
+    _lib.require_cuda(q_pts, s_pts, neighbors, f_bf16, w36, kernel_points)
+    assert f_bf16.dtype == torch.bfloat16 and f_bf16.is_contiguous() and f_bf16.dim() == 1
+    assert w36.dtype == torch.float32 and w36.is_contiguous() and w36.shape[0] == 36
+    assert neighbors.dtype == torch.int64 and neighbors.is_contiguous()
+    assert q_pts.dtype == torch.float32 and s_pts.dtype == torch.float32 and q_pts.is_contiguous() and s_pts.is_contiguous()
+    nq, h = neighbors.shape
+    ns, cout = f_bf16.shape[0], w36.shape[1]
+    assert s_pts.shape[0] == ns and q_pts.shape[0] == nq
+    out = torch.empty((nq * 6, cout), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=f_bf16.device)
+    stats, seg_off, groups, nseg = None, None, 0, 0
+    if gn is not None:
+        groups, seg_off = gn
+        nseg = seg_off.numel() - 1
+        stats = torch.empty((nseg, groups, 2), dtype=torch.float64, device=f_bf16.device)
+    L = _lib.lib()
+    ws = _lib.workspace.get(ns * 16 + 512, f_bf16.device)   # >= se3et_kpconv_lift_workspace_bytes(ns)
+    _lib.check(L.se3et_kpconv_lift(
+        _lib.ptr(q_pts), _lib.ptr(s_pts), _lib.ptr(neighbors), _lib.i64(nq), _lib.i64(ns), _lib.i64(h),
+        _lib.ptr(f_bf16), _lib.ptr(w36), _lib.i64(cout), _lib.ptr(kernel_points), _lib.f32(kp_extent), _lib.ptr(out),
+        ctypes.c_int(1 if out_bf16 else 0), _lib.ptr(stats), _lib.ptr(seg_off), _lib.i64(nseg), _lib.i64(groups),
+        _lib.ptr(ws), _lib.i64(ws.numel()), _lib.stream_ptr()), "kpconv_lift")
     return out, stats

@@ -190,10 +190,25 @@ def test_kpconv_lifted_input_matches_oracle(pyramid, cout):
     L.enabled = True
     L.reset()
     y, st = conv.forward_stats(p0.to(DEV), p0.to(DEV), nb.to(DEV), xd, 16, seg)
-    assert L.counts.get("se3et_kpconv_cin1", 0) == 1, L.counts
-    L.enabled = False
+    assert L.counts.get("se3et_kpconv_lift", 0) == 1, L.counts
     assert rel_err(y.cpu().view_as(want), want) < 2e-3
     assert torch.allclose(st, K.groupnorm_stats(y, 16, seg, 6), rtol=1e-5, atol=1e-3)
+    # the bf16 output of the same kernel: the rounded values, statistics taken before the rounding
+    y16, st16 = conv.forward_stats(p0.to(DEV), p0.to(DEV), nb.to(DEV), xd, 16, seg, allow_bf16=True)
+    assert y16.dtype == torch.bfloat16 and torch.equal(y16, y.bfloat16())
+    assert torch.allclose(st16, st, rtol=1e-5, atol=1e-3)   # fp32 shared-memory atomics: order-dependent rounding
+    # the round-1 kernel (one warp per point) stays available and agrees
+    M._GFLAGS['lift_kernel'] = False
+    try:
+        L.reset()
+        y1, st1 = conv.forward_stats(p0.to(DEV), p0.to(DEV), nb.to(DEV), xd, 16, seg)
+        assert L.counts.get("se3et_kpconv_cin1", 0) == 1, L.counts
+    finally:
+        M._GFLAGS['lift_kernel'] = True
+        L.enabled = False
+    assert rel_err(y1.cpu().view_as(want), want) < 2e-3
+    assert rel_err(y.cpu(), y1.cpu()) < 1e-4
+    assert torch.allclose(st1, st, rtol=1e-4, atol=1e-3)
 
 
 @pytest.mark.parametrize("cin,cout,G", [(16, 16, 16), (32, 32, 32), (32, 64, 16), (64, 128, 32), (128, 256, 32),
@@ -474,6 +489,47 @@ def test_double_groupnorm_equals_two_single_passes(c, G):
     st1 = K.groupnorm_stats(yd, G, seg, 6)
     got = K.groupnorm_double(yd, st1, g1.to(DEV), b1.to(DEV), g2.to(DEV), b2.to(DEV), G, seg, 6)
     assert torch.allclose(got.float().cpu(), want, rtol=2e-2, atol=2e-2), (got.float().cpu() - want).abs().max()
+
+
+@pytest.mark.parametrize("c,G", [(32, 32), (64, 32), (256, 32), (16, 4), (128, 16)])
+def test_double_groupnorm_bf16_input(c, G):
+    """The bf16-input form of se3et_groupnorm_double (what the conv kernels' bf16 outputs feed) against the torch fp32
+    chain on the same bf16-rounded values, statistics pass (apply = 2) included."""
+    g = torch.Generator().manual_seed(100 + c)
+    pts = [120, 0, 77, 301, 1]
+    seg = torch.tensor(np.concatenate([[0], np.cumsum(pts)]), dtype=torch.int64, device=DEV)
+    y = (torch.randn(6 * sum(pts), c, generator=g) * 1.3 + 0.2).bfloat16()
+    g1, b1, g2, b2 = (torch.randn(c, generator=g) for _ in range(4))
+    want = []
+    for i in range(len(pts)):
+        blk = y[6 * int(seg[i]):6 * int(seg[i + 1])].float()
+        if blk.numel():
+            f = torch.nn.functional.leaky_relu(oe.group_norm_epn(blk.view(-1, 6, c), G, g1, b1), 0.1)
+            want.append(torch.nn.functional.leaky_relu(oe.group_norm_epn(f, G, g2, b2), 0.1).reshape(-1, c))
+    want = torch.cat(want)
+    yd = y.to(DEV)
+    st1 = K.groupnorm_stats_stream(yd, G, seg, 6)
+    ref1 = K.groupnorm_stats(yd.float(), G, seg, 6)
+    assert torch.allclose(st1, ref1, rtol=1e-5, atol=1e-3)
+    got = K.groupnorm_double(yd, st1, g1.to(DEV), b1.to(DEV), g2.to(DEV), b2.to(DEV), G, seg, 6)
+    assert torch.allclose(got.float().cpu(), want, rtol=2e-2, atol=2e-2), (got.float().cpu() - want).abs().max()
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 32), (64, 64), (64, 128), (128, 256)])
+def test_kpconv_bf16_output_is_the_rounded_fp32_output(pyramid, cin, cout):
+    """out_bf16 = 1 of se3et_kpconv_rows / se3et_kpconv_fused: the same accumulators, rounded to bf16 in the epilogue."""
+    p0 = torch.from_numpy(pyramid["points"][0]).to(DEV)
+    nb = torch.from_numpy(pyramid["neighbors"][0]).to(DEV)
+    conv = M.KPConvInterSO3(15, 6, cin, cout, 0.05, 0.0625, non_sep_conv=True, rot_by_permute=True,
+                            quotient_factor=4).to(DEV)
+    x = helpers.seeded_tensor("conv.input", (p0.shape[0], 6, cin)).bfloat16().to(DEV)
+    for fn, w in ((K.kpconv_rows, conv._w_rows()), (lambda *a, **k: K.kpconv_fused(*a, **k)[0], conv._w_fused())):
+        if fn is K.kpconv_rows and not K.kpconv_rows_supported(cin, cout, nb.shape[1], p0.shape[0]):
+            continue
+        y32 = fn(p0, p0, nb, x, w, conv.kernel_points, conv.KP_extent)
+        y16 = fn(p0, p0, nb, x, w, conv.kernel_points, conv.KP_extent, out_bf16=True)
+        assert y16.dtype == torch.bfloat16 and y16.shape == y32.shape
+        assert torch.equal(y16, y32.bfloat16())
 
 
 def test_pooling_ops_match_oracle(pyramid):
