@@ -184,7 +184,7 @@ def algorithmic_work(cfg, n_levels, n_ref_c, n_src_c, limits):
         # class-pre-summed contraction as issued on tcgen05 (rows = points for mid <= 128: e2pn.py:_rows_ok); the
         # mma.sync basis weighting that feeds it is NOT counted against the tcgen05 peak
         conv_flops["se3et_kpconv_rows" if mid <= 128 else "se3et_kpconv_fused"] += 2.0 * nq * 6 * 36 * mid * mid
-        norm_bytes += nq * 6 * mid * (4 + 4 + 4 + 2)  # double GroupNorm: two statistics passes + apply over fp32, bf16 out
+        norm_bytes += nq * 6 * mid * (2 + 2 + 2 + 2)  # double GroupNorm: two statistics passes + apply over the bf16 conv output, bf16 out
         rows = 6.0 * nq
         stats_pass(rows, mid, cout)
         if cin != cout:
@@ -511,7 +511,7 @@ def main():
     barrier()
 
     # ---- timed region: K steps, CUDA events, per-entry-point events for the roofline
-    timed_names = ["se3et_kpconv_rows", "se3et_kpconv_fused", "se3et_kpconv_cin1", "se3et_kpconv_gather", "se3et_gemm_bf16", "se3et_gemm_bf16_gnstats",
+    timed_names = ["se3et_kpconv_rows", "se3et_kpconv_fused", "se3et_kpconv_cin1", "se3et_kpconv_lift", "se3et_kpconv_gather", "se3et_gemm_bf16", "se3et_gemm_bf16_gnstats",
                    "se3et_gemm_bf16_gnapply", "se3et_gemm_bf16_gnapply_dual", "se3et_linear_gnstats_gram",
                    "se3et_linear_gnstats_stream", "se3et_gemm_grouped_bf16", "se3et_groupnorm_double",
                    "se3et_groupnorm_apply", "se3et_groupnorm_stats", "se3et_maxpool_nbr", "se3et_radius_neighbors", "se3et_grid_subsample",

@@ -329,7 +329,7 @@ __device__ __forceinline__ void load_norm_cols_n(const NormSide& n, int seg, int
 }
 
 template <int kMode, bool kBf16>
-__global__ void __launch_bounds__(256, 3) groupnorm_double_kernel(NormSide a, NormSide b2, double* __restrict__ stats2_acc,
+__global__ void __launch_bounds__(256, (kMode == 1 || (kBf16 && kMode == 0)) ? 2 : 3) groupnorm_double_kernel(NormSide a, NormSide b2, double* __restrict__ stats2_acc,
                                                                 int64_t rows, int C, int cpg,
                                                                 const int64_t* __restrict__ seg_off, int nseg,
                                                                 int rows_per_point, float eps, float slope,
@@ -367,20 +367,27 @@ __global__ void __launch_bounds__(256, 3) groupnorm_double_kernel(NormSide a, No
     float s[N], ss[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) s[j] = ss[j] = 0.f;
-    // four rows per thread and iteration: the loads are issued together (bytes in flight, this kernel is pure streaming)
+    // four rows per thread and iteration, software pipelined: the loads of the next four rows are issued before this
+    // iteration's arithmetic (this kernel is pure streaming: the bytes in flight per SM decide its speed, and the bf16
+    // form has twice the arithmetic per byte)
     constexpr int kU = 4;
-    for (int64_t rowb = row0 + rsub; rowb < row1; rowb += (int64_t)kU * rstep) {
-      uint4 yv[kU];
+    const int64_t step = (int64_t)kU * rstep;
+    auto load_rows = [&](int64_t rowb, uint4 (&dst)[kU]) {
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int64_t row = rowb + (int64_t)u * rstep;
         if (row < row1) {
           if (kBf16)
-            yv[u] = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.y) + row * C + c0));
+            dst[u] = __ldcs(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.y) + row * C + c0));
           else
-            yv[u] = __ldcs(reinterpret_cast<const uint4*>(a.y + row * C + c0));
+            dst[u] = __ldcs(reinterpret_cast<const uint4*>(a.y + row * C + c0));
         }
       }
+    };
+    uint4 yv[kU], yn[kU];
+    load_rows(row0 + rsub, yv);
+    for (int64_t rowb = row0 + rsub; rowb < row1; rowb += step) {
+      load_rows(rowb + step, yn);
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int64_t row = rowb + (int64_t)u * rstep;
@@ -428,24 +435,37 @@ __global__ void __launch_bounds__(256, 3) groupnorm_double_kernel(NormSide a, No
           }
         }
       }
+#pragma unroll
+      for (int u = 0; u < kU; ++u) yv[u] = yn[u];
     }
     if (kMode != 1) {
       for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) sh_acc[i] = 0.f;
       __syncthreads();
-      if (cpg >= N) {  // the thread's columns share one group
-        float ts = 0.f, tss = 0.f;
+      // lanes V apart own the same columns: reduce them in registers first (float atomics on shared memory are
+      // compare-and-swap loops: 64 threads per address made this flush 40 % of the kernel's stall cycles)
+      for (int o = V; o < 32; o <<= 1) {
 #pragma unroll
         for (int j = 0; j < N; ++j) {
-          ts += s[j];
-          tss += ss[j];
+          s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+          ss[j] += __shfl_xor_sync(0xffffffffu, ss[j], o);
         }
-        atomicAdd(&sh_acc[2 * (c0 / cpg)], ts);
-        atomicAdd(&sh_acc[2 * (c0 / cpg) + 1], tss);
-      } else {
+      }
+      if (V >= 32 || (threadIdx.x & 31) < V) {
+        if (cpg >= N) {  // the thread's columns share one group
+          float ts = 0.f, tss = 0.f;
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-          atomicAdd(&sh_acc[2 * ((c0 + j) / cpg)], s[j]);
-          atomicAdd(&sh_acc[2 * ((c0 + j) / cpg) + 1], ss[j]);
+          for (int j = 0; j < N; ++j) {
+            ts += s[j];
+            tss += ss[j];
+          }
+          atomicAdd(&sh_acc[2 * (c0 / cpg)], ts);
+          atomicAdd(&sh_acc[2 * (c0 / cpg) + 1], tss);
+        } else {
+#pragma unroll
+          for (int j = 0; j < N; ++j) {
+            atomicAdd(&sh_acc[2 * ((c0 + j) / cpg)], s[j]);
+            atomicAdd(&sh_acc[2 * ((c0 + j) / cpg) + 1], ss[j]);
+          }
         }
       }
       __syncthreads();

@@ -481,17 +481,41 @@ __device__ __forceinline__ bool eval_candidate(const QueryCtx& c, const int* sh_
   return true;
 }
 
-__global__ void __launch_bounds__(kQueryWarps * 32) radius_query_kernel(
-    const float* __restrict__ q, int64_t nq, const int64_t* __restrict__ q_off, const int64_t* __restrict__ s_off,
-    int batch, const float* __restrict__ mins, const float4* __restrict__ sorted, const uint32_t* __restrict__ start,
-    uint32_t mask, float inv_cell, float r2, int32_t* counts, int64_t* out, int64_t width, int64_t ns_total,
-    int32_t* status, int32_t* cloud_max) {
-  __shared__ unsigned long long sh_keys[kQueryWarps][kHitCap];
-  __shared__ int sh_excl[kQueryWarps][32];
-  __shared__ int sh_start[kQueryWarps][32];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t qi = (int64_t)blockIdx.x * kQueryWarps + warp;
-  if (qi >= nq) return;  // whole warp exits; only __syncwarp below
+struct QueryArgs {
+  const float* q;
+  int64_t nq;
+  const int64_t* q_off;
+  const int64_t* s_off;
+  int batch;
+  const float* mins;
+  const float4* sorted;
+  const uint32_t* start;
+  uint32_t mask;
+  float inv_cell, r2;
+  int32_t* counts;
+  int64_t* out;
+  int64_t width, ns_total;
+  int32_t* status;
+  int32_t* cloud_max;
+};
+
+// one query per warp: 27-cell scan of the hashed grid, exact for any neighbour count
+__device__ __forceinline__ void query_one(const QueryArgs& A, int64_t qi, int lane, unsigned long long* keys,
+                                          int* sh_excl_w, int* sh_start_w) {
+  const float* __restrict__ q = A.q;
+  const int64_t* __restrict__ q_off = A.q_off;
+  const int64_t* __restrict__ s_off = A.s_off;
+  const int batch = A.batch;
+  const float* __restrict__ mins = A.mins;
+  const float4* __restrict__ sorted = A.sorted;
+  const uint32_t* __restrict__ start = A.start;
+  const uint32_t mask = A.mask;
+  const float inv_cell = A.inv_cell, r2 = A.r2;
+  int32_t* counts = A.counts;
+  int64_t* out = A.out;
+  const int64_t width = A.width, ns_total = A.ns_total;
+  int32_t* status = A.status;
+  int32_t* cloud_max = A.cloud_max;
   const int b = segment_of(q_off, batch, qi);
   QueryCtx c;
   c.qx = q[3 * qi]; c.qy = q[3 * qi + 1]; c.qz = q[3 * qi + 2];
@@ -512,16 +536,15 @@ __global__ void __launch_bounds__(kQueryWarps * 32) radius_query_kernel(
     if (lane >= o) incl += t;
   }
   const int total = __shfl_sync(0xffffffffu, incl, 31);
-  sh_excl[warp][lane] = incl - len;
-  sh_start[warp][lane] = st;
+  sh_excl_w[lane] = incl - len;
+  sh_start_w[lane] = st;
   __syncwarp();
 
-  unsigned long long* keys = sh_keys[warp];
   int nhit = 0;
   for (int base = 0; base < total; base += 32) {
     const int t = base + lane;
     unsigned long long key = 0;
-    const bool hit = t < total && eval_candidate(c, sh_excl[warp], sh_start[warp], t, key);
+    const bool hit = t < total && eval_candidate(c, sh_excl_w, sh_start_w, t, key);
     const unsigned ballot = __ballot_sync(0xffffffffu, hit);
     const int pos = nhit + __popc(ballot & ((1u << lane) - 1u));
     if (hit && pos < kHitCap) keys[pos] = key;
@@ -588,7 +611,7 @@ __global__ void __launch_bounds__(kQueryWarps * 32) radius_query_kernel(
       unsigned long long best = ~0ull;
       for (int t = lane; t < total; t += 32) {
         unsigned long long key;
-        if (eval_candidate(c, sh_excl[warp], sh_start[warp], t, key) && (k == 0 || key > last) && key < best) best = key;
+        if (eval_candidate(c, sh_excl_w, sh_start_w, t, key) && (k == 0 || key > last) && key < best) best = key;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -602,6 +625,217 @@ __global__ void __launch_bounds__(kQueryWarps * 32) radius_query_kernel(
   }
 }
 
+__global__ void __launch_bounds__(kQueryWarps * 32) radius_query_kernel(QueryArgs A) {
+  __shared__ unsigned long long sh_keys[kQueryWarps][kHitCap];
+  __shared__ int sh_excl[kQueryWarps][32];
+  __shared__ int sh_start[kQueryWarps][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t qi = (int64_t)blockIdx.x * kQueryWarps + warp;
+  if (qi >= A.nq) return;  // whole warp exits; only __syncwarp below
+  query_one(A, qi, lane, sh_keys[warp], sh_excl[warp], sh_start[warp]);
+}
+
+// the same search for a device-side list of queries (the by-cell kernel's overflow cases)
+__global__ void __launch_bounds__(kQueryWarps * 32) radius_query_list_kernel(QueryArgs A, const int32_t* __restrict__ list,
+                                                                            const int32_t* __restrict__ count) {
+  __shared__ unsigned long long sh_keys[kQueryWarps][kHitCap];
+  __shared__ int sh_excl[kQueryWarps][32];
+  __shared__ int sh_start[kQueryWarps][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = *count;
+  for (int i = blockIdx.x * kQueryWarps + warp; i < n; i += gridDim.x * kQueryWarps) {
+    query_one(A, list[i], lane, sh_keys[warp], sh_excl[warp], sh_start[warp]);
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Query by cell (round 2).  All queries of one grid cell share their 27-cell candidate set, so the queries are bucketed
+// with the support set's hash and a warp works through the non-empty query buckets: per cell the candidate runs are
+// scanned, validated (cloud, cell coordinates) and compacted into shared memory ONCE; per query only the distance test
+// over the staged candidates and the ranking remain (~2x fewer instructions per query than query_one).  Cells with more
+// than kCandCap candidates and queries with more than kCellHitCap hits go to a device-side list that
+// radius_query_list_kernel finishes with the exact general path.  Results are the same set ordered by the same key.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kCellWarps = 8;
+constexpr int kCandCap = 320;
+constexpr int kCellHitCap = 128;
+constexpr int kCellWarpBytes = kCandCap * 16 + kCellHitCap * 8 + 2 * 32 * 4;
+
+__device__ __forceinline__ void emit_row_small(const unsigned long long* keys, int nhit, int64_t* row, int64_t width,
+                                               int64_t ns_total, int lane) {
+  // nhit <= kCellHitCap = 128: rank every key against all others (keys are unique: the rank is the sorted position)
+  unsigned long long mine[4];
+  int rank[4] = {0, 0, 0, 0};
+  const int per = (nhit + 31) >> 5;  // keys per lane, 1..4 (warp-uniform)
+#pragma unroll
+  for (int u = 0; u < 4; ++u) mine[u] = (u < per && lane + 32 * u < nhit) ? keys[lane + 32 * u] : ~0ull;
+  if (per == 1) {
+#pragma unroll 4
+    for (int f = 0; f < nhit; ++f) rank[0] += keys[f] < mine[0] ? 1 : 0;
+  } else if (per == 2) {
+#pragma unroll 4
+    for (int f = 0; f < nhit; ++f) {
+      const unsigned long long kf = keys[f];
+      rank[0] += kf < mine[0] ? 1 : 0;
+      rank[1] += kf < mine[1] ? 1 : 0;
+    }
+  } else {
+#pragma unroll 2
+    for (int f = 0; f < nhit; ++f) {
+      const unsigned long long kf = keys[f];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rank[u] += kf < mine[u] ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if (u < per && lane + 32 * u < nhit && rank[u] < width) row[rank[u]] = (int64_t)(mine[u] & 0xffffffffull);
+  for (int k = nhit + lane; k < width; k += 32) row[k] = ns_total;
+}
+
+__global__ void __launch_bounds__(kCellWarps * 32) radius_cell_kernel(QueryArgs A, const float4* __restrict__ q_sorted,
+                                                                      const uint32_t* __restrict__ q_start,
+                                                                      uint32_t table, int32_t* __restrict__ fb_list,
+                                                                      int32_t* __restrict__ fb_count) {
+  extern __shared__ __align__(16) uint8_t cell_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* base = cell_smem + warp * kCellWarpBytes;
+  float4* cand = reinterpret_cast<float4*>(base);
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(base + kCandCap * 16);
+  int* sh_excl = reinterpret_cast<int*>(base + kCandCap * 16 + kCellHitCap * 8);
+  int* sh_start = sh_excl + 32;
+  const unsigned full = 0xffffffffu;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const float inv_cell = A.inv_cell, r2 = A.r2;
+  int warp_max = 0;
+  const uint32_t nchunks = (table + 31) / 32;
+  for (uint32_t chunk = blockIdx.x * kCellWarps + warp; chunk < nchunks; chunk += gridDim.x * kCellWarps) {
+    // 32 consecutive buckets per trip: most are empty
+    const uint32_t hb = chunk * 32 + lane;
+    const uint32_t my_s = hb <= table ? q_start[hb] : 0u;
+    uint32_t my_e = __shfl_down_sync(full, my_s, 1);
+    if (lane == 31) my_e = hb + 1 <= table ? q_start[hb + 1] : my_s;
+    if (hb >= table) my_e = my_s;
+    unsigned nonempty = __ballot_sync(full, my_e > my_s);
+    while (nonempty) {
+      const int bl = __ffs(nonempty) - 1;
+      nonempty &= nonempty - 1;
+      const uint32_t qs = __shfl_sync(full, my_s, bl), qe = __shfl_sync(full, my_e, bl);
+      for (uint32_t qb = qs; qb < qe; qb += 32) {
+        const bool have = qb + lane < qe;
+        const float4 qv = have ? q_sorted[qb + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int qi = have ? __float_as_int(qv.w) : -1;
+        int b = -1, cx = 0, cy = 0, cz = 0;
+        if (have) {
+          b = segment_of(A.q_off, A.batch, qi);
+          cell_of_point(qv.x, qv.y, qv.z, A.mins + 3 * b, inv_cell, cx, cy, cz);
+        }
+        unsigned remaining = __ballot_sync(full, have);
+        while (remaining) {
+          const int leader = __ffs(remaining) - 1;
+          const int lb = __shfl_sync(full, b, leader), lcx = __shfl_sync(full, cx, leader);
+          const int lcy = __shfl_sync(full, cy, leader), lcz = __shfl_sync(full, cz, leader);
+          const unsigned group = __ballot_sync(full, have && b == lb && cx == lcx && cy == lcy && cz == lcz);
+          remaining &= ~group;
+          // ---- candidates of the cell's 27 neighbours, validated and compacted once --------------------------------
+          const int s_lo = (int)A.s_off[lb], s_hi = (int)A.s_off[lb + 1];
+          const float* mn = A.mins + 3 * lb;
+          int st = 0, len = 0;
+          if (lane < 27 && s_hi > s_lo) {
+            const uint32_t h = cell_hash(lb, lcx + (lane % 3) - 1, lcy + ((lane / 3) % 3) - 1, lcz + (lane / 9) - 1) & A.mask;
+            st = (int)A.start[h];
+            len = (int)A.start[h + 1] - st;
+          }
+          int incl = len;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(full, incl, o);
+            if (lane >= o) incl += t;
+          }
+          const int total = __shfl_sync(full, incl, 31);
+          __syncwarp();
+          sh_excl[lane] = incl - len;
+          sh_start[lane] = st;
+          __syncwarp();
+          int ncand = 0;
+          for (int tb = 0; tb < total; tb += 32) {
+            const int t = tb + lane;
+            bool ok = false;
+            float4 sp = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t < total) {
+              int lo = 0, hi = 26;  // largest cell index with excl <= t
+              while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (sh_excl[mid] <= t) lo = mid; else hi = mid - 1;
+              }
+              sp = A.sorted[sh_start[lo] + (t - sh_excl[lo])];
+              const int j = __float_as_int(sp.w);
+              if (j >= s_lo && j < s_hi) {  // else: hash collision with another cloud
+                int scx, scy, scz;
+                cell_of_point(sp.x, sp.y, sp.z, mn, inv_cell, scx, scy, scz);
+                // accept only from the probed cell: rejects bucket collisions and double visits
+                ok = scx == lcx + (lo % 3) - 1 && scy == lcy + ((lo / 3) % 3) - 1 && scz == lcz + (lo / 9) - 1;
+              }
+            }
+            const unsigned bal = __ballot_sync(full, ok);
+            const int pos = ncand + __popc(bal & lt_mask);
+            if (ok && pos < kCandCap) cand[pos] = sp;
+            ncand += __popc(bal);
+          }
+          __syncwarp();
+          if (ncand > kCandCap) {  // dense cell: the general kernel finishes these queries
+            if ((group >> lane) & 1u) fb_list[atomicAdd(fb_count, 1)] = qi;
+            continue;
+          }
+          // ---- the queries of the cell, one after the other ---------------------------------------------------------
+          int gmax = 0;
+          unsigned g = group;
+          while (g) {
+            const int ql = __ffs(g) - 1;
+            g &= g - 1;
+            const float qx = __shfl_sync(full, qv.x, ql), qy = __shfl_sync(full, qv.y, ql);
+            const float qz = __shfl_sync(full, qv.z, ql);
+            const int qq = __shfl_sync(full, qi, ql);
+            int nhit = 0;
+            for (int tb = 0; tb < ncand; tb += 32) {
+              const int t = tb + lane;
+              bool hit = false;
+              unsigned long long key = 0;
+              if (t < ncand) {
+                const float4 sp = cand[t];
+                const float dx = __fsub_rn(qx, sp.x), dy = __fsub_rn(qy, sp.y), dz = __fsub_rn(qz, sp.z);
+                // nanoflann.hpp:432-440: result = ((0 + dx*dx) + dy*dy) + dz*dz
+                const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                hit = d2 < r2;  // nanoflann.hpp:249-253, strict
+                key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)__float_as_int(sp.w);
+              }
+              const unsigned bal = __ballot_sync(full, hit);
+              const int pos = nhit + __popc(bal & lt_mask);
+              if (hit && pos < kCellHitCap) keys[pos] = key;
+              nhit += __popc(bal);
+            }
+            if (nhit > kCellHitCap) {  // general kernel (it also reports the count)
+              if (lane == 0) fb_list[atomicAdd(fb_count, 1)] = qq;
+              continue;
+            }
+            gmax = max(gmax, nhit);
+            if (lane == 0 && A.counts) A.counts[qq] = nhit;
+            if (A.out && A.width > 0) {
+              __syncwarp();
+              emit_row_small(keys, nhit, A.out + (int64_t)qq * A.width, A.width, A.ns_total, lane);
+            }
+            __syncwarp();  // keys are reused by the next query
+          }
+          if (lane == 0 && A.cloud_max && gmax > 0) atomicMax(&A.cloud_max[lb], gmax);
+          warp_max = max(warp_max, gmax);
+        }
+      }
+    }
+  }
+  if (lane == 0 && warp_max > 0) atomicMax(&A.status[SE3ET_STATUS_MAX_COUNT], warp_max);
+}
+
 struct RadiusWs {
   int64_t *q_off, *s_off;
   Bounds* bounds;
@@ -609,6 +843,10 @@ struct RadiusWs {
   uint32_t *bucket_of, *hist, *start, *cursor, *block_sums;
   float4* sorted;
   int64_t table;
+  // query side of the by-cell search
+  uint32_t *q_bucket_of, *q_hist, *q_start, *q_cursor;
+  float4* q_sorted;
+  int32_t *fb_list, *fb_count;
 };
 
 static int64_t hash_table_size(int64_t ns) {
@@ -617,7 +855,7 @@ static int64_t hash_table_size(int64_t ns) {
   return t;
 }
 
-static bool carve_radius(Carver& c, int64_t ns, int64_t batch, RadiusWs& w) {
+static bool carve_radius(Carver& c, int64_t nq, int64_t ns, int64_t batch, RadiusWs& w) {
   w.table = hash_table_size(ns);
   const int64_t nn = ns > 0 ? ns : 1;
   w.q_off = c.take<int64_t>(batch + 1);
@@ -630,6 +868,14 @@ static bool carve_radius(Carver& c, int64_t ns, int64_t batch, RadiusWs& w) {
   w.cursor = c.take<uint32_t>(w.table + 1);
   w.block_sums = c.take<uint32_t>(scan_num_blocks(w.table + 1));
   w.sorted = c.take<float4>(nn);
+  const int64_t nnq = nq > 0 ? nq : 1;
+  w.q_bucket_of = c.take<uint32_t>(nnq);
+  w.q_hist = c.take<uint32_t>(w.table + 1);
+  w.q_start = c.take<uint32_t>(w.table + 1);
+  w.q_cursor = c.take<uint32_t>(w.table + 1);
+  w.q_sorted = c.take<float4>(nnq);
+  w.fb_list = c.take<int32_t>(nnq);
+  w.fb_count = c.take<int32_t>(4);
   return c.fits();
 }
 
@@ -708,7 +954,7 @@ extern "C" int se3et_radius_neighbors_workspace_bytes(int64_t nq_total, int64_t 
   if (!bytes || nq_total < 0 || ns_total < 0 || batch <= 0) return SE3ET_ERR_ARG;
   Carver c(nullptr, 0);
   RadiusWs w;
-  carve_radius(c, ns_total, batch, w);
+  carve_radius(c, nq_total, ns_total, batch, w);
   *bytes = c.off + 256;
   return SE3ET_OK;
 }
@@ -725,7 +971,7 @@ extern "C" int se3et_radius_neighbors(const float* q_points, const float* s_poin
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Carver c(workspace, workspace_bytes);
   RadiusWs w;
-  if (!carve_radius(c, ns_total, batch, w)) return SE3ET_ERR_WORKSPACE;
+  if (!carve_radius(c, nq_total, ns_total, batch, w)) return SE3ET_ERR_WORKSPACE;
   const uint32_t mask = (uint32_t)(w.table - 1);
   const float r2 = radius * radius;                  // fp32 product (radius_neighbors_cpu.cpp:12)
   const float inv_cell = 1.0f / (radius * 1.001f);   // cell slightly larger than the radius: 27 cells always suffice
@@ -756,9 +1002,47 @@ extern "C" int se3et_radius_neighbors(const float* q_points, const float* s_poin
     SE3ET_LAUNCH_CHECK();
   }
   if (nq_total > 0) {
-    radius_query_kernel<<<(int)ceil_div(nq_total, kQueryWarps), kQueryWarps * 32, 0, st>>>(
-        q_points, nq_total, w.q_off, w.s_off, (int)batch, w.mins, w.sorted, w.start, mask, inv_cell, r2, counts, out,
-        width, ns_total, status, cloud_max);
+    QueryArgs qa;
+    qa.q = q_points; qa.nq = nq_total; qa.q_off = w.q_off; qa.s_off = w.s_off; qa.batch = (int)batch; qa.mins = w.mins;
+    qa.sorted = w.sorted; qa.start = w.start; qa.mask = mask; qa.inv_cell = inv_cell; qa.r2 = r2; qa.counts = counts;
+    qa.out = out; qa.width = width; qa.ns_total = ns_total; qa.status = status; qa.cloud_max = cloud_max;
+    static const bool by_cell = [] {
+      const char* e = getenv("SE3ET_RADIUS_BY_CELL");
+      return !(e && e[0] == '0');
+    }();
+    if (!by_cell || ns_total == 0) {
+      radius_query_kernel<<<(int)ceil_div(nq_total, kQueryWarps), kQueryWarps * 32, 0, st>>>(qa);
+      SE3ET_LAUNCH_CHECK();
+      return SE3ET_OK;
+    }
+    // queries bucketed with the support set's hash (self search: the support table itself)
+    const float4* q_sorted = w.sorted;
+    const uint32_t* q_start = w.start;
+    if (!(q_points == s_points && q_lengths == s_lengths && nq_total == ns_total)) {
+      SE3ET_CUDA_CHECK(cudaMemsetAsync(w.q_hist, 0, sizeof(uint32_t) * (w.table + 1), st));
+      SE3ET_CUDA_CHECK(cudaMemsetAsync(w.q_cursor, 0, sizeof(uint32_t) * (w.table + 1), st));
+      const int qblk = (int)ceil_div(nq_total, 256);
+      // cell coordinates in the SUPPORT cloud's frame (w.mins), as the per-query kernel computes them
+      hash_count_kernel<<<qblk, 256, 0, st>>>(q_points, nq_total, w.q_off, (int)batch, w.mins, inv_cell, mask,
+                                              w.q_bucket_of, w.q_hist);
+      SE3ET_LAUNCH_CHECK();
+      rc = exclusive_scan(U32Load{w.q_hist}, nullptr, w.table + 1, w.block_sums, w.q_start, nullptr, st);
+      if (rc) return rc;
+      hash_scatter_kernel<<<qblk, 256, 0, st>>>(q_points, nq_total, w.q_bucket_of, w.q_start, w.q_cursor, w.q_sorted);
+      SE3ET_LAUNCH_CHECK();
+      q_sorted = w.q_sorted;
+      q_start = w.q_start;
+    }
+    SE3ET_CUDA_CHECK(cudaMemsetAsync(w.fb_count, 0, sizeof(int32_t) * 4, st));
+    const size_t smem = (size_t)kCellWarps * kCellWarpBytes;
+    SE3ET_ENSURE_SMEM(radius_cell_kernel, smem);
+    const int64_t chunks = ceil_div(w.table, 32);
+    int64_t blocks = ceil_div(chunks, kCellWarps);
+    if (blocks > (int64_t)kNumSMs * 4) blocks = (int64_t)kNumSMs * 4;
+    radius_cell_kernel<<<(unsigned)blocks, kCellWarps * 32, smem, st>>>(qa, q_sorted, q_start, (uint32_t)w.table,
+                                                                       w.fb_list, w.fb_count);
+    SE3ET_LAUNCH_CHECK();
+    radius_query_list_kernel<<<kNumSMs * 2, kQueryWarps * 32, 0, st>>>(qa, w.fb_list, w.fb_count);
     SE3ET_LAUNCH_CHECK();
   }
   return SE3ET_OK;
