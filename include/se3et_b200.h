@@ -81,9 +81,13 @@ int se3et_grid_subsample(const float* points, const int64_t* lengths, const floa
  *           indices, padded with ns_total
  * status[MAX_COUNT] receives the maximum count; cloud_max (optional, int32[batch]) the maximum
  * per cloud, which is what decides the reference's matrix width when pairs are processed one at a
- * time.  Hashed uniform grid (cell = radius) over the support set + one warp per query.
+ * time.  Hashed uniform grid (cell = radius) over the support set + one warp per query; large self searches run by
+ * CELL instead (round 2): the queries are bucketed with the same hash and a warp stages the 27-cell candidate set of a
+ * cell once for all its queries (same result, ~1.6x faster at 900k points).
+ * se3et_radius_set_mode: 0 = always per query, 1 = always by cell, 2 = automatic (default); process-wide.
  * ------------------------------------------------------------------------------------------ */
 int se3et_radius_neighbors_workspace_bytes(int64_t nq_total, int64_t ns_total, int64_t batch, size_t* bytes);
+int se3et_radius_set_mode(int mode);
 int se3et_radius_neighbors(const float* q_points, const float* s_points, const int64_t* q_lengths,
                            const int64_t* s_lengths, int64_t nq_total, int64_t ns_total, int64_t batch,
                            float radius, int32_t* counts, int64_t* out, int64_t width, int32_t* status,

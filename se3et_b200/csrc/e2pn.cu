@@ -482,6 +482,13 @@ __global__ void __launch_bounds__(256, (kMode == 1 || (kBf16 && kMode == 0)) ? 2
 // flight) of one query.
 constexpr int kPoolQ = 4;
 
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ void max_bf16x8_packed(uint4& m, const uint4& v) {
+  m.x = max_bf16x2(m.x, v.x); m.y = max_bf16x2(m.y, v.y); m.z = max_bf16x2(m.z, v.z); m.w = max_bf16x2(m.w, v.w);
+}
 __device__ __forceinline__ void max_bf16x8(float (&m)[8], const uint4& v) {
   m[0] = fmaxf(m[0], bf_lo(v.x)); m[1] = fmaxf(m[1], bf_hi(v.x));
   m[2] = fmaxf(m[2], bf_lo(v.y)); m[3] = fmaxf(m[3], bf_hi(v.y));
@@ -520,31 +527,32 @@ __global__ void __launch_bounds__(256) maxpool_nbr_kernel(const __nv_bfloat16* _
     const int64_t q = q0 + qi;
     if (q >= nq) continue;
     const int H = sh_h[qi];
-    float m[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) m[i] = -INFINITY;
+    // running maximum as four packed bf16 pairs (HMNMX2.BF16: the maximum of bf16 values is exact, so this equals the
+    // fp32 maximum rounded back; 4 instructions per 16-byte row piece instead of 16), four neighbour rows in flight
+    uint4 m = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);  // -inf
     bool shadow = false;
+    const __nv_bfloat16* xv = x + 8 * v;
     int n = 0;
-    for (; n + 1 < H; n += 2) {
-      const int j0 = sh_idx[qi][n], j1 = sh_idx[qi][n + 1];
-      uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
-      if (j0 >= 0) a = *reinterpret_cast<const uint4*>(x + (int64_t)j0 * width + 8 * v);
-      if (j1 >= 0) b = *reinterpret_cast<const uint4*>(x + (int64_t)j1 * width + 8 * v);
-      shadow |= (j0 < 0) | (j1 < 0);
-      if (j0 >= 0) max_bf16x8(m, a);
-      if (j1 >= 0) max_bf16x8(m, b);
+    for (; n + 3 < H; n += 4) {
+      int j[4];
+      uint4 r[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        j[t] = sh_idx[qi][n + t];
+        r[t] = m;
+        if (j[t] >= 0) r[t] = *reinterpret_cast<const uint4*>(xv + (int64_t)j[t] * width);
+        shadow |= j[t] < 0;
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) max_bf16x8_packed(m, r[t]);
     }
-    if (n < H) {
+    for (; n < H; ++n) {
       const int j0 = sh_idx[qi][n];
-      if (j0 >= 0) max_bf16x8(m, *reinterpret_cast<const uint4*>(x + (int64_t)j0 * width + 8 * v));
+      if (j0 >= 0) max_bf16x8_packed(m, *reinterpret_cast<const uint4*>(xv + (int64_t)j0 * width));
       else shadow = true;
     }
-    if (shadow) {  // the zero shadow row takes part in the max
-#pragma unroll
-      for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], 0.f);
-    }
-    uint4 o;
-    o.x = pack_bf16(m[0], m[1]); o.y = pack_bf16(m[2], m[3]); o.z = pack_bf16(m[4], m[5]); o.w = pack_bf16(m[6], m[7]);
+    if (shadow) max_bf16x8_packed(m, make_uint4(0u, 0u, 0u, 0u));  // the zero shadow row takes part in the max
+    const uint4 o = m;
     *reinterpret_cast<uint4*>(out + q * width + 8 * v) = o;
   }
 }

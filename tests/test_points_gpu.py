@@ -15,6 +15,16 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True, params=["per_query", "by_cell"])
+def radius_mode(request):
+    """Every test of this file runs with both neighbour-search kernels: one warp per query (mode 0) and the by-cell
+    kernel (mode 1; automatic selection only picks it for large self searches, which the small fixtures are not)."""
+    L = _lib.lib()
+    assert L.se3et_radius_set_mode(0 if request.param == "per_query" else 1) == 0
+    yield request.param
+    assert L.se3et_radius_set_mode(2) == 0
+
+
 def _t(a, dtype=None):
     return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
 
