@@ -20,6 +20,8 @@ pairs = [synthetic.make_3dmatch_pair(i) for i in range(npairs)]
 lens = np.array([len(c) for p in pairs for c in (p['ref_points'], p['src_points'])], dtype=np.int64)
 pts = torch.from_numpy(np.concatenate([c for p in pairs for c in (p['ref_points'], p['src_points'])])).to(dev)
 L = _lib.lib()
+if os.environ.get('SE3ET_RADIUS_MODE'):
+    L.se3et_radius_set_mode(int(os.environ['SE3ET_RADIUS_MODE']))
 for i in range(passes):
     if i == 1:
         torch.cuda.profiler.start()
