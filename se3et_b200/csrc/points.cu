@@ -1018,12 +1018,13 @@ extern "C" int se3et_radius_neighbors(const float* q_points, const float* s_poin
     qa.q = q_points; qa.nq = nq_total; qa.q_off = w.q_off; qa.s_off = w.s_off; qa.batch = (int)batch; qa.mins = w.mins;
     qa.sorted = w.sorted; qa.start = w.start; qa.mask = mask; qa.inv_cell = inv_cell; qa.r2 = r2; qa.counts = counts;
     qa.out = out; qa.width = width; qa.ns_total = ns_total; qa.status = status; qa.cloud_max = cloud_max;
-    // by cell where it wins (measured on B200, 32 stacked pairs): large self searches (917k points 1.19 -> 0.76 ms,
-    // 272k points 0.35 -> 0.29 ms); cross-level searches have too few queries per cell to amortise the staging and
-    // small clouds too few cells to fill the GPU one warp per cell.  se3et_radius_set_mode overrides (tests).
+    // by cell where it wins (measured on B200, 32 stacked pairs): support sets of 100k points and more (917k points:
+    // 1.19 -> 0.57 ms self, 0.36 -> 0.29 ms from the next level; 272k points: 0.35 -> 0.21 ms); smaller support sets
+    // have too few cells to fill the GPU one warp per cell (74k points: 0.12 -> 0.13 ms, 21k: 0.04 -> 0.10 ms).
+    // se3et_radius_set_mode overrides (tests).
     const int mode = g_radius_mode.load(std::memory_order_relaxed);
     const bool self = q_points == s_points && q_lengths == s_lengths && nq_total == ns_total;
-    const bool by_cell = mode == 1 || (mode == 2 && self && ns_total >= 100000);
+    const bool by_cell = mode == 1 || (mode == 2 && ns_total >= 100000);
     if (!by_cell || ns_total == 0) {
       radius_query_kernel<<<(int)ceil_div(nq_total, kQueryWarps), kQueryWarps * 32, 0, st>>>(qa);
       SE3ET_LAUNCH_CHECK();
