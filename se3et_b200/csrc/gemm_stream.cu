@@ -255,9 +255,7 @@ gemm_stream_gnapply_kernel(const __grid_constant__ CUtensorMap tma_a1, const __g
           if (kDual) tc::tmem_ld_32x32b_x16(taddr + kSBN, r2);
           tc::tmem_ld_wait();
           float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float4 tb = uniform ? lds_f4(table_s + (uint32_t)((c * 16 + j) * 16)) : __ldg(row_tab + c * 16 + j);
+          auto element = [&](int j, const float4 tb) {
             float x = kDual ? fmaf(__uint_as_float(r1[j]), tb.x, fmaf(__uint_as_float(r2[j]), tb.y, tb.z))
                             : fmaf(__uint_as_float(r1[j]), tb.x, tb.z);
             if (!kDual && has_resid) {
@@ -266,6 +264,15 @@ gemm_stream_gnapply_kernel(const __grid_constant__ CUtensorMap tma_a1, const __g
               x += (j & 1) ? __uint_as_float(rw & 0xffff0000u) : __uint_as_float(rw << 16);
             }
             v[j] = fmaxf(x, x * args.slope);  // LeakyReLU for slope <= 1
+          };
+          // two code paths, not a select per element: with `uniform ? lds : ldg` inside the loop the compiler issued
+          // BOTH loads (predicated, as 4-byte pieces) for every element -- four load instructions per output value
+          if (uniform) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) element(j, lds_f4(table_s + (uint32_t)((c * 16 + j) * 16)));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) element(j, __ldg(row_tab + c * 16 + j));
           }
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj) {

@@ -953,7 +953,11 @@ extern "C" int se3et_grid_subsample(const float* points, const int64_t* lengths,
   return SE3ET_OK;
 }
 
-static std::atomic<int> g_radius_mode{2};
+static int radius_mode_default() {
+  const char* e = getenv("SE3ET_RADIUS_MODE");  // A/B measurements: 0 per query, 1 by cell, 2 automatic
+  return (e && e[0] >= '0' && e[0] <= '2' && !e[1]) ? e[0] - '0' : 2;
+}
+static std::atomic<int> g_radius_mode{radius_mode_default()};
 
 extern "C" int se3et_radius_set_mode(int mode) {
   if (mode < 0 || mode > 2) return SE3ET_ERR_ARG;
