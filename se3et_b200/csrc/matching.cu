@@ -48,6 +48,92 @@ __global__ void __launch_bounds__(256) spm_exp_rows_kernel(const float* __restri
   }
 }
 
+// Register-tiled form of the same pass (round 2): a CTA owns 32 ref rows and walks the src rows 128 at a time; the ref
+// block stays in shared memory (k-major), a thread accumulates a 4 x 4 block over k in ascending order (fp32 FMA: the
+// dot products of unit features need fp32 for the 1e-4 score tolerance, so no bf16 tensor-core product), the row sums
+// are a fixed-order reduction (warp tree per column tile, tiles in ascending order): deterministic, 8x fewer
+// instructions than one warp-reduced dot product per matrix entry.
+constexpr int kMatRows = 32, kMatCols = 128, kMatK = 16, kMatMaxC = 256;
+
+__global__ void __launch_bounds__(256) spm_exp_tiles_kernel(const float* __restrict__ ref, const float* __restrict__ src,
+                                                             int C, const uint8_t* __restrict__ ref_mask,
+                                                             const uint8_t* __restrict__ src_mask,
+                                                             const MatchProblem* __restrict__ problems,
+                                                             float* __restrict__ e, float* __restrict__ row_sum) {
+  __shared__ __align__(16) float As[kMatMaxC][kMatRows];  // [k][ref row]
+  __shared__ __align__(16) float Bs[kMatK][kMatCols];     // [k][src row]
+  const MatchProblem pr = problems[blockIdx.y];
+  const int n0 = blockIdx.x * kMatRows;
+  if (n0 >= pr.n_ref) return;
+  const int tid = threadIdx.x, lane = tid & 31, ty = tid >> 5;  // rows 4 ty .. 4 ty + 3, columns 4 lane .. 4 lane + 3
+  const int n_src = (int)pr.n_src, n_ref = (int)pr.n_ref;
+  // the ref block, transposed: thread -> (row = i % 32, four consecutive k)
+  for (int i = tid; i < kMatRows * (C / 4); i += 256) {
+    const int row = i & 31, k4 = (i >> 5) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n0 + row < n_ref) v = *reinterpret_cast<const float4*>(ref + (pr.ref_start + n0 + row) * C + k4);
+    As[k4][row] = v.x; As[k4 + 1][row] = v.y; As[k4 + 2][row] = v.z; As[k4 + 3][row] = v.w;
+  }
+  bool row_on[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + 4 * ty + i;
+    row_on[i] = n < n_ref && (!ref_mask || ref_mask[pr.ref_start + n]);
+  }
+  float rsum[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int m0 = 0; m0 < n_src; m0 += kMatCols) {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < C; k0 += kMatK) {
+      __syncthreads();  // Bs (and, first time, As) ready to be overwritten / read
+      for (int i = tid; i < kMatCols * (kMatK / 4); i += 256) {
+        const int col = i & (kMatCols - 1), k4 = (i / kMatCols) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m0 + col < n_src) v = *reinterpret_cast<const float4*>(src + (pr.src_start + m0 + col) * C + k0 + k4);
+        Bs[k4][col] = v.x; Bs[k4 + 1][col] = v.y; Bs[k4 + 2][col] = v.z; Bs[k4 + 3][col] = v.w;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < kMatK; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[k0 + k][4 * ty]);
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[k][4 * lane]);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+    }
+    bool col_on[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + 4 * lane + j;
+      col_on[j] = m < n_src && (!src_mask || src_mask[pr.src_start + m]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = n0 + 4 * ty + i;
+      float part = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int m = m0 + 4 * lane + j;
+        const float v = (row_on[i] && col_on[j]) ? expf(-fmaxf(2.f - 2.f * acc[i][j], 0.f)) : 0.f;
+        if (n < n_ref && m < n_src) e[pr.e_off + (int64_t)n * n_src + m] = v;
+        part += v;
+      }
+      rsum[i] += warp_sum(part);  // the same value in every lane; column tiles in ascending order
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (n0 + 4 * ty + i < n_ref) row_sum[pr.ref_start + n0 + 4 * ty + i] = rsum[i];
+  }
+}
+
 // one thread per column (fixed-order sum over rows)
 __global__ void __launch_bounds__(128) spm_col_sums_kernel(const float* __restrict__ e,
                                                             const MatchProblem* __restrict__ problems,
@@ -303,9 +389,18 @@ extern "C" int se3et_superpoint_matching(const float* ref_feats, const float* sr
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const auto* pr = reinterpret_cast<const MatchProblem*>(problems);
   if (max_ref > 0 && max_src > 0) {
-    dim3 g1((unsigned)max_ref, (unsigned)num_pairs);
-    spm_exp_rows_kernel<<<g1, 256, sizeof(float) * (channels + 8), st>>>(ref_feats, src_feats, (int)channels, ref_masks,
-                                                                         src_masks, pr, e_workspace, row_sums);
+    const bool tiles = channels % 16 == 0 && channels <= kMatMaxC && !(reinterpret_cast<uintptr_t>(ref_feats) & 15) &&
+                       !(reinterpret_cast<uintptr_t>(src_feats) & 15);
+    if (tiles) {
+      dim3 g1((unsigned)ceil_div(max_ref, kMatRows), (unsigned)num_pairs);
+      spm_exp_tiles_kernel<<<g1, 256, 0, st>>>(ref_feats, src_feats, (int)channels, ref_masks, src_masks, pr,
+                                               e_workspace, row_sums);
+    } else {
+      dim3 g1((unsigned)max_ref, (unsigned)num_pairs);
+      spm_exp_rows_kernel<<<g1, 256, sizeof(float) * (channels + 8), st>>>(ref_feats, src_feats, (int)channels,
+                                                                           ref_masks, src_masks, pr, e_workspace,
+                                                                           row_sums);
+    }
     SE3ET_LAUNCH_CHECK();
     dim3 g2((unsigned)ceil_div(max_src, 128), (unsigned)num_pairs);
     spm_col_sums_kernel<<<g2, 128, 0, st>>>(e_workspace, pr, col_sums);
