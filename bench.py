@@ -132,11 +132,13 @@ def calibrated_limits(cfg, generator, dev=None):
     return [int(v) for v in lim]
 
 
-NCU_KERNEL = {"se3et_kpconv_rows": "kpconv_rows_kernel", "se3et_kpconv_fused": "kpconv_fused_kernel", "se3et_gemm_bf16_gnstats": "gemm_tma_kernel",
-              "se3et_gemm_bf16_gnapply": "gemm_tma_kernel", "se3et_gemm_grouped_bf16": "gemm_tma_kernel",
-              "se3et_gemm_bf16_gnapply_dual": "gemm_dual_gnapply_kernel", "se3et_linear_gnstats_gram": "gram_kernel",
-              "se3et_linear_gnstats_stream": "gnstats_stream_kernel",
-              "se3et_geo_embed_project": "geo_embed_project_kernel", "se3et_geo_embed_lookup": "geo_embed_lookup_kernel", "se3et_radius_neighbors": "radius_query_kernel",
+NCU_KERNEL = {"se3et_kpconv_rows": "rows::kpconv_rows_kernel", "se3et_kpconv_fused": "kpconv_fused_kernel",
+              "se3et_kpconv_lift": "lift::kpconv_lift_kernel", "se3et_gemm_bf16_gnstats": "gemm_tma_kernel",
+              "se3et_gemm_bf16_gnapply": "gemm_stream_gnapply_kernel<0>", "se3et_gemm_grouped_bf16": "gemm_tma_kernel<32, 0>",
+              "se3et_gemm_bf16_gnapply_dual": "gemm_stream_gnapply_kernel<1>", "se3et_linear_gnstats_gram": "gram_kernel",
+              "se3et_linear_gnstats_stream": "gst::gnstats_stream_t_kernel",
+              "se3et_geo_embed_project": "geo_embed_project_kernel", "se3et_geo_embed_lookup": "geo_embed_lookup_kernel",
+              "se3et_radius_neighbors": "radius_cell_kernel", "se3et_maxpool_nbr": "maxpool_nbr_kernel",
               "se3et_groupnorm_double": "groupnorm_double_kernel", "se3et_flash_attention": "flash_attention_kernel"}
 
 

@@ -41,6 +41,17 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
                     points = torch.cat((points[:k0], points[l0:l0 + k1]), dim=0)
                     normals = torch.cat((normals[:k0], normals[l0:l0 + k1]), dim=0)
                     lengths = torch.tensor([k0, k1], dtype=torch.int64, device=points.device)
+            elif bool((lengths > 2000).any()):
+                # stacked pairs: the same cap per cloud, so that a pair gives the same result batched and alone (the
+                # read-back rides on the grid_subsample sync just before; the slicing itself is the rare path)
+                host = [int(v) for v in lengths.tolist()]
+                keep, start = [], 0
+                for l in host:
+                    keep.append(torch.arange(start, start + min(l, 2000), device=points.device))
+                    start += l
+                keep = torch.cat(keep)
+                points, normals = points[keep].contiguous(), normals[keep].contiguous()
+                lengths = torch.tensor([min(l, 2000) for l in host], dtype=torch.int64, device=points.device)
         points_list.append(points)
         lengths_list.append(lengths)
         normals_list.append(normals)

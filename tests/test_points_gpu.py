@@ -137,6 +137,23 @@ def test_batch_of_pairs_equals_pair_by_pair():
         c += sl[i]
 
 
+def test_superpoint_cap_applies_to_stacked_pairs_too():
+    """data.py:34-43 keeps at most 2000 superpoints per cloud; stacked launch sequences apply the same cap per cloud,
+    so that a pair gives the same pyramid batched and alone."""
+    rng = np.random.default_rng(7)
+    clouds = [rng.uniform(0, 1, (n, 3)).astype(np.float32) for n in (6000, 3000, 1500, 5000)]
+    pts, lens = np.concatenate(clouds), np.array([len(c) for c in clouds])
+    d = precompute_data_stack_mode(_t(pts), _t(lens), 2, 0.005, 0.0125, [8, 8])
+    got_l = d["lengths"][1].cpu().numpy()
+    assert got_l.max() == 2000 and got_l[2] < 2000
+    off = np.concatenate([[0], np.cumsum(got_l)])
+    for p in range(2):
+        one = precompute_data_stack_mode(_t(np.concatenate(clouds[2 * p:2 * p + 2])), _t(lens[2 * p:2 * p + 2]), 2, 0.005,
+                                         0.0125, [8, 8])
+        assert np.array_equal(one["lengths"][1].cpu().numpy(), got_l[2 * p:2 * p + 2])
+        assert np.array_equal(one["points"][1].cpu().numpy(), d["points"][1][off[2 * p]:off[2 * p + 2]].cpu().numpy())
+
+
 def test_rejects_bad_arguments():
     pts = torch.zeros(4, 3, device=DEV)
     with pytest.raises(RuntimeError, match="float"):
