@@ -386,7 +386,7 @@ def measure_train(args, world, rank, dev, steps=None, warmup=None):
     from se3et_b200 import training as TR
     from se3et_b200.model import create_model, make_cfg
     steps = steps or max(2, min(args.steps, 5))
-    warmup = warmup if warmup is not None else 2
+    warmup = warmup if warmup is not None else 4   # every one of the four synthetic pairs once: allocator / cuBLAS warm for its shapes
     cfg = make_cfg("se3eti.3dmatch")
     TR.RECOMPUTE['autocast'] = torch.bfloat16   # configs[4]: bf16 (operands; statistics, losses and the optimizer stay fp32)
     torch.manual_seed(0)
