@@ -81,13 +81,12 @@ class _Bf16Cache:
                     self._val, self._event, self._synced = val, ev, synced
                     self._key = key  # last: whoever sees the key sees the value and its event
         val = self._val
-        if val.is_cuda:
+        if val.is_cuda and _lib._raw_stream(val.device.index) not in self._synced:   # raw handle: this is a hot path
             st = torch.cuda.current_stream(val.device)
-            if st.cuda_stream not in self._synced:
-                with self._lock:
-                    if self._event is not None:
-                        st.wait_event(self._event)
-                    self._synced.add(st.cuda_stream)
+            with self._lock:
+                if self._event is not None:
+                    st.wait_event(self._event)
+                self._synced.add(st.cuda_stream)
         return val
 
 
