@@ -380,6 +380,68 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
   }
 }
 
+// C a multiple of 256 (the transformer's hidden width): a lane owns 8 consecutive columns per 256-column chunk, so x is read
+// as two 16-byte loads, the residual as one and the bf16 result written as one (the scalar form above moves 4 / 2 bytes
+// per instruction: 2.8 TB/s on 130k x 256 rows)
+template <int kChunks>
+__global__ void __launch_bounds__(256) add_layernorm_vec_kernel(const float* __restrict__ x,
+                                                                 const __nv_bfloat16* __restrict__ resid, int resid_div,
+                                                                 int64_t rows, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, float eps,
+                                                                 float* __restrict__ out_f32,
+                                                                 __nv_bfloat16* __restrict__ out_bf16) {
+  constexpr int C = 256 * kChunks;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float v[kChunks][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < kChunks; ++k) {
+    const int c = 256 * k + 8 * lane;
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(x + row * C + c));
+    const float4 b = __ldcs(reinterpret_cast<const float4*>(x + row * C + c + 4));
+    v[k][0] = a.x; v[k][1] = a.y; v[k][2] = a.z; v[k][3] = a.w;
+    v[k][4] = b.x; v[k][5] = b.y; v[k][6] = b.z; v[k][7] = b.w;
+    if (resid) {
+      float r[8];
+      bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(resid + (row / resid_div) * C + c)), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[k][j] += r[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[k][j];
+  }
+  const float mean = warp_sum(s) / C;
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < kChunks; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float dlt = v[k][j] - mean;
+      ss += dlt * dlt;
+    }
+  const float rstd = rsqrtf(warp_sum(ss) / C + eps);
+#pragma unroll
+  for (int k = 0; k < kChunks; ++k) {
+    const int c = 256 * k + 8 * lane;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (v[k][j] - mean) * rstd * g[j] + bb[j];
+    if (out_f32) {
+      *reinterpret_cast<float4*>(out_f32 + row * C + c) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(out_f32 + row * C + c + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+    if (out_bf16)
+      *reinterpret_cast<uint4*>(out_bf16 + row * C + c) =
+          make_uint4(pack2_bf16(o[0], o[1]), pack2_bf16(o[2], o[3]), pack2_bf16(o[4], o[5]), pack2_bf16(o[6], o[7]));
+  }
+}
+
 __global__ void __launch_bounds__(256) l2_normalize_rows_kernel(const float* __restrict__ x, int64_t rows, int C,
                                                                  float eps, float* __restrict__ out) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -472,6 +534,15 @@ extern "C" int se3et_add_layernorm(const float* x, const void* resid_bf16, int64
   auto* ob = static_cast<__nv_bfloat16*>(out_bf16);
   const unsigned blocks = (unsigned)ceil_div(rows, 8);
   const int C = (int)channels;
+  const bool aligned = !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(gamma) |
+                          reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(out_f32) |
+                          reinterpret_cast<uintptr_t>(ob)) & 15);
+  if (aligned && (C == 256 || C == 512)) {
+    if (C == 256) add_layernorm_vec_kernel<1><<<blocks, 256, 0, st>>>(x, r, (int)resid_div, rows, gamma, beta, eps, out_f32, ob);
+    else add_layernorm_vec_kernel<2><<<blocks, 256, 0, st>>>(x, r, (int)resid_div, rows, gamma, beta, eps, out_f32, ob);
+    SE3ET_LAUNCH_CHECK();
+    return SE3ET_OK;
+  }
   if (C <= 64) add_layernorm_kernel<2><<<blocks, 256, 0, st>>>(x, r, (int)resid_div, rows, C, gamma, beta, eps, out_f32, ob);
   else if (C <= 128) add_layernorm_kernel<4><<<blocks, 256, 0, st>>>(x, r, (int)resid_div, rows, C, gamma, beta, eps, out_f32, ob);
   else if (C <= 256) add_layernorm_kernel<8><<<blocks, 256, 0, st>>>(x, r, (int)resid_div, rows, C, gamma, beta, eps, out_f32, ob);

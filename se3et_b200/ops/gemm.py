@@ -185,7 +185,7 @@ def dual_apply_supported(n, k1, k2):
     return n % 32 == 0 and k1 % 8 == 0 and k2 % 8 == 0
 
 
-_GRAM = {'on': True}
+_GRAM = {'on': True, 'min_n': 256}
 
 
 # A/B switch (tests, measurements): the streaming statistics pass is the product path
@@ -212,8 +212,10 @@ def linear_gn_stats_stream(a, w, bias, groups, seg_off, rows_per_point):
 
 
 def gram_stats_supported(n, k):
-    """The Gram-matrix statistics pass pays off when the Linear widens (its cost does not depend on n)."""
-    return _GRAM['on'] and k in (32, 64, 128) and n >= 2 * k
+    """The Gram-matrix statistics pass pays off when the Linear widens beyond what the streaming kernel covers in one
+    pass over A (its cost does not depend on n).  Up to 256 output columns the transposed streaming kernel reads A once
+    too, at 4.5 TB/s against the Gram kernel's 2-3.4 TB/s plus its finalize launch (measured on B200, round 2)."""
+    return _GRAM['on'] and k in (32, 64, 128) and n >= 2 * k and n > _GRAM['min_n']
 
 
 def linear_gn_stats_gram(a, w, bias, groups, seg_off, rows_per_point):
