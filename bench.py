@@ -175,7 +175,7 @@ def algorithmic_work(cfg, n_levels, n_ref_c, n_src_c, limits):
 
     def stats_pass(rows, k, n):
         # ops/gemm.py:linear_gn_stats: Gram matrix of the input for widening Linears with a small K, else the streaming pass
-        ub["gram" if (k in (32, 64, 128) and n >= 2 * k and n > 256) else "stream"] += rows * k * 2
+        ub["gram" if (k in (32, 64, 128) and n >= 2 * k) else "stream"] += rows * k * 2
 
     def block(nq, ns, h, cin, cout, strided):
         nonlocal norm_bytes

@@ -245,7 +245,8 @@ class KPConvInterSO3(nn.Module):
                 # round 2: a thread per point + mma.sync for the 16 -> 6 * Cout product (csrc/kpconv_lift.cu)
                 return K.kpconv_lift(q_pts, s_pts, neighb_inds.contiguous(), _act(x[:, 0, 0]).contiguous(), w36,
                                      self.kernel_points, self.KP_extent, gn=(groups, seg),
-                                     out_bf16=allow_bf16 and _GFLAGS['conv_bf16'])
+                                     out_bf16=allow_bf16 and _GFLAGS['conv_bf16'] and
+                                     K.groupnorm_double_supported(self.out_channels, bf16=True))
             return K.kpconv_cin1(q_pts, s_pts, neighb_inds.contiguous(), _act(x[:, 0, 0]).contiguous(), w36,
                                  self.kernel_points, self.KP_extent, gn=(groups, seg), lifted=True)
         if _GFLAGS['cin1_kernel'] and cin1_ok:
@@ -256,7 +257,8 @@ class KPConvInterSO3(nn.Module):
             if _GFLAGS['conv_stats_stream'] and K.groupnorm_double_supported(self.out_channels):
                 # the statistics as a streaming pass over the (small) conv output: in the fused kernel's epilogue they
                 # sit on the producers' critical path (4-10 % of that kernel), here they cost one read of y
-                y = self._conv(q_pts, s_pts, neighb_inds, x, out_bf16=allow_bf16 and _GFLAGS['conv_bf16'])
+                y = self._conv(q_pts, s_pts, neighb_inds, x, out_bf16=allow_bf16 and _GFLAGS['conv_bf16'] and
+                               K.groupnorm_double_supported(self.out_channels, bf16=True))
                 return y, K.groupnorm_stats_stream(y, groups, seg, self.kanchor)
             return K.kpconv_fused(q_pts, s_pts, neighb_inds.contiguous(), _act(x).contiguous(), self._w_fused(),
                                   self.kernel_points, self.KP_extent, gn=(groups, seg))

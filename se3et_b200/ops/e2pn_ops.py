@@ -189,9 +189,11 @@ def kpconv_rows(q_pts, s_pts, neighbors, x_bf16, w_rows, kernel_points, kp_exten
     return out
 
 
-def groupnorm_double_supported(channels):
+def groupnorm_double_supported(channels, bf16=False):
+    """Row widths se3et_groupnorm_double covers; bf16=True: for a bf16 input (8 columns per thread)."""
     v = channels // 4
-    return channels % 4 == 0 and 0 < v <= 256 and (v & (v - 1)) == 0
+    ok = channels % 4 == 0 and 0 < v <= 256 and (v & (v - 1)) == 0
+    return ok and (not bf16 or (channels % 8 == 0 and v >= 2))
 
 
 def groupnorm_double(y, stats1, gamma1, beta1, gamma2, beta2, groups, seg_off, rows_per_point, slope=0.1, eps=1e-5):

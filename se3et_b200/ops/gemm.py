@@ -185,7 +185,7 @@ def dual_apply_supported(n, k1, k2):
     return n % 32 == 0 and k1 % 8 == 0 and k2 % 8 == 0
 
 
-_GRAM = {'on': True, 'min_n': 256}
+_GRAM = {'on': True, 'min_n': 0}
 
 
 # A/B switch (tests, measurements): the streaming statistics pass is the product path
@@ -212,9 +212,10 @@ def linear_gn_stats_stream(a, w, bias, groups, seg_off, rows_per_point):
 
 
 def gram_stats_supported(n, k):
-    """The Gram-matrix statistics pass pays off when the Linear widens beyond what the streaming kernel covers in one
-    pass over A (its cost does not depend on n).  Up to 256 output columns the transposed streaming kernel reads A once
-    too, at 4.5 TB/s against the Gram kernel's 2-3.4 TB/s plus its finalize launch (measured on B200, round 2)."""
+    """The Gram-matrix statistics pass pays off when the Linear widens (its cost does not depend on n).  Measured on
+    B200 (round 2): sending the widening Linears with n <= 256 to the transposed streaming kernel instead (min_n = 256)
+    is no faster -- Gram 2.58 -> 0.76 ms but streaming 3.90 -> 5.93 ms per 64 pairs: at K = 32 / 64 a 128-row tile is
+    only 8-16 KB and the per-tile hand-offs dominate -- so the Gram pass keeps them."""
     return _GRAM['on'] and k in (32, 64, 128) and n >= 2 * k and n > _GRAM['min_n']
 
 
