@@ -518,6 +518,7 @@ def main():
                    "se3et_linear_gnstats_stream", "se3et_gemm_grouped_bf16", "se3et_groupnorm_double",
                    "se3et_groupnorm_apply", "se3et_groupnorm_stats", "se3et_maxpool_nbr", "se3et_radius_neighbors", "se3et_grid_subsample",
                    "se3et_geo_embed_project", "se3et_geo_embed_lookup", "se3et_geo_embed_indices", "se3et_flash_attention",
+                   "se3et_linear_add_layernorm", "se3et_add_layernorm",
                    "se3et_superpoint_matching", "se3et_point_to_node_partition"]
     L.enabled = True
     L.reset(timed=timed_names if args.streams <= 1 else ())

@@ -384,6 +384,15 @@ int se3et_sh_bias_add(const float* points, const int64_t* problems, int64_t num_
 int se3et_add_layernorm(const float* x, const void* resid_bf16, int64_t resid_div, int64_t rows, int64_t channels,
                         const float* gamma, const float* beta, float eps, float* out_f32, void* out_bf16,
                         se3et_stream_t stream);
+
+/* linear_add_layernorm -- `linear` / `squeeze` + residual + LayerNorm of the transformer layers in one kernel
+ * (rpe_transformer.py:163-175, vanilla_transformer.py:905-913, output_layer.py:17-22):
+ *   out = LayerNorm(resid[row / resid_div] + a W^T + bias),  a bf16 [m, k], W bf16 [n, k], out bf16 [m, n].
+ * The fp32 Linear output never reaches memory.  n must be 256 (the hidden width of every SE3ET variant) and k a
+ * multiple of 8; otherwise SE3ET_ERR_UNSUPPORTED and the host uses se3et_gemm_bf16 + se3et_add_layernorm. */
+int se3et_linear_add_layernorm(const void* a_bf16, int64_t lda, const void* w_bf16, int64_t ldw, int64_t m, int64_t n,
+                               int64_t k, const float* bias, const void* resid_bf16, int64_t resid_div,
+                               const float* gamma, const float* beta, float eps, void* out_bf16, se3et_stream_t stream);
 /* F.normalize(x, p=2, dim=1) (experiments/se3eti.3dmatch/model.py:156-157). */
 int se3et_l2_normalize_rows(const float* x, int64_t rows, int64_t channels, float eps, float* out,
                             se3et_stream_t stream);

@@ -211,7 +211,10 @@ class AttentionOutput(nn.Module):
     def fused(self, x, out=None):
         """x bf16 (rows, C) -> bf16 (rows, C)."""
         _, h = linear_bf16(x, self._we.get(self.expand.weight), self.expand.bias, relu=True, out_f32=False, out_bf16=True)
-        z, _ = linear_bf16(h, self._ws.get(self.squeeze.weight), self.squeeze.bias)
+        ws = self._ws.get(self.squeeze.weight)
+        if T.linear_add_layernorm_supported(h, ws):   # squeeze + residual + LayerNorm in one kernel
+            return T.linear_add_layernorm(h, ws, self.squeeze.bias, x, 1, self.norm.weight, self.norm.bias, self.norm.eps)
+        z, _ = linear_bf16(h, ws, self.squeeze.bias)
         _, y = T.add_layernorm(z, x, 1, self.norm.weight, self.norm.bias, self.norm.eps)
         return y
 
@@ -308,7 +311,10 @@ class RPEAttentionLayer(nn.Module):
 
     def fused(self, x, emb, ctx, points=None, anchors_mat=None):
         hid = self.attention.fused(x, emb, ctx, points, anchors_mat)
-        y, _ = linear_bf16(hid, self._wl.get(self.linear.weight), self.linear.bias)
+        wl = self._wl.get(self.linear.weight)
+        if T.linear_add_layernorm_supported(hid, wl):
+            return T.linear_add_layernorm(hid, wl, self.linear.bias, x, 1, self.norm.weight, self.norm.bias, self.norm.eps)
+        y, _ = linear_bf16(hid, wl, self.linear.bias)
         _, out = T.add_layernorm(y, x, 1, self.norm.weight, self.norm.bias, self.norm.eps)
         return out
 
@@ -476,15 +482,23 @@ class AttentionLayer(nn.Module):
 
     def fused(self, q_inv, k_inv, v_eq, problems, max_q, anchors):
         hid = self.attention.fused(q_inv, k_inv, v_eq, problems, max_q, anchors)
-        y, _ = linear_bf16(hid, self._wl.get(self.linear.weight), self.linear.bias)
+        wl = self._wl.get(self.linear.weight)
         # (N, C) residual broadcast onto (A, N, C) (vanilla_transformer.py:911)
+        if T.linear_add_layernorm_supported(hid, wl):
+            return T.linear_add_layernorm(hid, wl, self.linear.bias, q_inv, anchors, self.norm.weight, self.norm.bias,
+                                          self.norm.eps)
+        y, _ = linear_bf16(hid, wl, self.linear.bias)
         _, out = T.add_layernorm(y, q_inv, anchors, self.norm.weight, self.norm.bias, self.norm.eps)
         return out
 
     def fused_eq(self, x_q, x_k, problems, max_q, cloud_off, anchors):
         """equivariant layer (vanilla_transformer.py:886-915): x_q (Nq*A, C), x_k (Nk*A, C) -> ((Nq*A, C), W, attn_r)."""
         hid, w, attn_r = self.attention.fused(x_q, x_k, problems, max_q, cloud_off, anchors)
-        y, _ = linear_bf16(hid, self._wl.get(self.linear.weight), self.linear.bias)
+        wl = self._wl.get(self.linear.weight)
+        if T.linear_add_layernorm_supported(hid, wl):
+            return T.linear_add_layernorm(hid, wl, self.linear.bias, x_q, 1, self.norm.weight, self.norm.bias,
+                                          self.norm.eps), w, attn_r
+        y, _ = linear_bf16(hid, wl, self.linear.bias)
         _, out = T.add_layernorm(y, x_q, 1, self.norm.weight, self.norm.bias, self.norm.eps)
         return out, w, attn_r
 

@@ -78,6 +78,31 @@ def add_layernorm(x, resid, resid_div, gamma, beta, eps=1e-5, out_f32=False, out
     return of, ob
 
 
+FUSED_LN = {'on': True}
+
+
+def linear_add_layernorm_supported(a, w):
+    return FUSED_LN['on'] and w.shape[0] == 256 and a.shape[1] % 8 == 0 and a.shape[0] > 0
+
+
+def linear_add_layernorm(a, w, bias, resid, resid_div, gamma, beta, eps=1e-5):
+    """bf16 LayerNorm(resid[row // resid_div] + a @ w.T + bias) in one kernel (se3et_linear_add_layernorm); a bf16
+    (rows, K), w bf16 (256, K), resid bf16 (ceil(rows / resid_div), 256)."""
+    _lib.require_cuda(a, w, resid, gamma, beta)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
+    assert a.stride(1) == 1 and w.stride(1) == 1 and a.shape[1] == w.shape[1]
+    assert resid.dtype == torch.bfloat16 and resid.is_contiguous() and resid.shape[1] == w.shape[0]
+    assert gamma.dtype == torch.float32 and beta.dtype == torch.float32
+    rows, k = a.shape
+    n = w.shape[0]
+    out = torch.empty((rows, n), dtype=torch.bfloat16, device=a.device)
+    _lib.check(_lib.lib().se3et_linear_add_layernorm(
+        _lib.ptr(a), _lib.i64(a.stride(0) if rows > 1 else k), _lib.ptr(w), _lib.i64(w.stride(0)), _lib.i64(rows),
+        _lib.i64(n), _lib.i64(k), _lib.ptr(bias), _lib.ptr(resid), _lib.i64(resid_div), _lib.ptr(gamma), _lib.ptr(beta),
+        _lib.f32(eps), _lib.ptr(out), _lib.stream_ptr()), "linear_add_layernorm")
+    return out
+
+
 def l2_normalize_rows(x, eps=1e-12):
     assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
     out = torch.empty_like(x)

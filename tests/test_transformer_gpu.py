@@ -119,6 +119,28 @@ def test_add_layernorm_and_l2_normalize():
     assert torch.allclose(n, torch.nn.functional.normalize(x, p=2, dim=1), rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("rows,k,div", [(1000, 256, 1), (777, 512, 1), (6 * 301, 256, 6), (128, 64, 1), (5, 256, 1)])
+def test_linear_add_layernorm_matches_torch(rows, k, div):
+    """se3et_linear_add_layernorm (Linear + residual + LayerNorm in one tcgen05 kernel) against torch fp32 on the same
+    bf16 operands: ragged last tile, both K of the model (256: `linear`, 512: `squeeze`), the (N, C) residual broadcast
+    over anchors (resid_div = 6); and against the two-kernel form it replaces."""
+    g = torch.Generator().manual_seed(rows + k)
+    a = (torch.randn(rows, k, generator=g) * 0.7).bfloat16()
+    w = (torch.randn(256, k, generator=g) / k ** 0.5).bfloat16()
+    b = torch.randn(256, generator=g) * 0.1
+    resid = (torch.randn((rows + div - 1) // div, 256, generator=g) * 1.5 + 0.3).bfloat16()
+    gamma, beta = torch.randn(256, generator=g), torch.randn(256, generator=g)
+    y = a.float() @ w.float().t() + b + resid.float().repeat_interleave(div, 0)[:rows]
+    want = torch.nn.functional.layer_norm(y, (256,), gamma, beta, 1e-5)
+    got = T.linear_add_layernorm(a.to(DEV), w.to(DEV), b.to(DEV), resid.to(DEV), div, gamma.to(DEV), beta.to(DEV), 1e-5)
+    assert got.dtype == torch.bfloat16 and got.shape == (rows, 256)
+    assert torch.allclose(got.float().cpu(), want, rtol=2e-2, atol=2e-2), (got.float().cpu() - want).abs().max()
+    from se3et_b200.ops.gemm import linear_bf16
+    z, _ = linear_bf16(a.to(DEV), w.to(DEV), b.to(DEV))
+    _, two = T.add_layernorm(z, resid.to(DEV), div, gamma.to(DEV), beta.to(DEV), 1e-5)
+    assert torch.allclose(got.float(), two.float(), rtol=2e-2, atol=2e-2)
+
+
 def test_transformer_matches_oracle_and_reference(gold):
     S = helpers.SMALL_CFG
     rp, sp, rf, sf = coarse_inputs(gold)
