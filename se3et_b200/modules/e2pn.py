@@ -64,14 +64,17 @@ class _Bf16Cache:
         self._key, self._val, self._event, self._synced = None, None, None, set()
         self._lock = threading.Lock()
 
-    def get(self, p, transform=None):
+    def get(self, p, transform=None, extra=None, dtype=torch.bfloat16):
+        """`extra`: a second parameter the transform reads (its version joins the key); `dtype`: of the cached copy."""
         key = (p.data_ptr(), p._version, p.device)
+        if extra is not None:
+            key = key + (extra.data_ptr(), extra._version)
         if key != self._key:
             with self._lock:
                 if key != self._key:
                     with torch.no_grad():
                         v = p.detach() if transform is None else transform(p.detach())
-                        val = v.to(torch.bfloat16).contiguous()
+                        val = v.to(dtype).contiguous()
                     ev, synced = None, set()
                     if val.is_cuda:
                         st = torch.cuda.current_stream(val.device)

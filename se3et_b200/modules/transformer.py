@@ -36,6 +36,10 @@ from .e2pn import _Bf16Cache, _act
 _EMBED_TABLE = {'on': True}
 
 
+# A/B switch (tests): the positional query projection folded into one Linear of the layer input
+_QP_FOLDED = {'on': True}
+
+
 class CloudContext:
     """Flat layout bookkeeping for a batch of pairs. sizes = [n_ref_0.., n_src_0..] (python ints)."""
 
@@ -242,7 +246,7 @@ class RPEMultiHeadAttention(nn.Module):
         self.proj_p = nn.Linear(d_model, d_model)
         if self.equivariant and d_equiv_embed > 0:
             self.proj_eq = nn.Linear(d_equiv_embed, d_model)
-        self._wqkv, self._wpt, self._wu = _Bf16Cache(), _Bf16Cache(), _Bf16Cache()
+        self._wqkv, self._wpt, self._wu, self._bqp = _Bf16Cache(), _Bf16Cache(), _Bf16Cache(), _Bf16Cache()
 
     def _u_weight(self):
         """(16, C) bf16, block diagonal over heads: row 3 h + d = proj_eq.weight[head h channels, 1 + d]."""
@@ -263,13 +267,27 @@ class RPEMultiHeadAttention(nn.Module):
                                                                     self.proj_v.weight.detach()], 0))
         b = torch.cat([self.proj_q.bias, self.proj_k.bias, self.proj_v.bias]).detach()
         _, qkv = linear_bf16(x, w, b, out_f32=False, out_bf16=True)  # (T*A, 3C)
-        # qp[(n,a), h, :] = W_p[h]^T q[(n,a), h]  (the proj_p bias only shifts every key equally: softmax-invariant)
-        wpt = self._wpt.get(self.proj_p.weight, lambda p: p.t())
+        # qp[(n,a), h, :] = W_p[h]^T q[(n,a), h]  (the proj_p bias only shifts every key equally: softmax-invariant).
+        # With q = W_q x + b_q this is ONE Linear of x: qp[h] = (W_p[h]^T W_q[h]) x + W_p[h]^T b_q[h] -- the four per-head
+        # GEMMs on the bf16 q (and q's rounding in between) become a single launch with 4 C output columns
         rows = x.shape[0]
-        qp = torch.empty((rows, h * c), dtype=torch.bfloat16, device=x.device)
-        for i in range(h):
-            linear_bf16(qkv[:, i * hc:(i + 1) * hc], wpt[:, i * hc:(i + 1) * hc], out_f32=False,
-                        out_bf16=qp[:, i * c:(i + 1) * c])
+        if _QP_FOLDED['on']:
+            def fold(p):
+                wq, wp = self.proj_q.weight.detach().float(), p.float()
+                return torch.cat([wp[i * hc:(i + 1) * hc].t() @ wq[i * hc:(i + 1) * hc] for i in range(h)], 0)  # (h C, C)
+            wqp = self._wpt.get(self.proj_p.weight, fold, extra=self.proj_q.weight)
+
+            def fold_bias(p):
+                bq, wp = self.proj_q.bias.detach().float(), p.float()
+                return torch.cat([wp[i * hc:(i + 1) * hc].t() @ bq[i * hc:(i + 1) * hc] for i in range(h)])
+            bqp = self._bqp.get(self.proj_p.weight, fold_bias, extra=self.proj_q.bias, dtype=torch.float32)
+            _, qp = linear_bf16(x, wqp, bqp, out_f32=False, out_bf16=True)
+        else:
+            wpt = self._wpt.get(self.proj_p.weight, lambda p: p.t())
+            qp = torch.empty((rows, h * c), dtype=torch.bfloat16, device=x.device)
+            for i in range(h):
+                linear_bf16(qkv[:, i * hc:(i + 1) * hc], wpt[:, i * hc:(i + 1) * hc], out_f32=False,
+                            out_bf16=qp[:, i * c:(i + 1) * c])
         ah = a * h
         s_p = torch.empty((ctx.R * ah,), dtype=torch.float32, device=x.device)
         T.gemm_grouped_t(emb, ctx.R, qp.view(rows * h, c), rows * h, ctx.rpe_groups, ctx.max_n, (ah + 15) // 16 * 16, ah,
