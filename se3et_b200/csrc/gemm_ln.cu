@@ -11,6 +11,8 @@
 //   warps 2-9  epilogue: thread = one row (TMEM lane) x 128 of the 256 columns (two warps share a lane quarter).  The 128
 //              values stay in registers: + bias + residual, row mean and centred variance (two-pass, as nn.LayerNorm; the
 //              two half-row partials meet through shared memory and a 64-thread named barrier), normalise, bf16 out.
+//              Measured and rejected: residual in / result out through a per-warp staging buffer (whole 256-byte row
+//              segments per instruction instead of 32 half-used sectors) with a 3-stage ring: 87 -> 122 us for 130k rows.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
