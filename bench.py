@@ -70,7 +70,7 @@ class ClockSampler(threading.Thread):
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
@@ -522,8 +522,11 @@ def main():
                    "se3et_superpoint_matching", "se3et_point_to_node_partition"]
     L.enabled = True
     L.reset(timed=timed_names if args.streams <= 1 else ())
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    # rank 0 alone samples (all GPUs of the job, one nvidia-smi process): eight 10 Hz pollers, one per rank, hold the
+    # driver's locks often enough to show up in the launch path at 8 GPUs
+    sampler = ClockSampler(",".join(str(i) for i in range(world))) if rank == 0 else None
+    if sampler is not None:
+        sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -531,7 +534,7 @@ def main():
         step_device()
     e1.record()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler is not None else None
     L.enabled = False
     ms = e0.elapsed_time(e1)
     launches = L.launches()
