@@ -40,7 +40,7 @@ struct StreamArgs {
   int64_t ldc;
   const int64_t* seg_off;
   int nseg, cpg, groups, rpp;
-  const float4* tab;    // [nseg][N] {scale1, scale2, shift, -} from gn_table_kernel; NULL = plain Linear (below)
+  const float4* tab;    // [nseg][N] {scale1, shift, scale2, -} from gn_table_kernel; NULL = plain Linear (below)
   float slope;
   const float* plain_bias;  // plain mode: out = act(alpha * acc + bias), act = LeakyReLU_slope (slope 0 = ReLU, 1 = none)
   float plain_alpha;
@@ -56,7 +56,7 @@ __device__ __forceinline__ float2 stream_affine(const StreamNorm& n, int seg, in
   return make_float2(sc, __ldg(n.beta + c) + (b - (float)mean) * sc);
 }
 
-// tab[seg][c] = {scale1, scale2, shift1 + shift2, 0}: y -> (y + bias - mean) * rstd * gamma + beta folded per pair and
+// tab[seg][c] = {scale1, shift1 + shift2, scale2, 0} (scale and shift adjacent: one 8-byte load on the single-Linear path): y -> (y + bias - mean) * rstd * gamma + beta folded per pair and
 // column, so that the GEMM epilogue is one table load and one or two FMAs per element (no fp64 there)
 __global__ void gn_table_kernel(StreamNorm n1, StreamNorm n2, int dual, const int64_t* __restrict__ seg_off, int rpp,
                                 int N, int groups, float eps, float4* __restrict__ tab) {
@@ -68,11 +68,11 @@ __global__ void gn_table_kernel(StreamNorm n1, StreamNorm n2, int dual, const in
     if (cnt > 0.0) {
       const float2 f1 = stream_affine(n1, seg, c, groups, cpg, cnt, eps);
       o.x = f1.x;
-      o.z = f1.y;
+      o.y = f1.y;
       if (dual) {
         const float2 f2 = stream_affine(n2, seg, c, groups, cpg, cnt, eps);
-        o.y = f2.x;
-        o.z += f2.y;
+        o.z = f2.x;
+        o.y += f2.y;
       }
     }
     tab[(int64_t)seg * N + c] = o;
@@ -196,7 +196,7 @@ gemm_stream_gnapply_kernel(const __grid_constant__ CUtensorMap tma_a1, const __g
       const float4* row_tab = args.tab;
       if (warp_ok) {
         const int64_t wlast = min(wfirst + 31, (int64_t)args.M - 1);
-        if (!args.tab) {  // plain Linear: one segment, the table row is {alpha, 0, bias}
+        if (!args.tab) {  // plain Linear: one segment, the table row is {alpha, bias, 0}
           seg_lo = 0;
           seg_hi = args.M;
         } else if (!(wfirst >= seg_lo && wlast < seg_hi)) {
@@ -208,8 +208,8 @@ gemm_stream_gnapply_kernel(const __grid_constant__ CUtensorMap tma_a1, const __g
         if (uniform) {
           // this warp's 32 columns of the pair's table: one coalesced 512-byte load, broadcast from shared memory
           const float4 te = args.tab ? __ldg(args.tab + (int64_t)seg_cached * args.N + n0 + lane)
-                                     : make_float4(args.plain_alpha, 0.f,
-                                                   args.plain_bias ? __ldg(args.plain_bias + n0 + lane) : 0.f, 0.f);
+                                     : make_float4(args.plain_alpha,
+                                                   args.plain_bias ? __ldg(args.plain_bias + n0 + lane) : 0.f, 0.f, 0.f);
           __syncwarp();
           table[lane] = te;
           __syncwarp();
@@ -256,8 +256,8 @@ gemm_stream_gnapply_kernel(const __grid_constant__ CUtensorMap tma_a1, const __g
           tc::tmem_ld_wait();
           float v[16];
           auto element = [&](int j, const float4 tb) {
-            float x = kDual ? fmaf(__uint_as_float(r1[j]), tb.x, fmaf(__uint_as_float(r2[j]), tb.y, tb.z))
-                            : fmaf(__uint_as_float(r1[j]), tb.x, tb.z);
+            float x = kDual ? fmaf(__uint_as_float(r1[j]), tb.x, fmaf(__uint_as_float(r2[j]), tb.z, tb.y))
+                            : fmaf(__uint_as_float(r1[j]), tb.x, tb.y);
             if (!kDual && has_resid) {
               const uint4 rq = res[c * 2 + (j >> 3)];
               const uint32_t rw = ((j >> 1) & 3) == 0 ? rq.x : (((j >> 1) & 3) == 1 ? rq.y : (((j >> 1) & 3) == 2 ? rq.z : rq.w));
