@@ -514,7 +514,7 @@ def main():
 
     # ---- timed region: K steps, CUDA events, per-entry-point events for the roofline
     timed_names = ["se3et_kpconv_rows", "se3et_kpconv_fused", "se3et_kpconv_cin1", "se3et_kpconv_lift", "se3et_kpconv_gather", "se3et_gemm_bf16", "se3et_gemm_bf16_gnstats",
-                   "se3et_gemm_bf16_gnapply", "se3et_gemm_bf16_gnapply_dual", "se3et_linear_gnstats_gram",
+                   "se3et_gemm_bf16_gnapply", "se3et_gemm_bf16_gnapply_dual", "se3et_linear_gnstats_gram", "se3et_linear_gnstats_gram2",
                    "se3et_linear_gnstats_stream", "se3et_gemm_grouped_bf16", "se3et_groupnorm_double",
                    "se3et_groupnorm_apply", "se3et_groupnorm_stats", "se3et_maxpool_nbr", "se3et_radius_neighbors", "se3et_grid_subsample",
                    "se3et_geo_embed_project", "se3et_geo_embed_lookup", "se3et_geo_embed_indices", "se3et_flash_attention",

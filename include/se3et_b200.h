@@ -166,6 +166,13 @@ int se3et_linear_gnstats_gram(const void* a, int64_t lda, int64_t m, int64_t k, 
                               int64_t n, const float* bias, const int64_t* seg_offsets, int64_t nseg, int64_t groups,
                               int64_t rows_per_point, int64_t upper_tiles, void* workspace, size_t workspace_bytes,
                               double* stats, se3et_stream_t stream);
+/* The same for TWO Linears on the same input in one pass over A (the block input of ResnetBottleneckBlockEPN feeds unary1
+ * and the shortcut Linear, blocks_epn.py:833-852): the Gram matrix is built once, finalised twice. */
+int se3et_linear_gnstats_gram2(const void* a, int64_t lda, int64_t m, int64_t k, const void* w1_bf16, int64_t ldw1,
+                               int64_t n1, const float* bias1, int64_t groups1, double* stats1, const void* w2_bf16,
+                               int64_t ldw2, int64_t n2, const float* bias2, int64_t groups2, double* stats2,
+                               const int64_t* seg_offsets, int64_t nseg, int64_t rows_per_point, void* workspace,
+                               size_t workspace_bytes, se3et_stream_t stream);
 
 /* Tail of ResnetBottleneckBlockEPN (blocks_epn.py:833-852) in one kernel:
  *   out_bf16 = LeakyReLU_slope( GroupNorm_1(A1 B1^T + bias1) + GroupNorm_2(A2 B2^T + bias2) )

@@ -25,7 +25,7 @@ _lib = None
 
 # kernels launched by one call of each entry point (cudaMemsetAsync nodes are not counted)
 KERNELS_PER_CALL = {
-    "se3et_grid_subsample": 16, "se3et_radius_neighbors": 9, "se3et_gemm_bf16": 1, "se3et_gemm_bf16_gnstats": 1, "se3et_gemm_bf16_gnapply": 2, "se3et_gemm_bf16_gnapply_dual": 2, "se3et_linear_gnstats_gram": 2, "se3et_linear_gnstats_stream": 1, "se3et_gemm_grouped_bf16": 1,
+    "se3et_grid_subsample": 16, "se3et_radius_neighbors": 9, "se3et_gemm_bf16": 1, "se3et_gemm_bf16_gnstats": 1, "se3et_gemm_bf16_gnapply": 2, "se3et_gemm_bf16_gnapply_dual": 2, "se3et_linear_gnstats_gram": 2, "se3et_linear_gnstats_gram2": 3, "se3et_linear_gnstats_stream": 1, "se3et_gemm_grouped_bf16": 1,
     "se3et_kpconv_gather": 1, "se3et_kpconv_fused": 1, "se3et_kpconv_rows": 1, "se3et_kpconv_cin1": 1, "se3et_kpconv_lift": 2, "se3et_groupnorm_stats": 1, "se3et_groupnorm_apply": 1, "se3et_groupnorm_double": 1, "se3et_maxpool_nbr": 1,
     "se3et_anchor_max": 1, "se3et_upsample_concat": 1, "se3et_geo_embed_indices": 1, "se3et_geo_embed_project": 1, "se3et_geo_embed_lookup": 1,
     "se3et_flash_attention": 1, "se3et_add_layernorm": 1, "se3et_linear_add_layernorm": 1, "se3et_l2_normalize_rows": 1,

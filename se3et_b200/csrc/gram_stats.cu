@@ -307,3 +307,27 @@ extern "C" int se3et_linear_gnstats_gram(const void* a, int64_t lda, int64_t m, 
   SE3ET_LAUNCH_CHECK();
   return SE3ET_OK;
 }
+
+// One Gram pass for TWO Linears applied to the same input (the block input x feeds both the narrowing
+// unary1 and the widening shortcut of a ResnetBottleneckBlockEPN, blocks_epn.py:833-852): G = A^T A and s = 1^T A give
+// the GroupNorm statistics of every Linear on A, so x is read once for statistics instead of twice.
+extern "C" int se3et_linear_gnstats_gram2(const void* a, int64_t lda, int64_t m, int64_t k, const void* w1_bf16,
+                                          int64_t ldw1, int64_t n1, const float* bias1, int64_t groups1, double* stats1,
+                                          const void* w2_bf16, int64_t ldw2, int64_t n2, const float* bias2,
+                                          int64_t groups2, double* stats2, const int64_t* seg_offsets, int64_t nseg,
+                                          int64_t rows_per_point, void* workspace, size_t workspace_bytes,
+                                          se3et_stream_t stream) {
+  if (!a || !w1_bf16 || !w2_bf16 || !seg_offsets || !stats1 || !stats2 || !workspace || m < 0 || n1 <= 0 || n2 <= 0 ||
+      nseg <= 0 || groups1 <= 0 || groups2 <= 0 || n1 % groups1 || n2 % groups2 || rows_per_point <= 0 ||
+      rows_per_point > INT32_MAX)
+    return SE3ET_ERR_ARG;
+  // the first Linear's statistics with the Gram pass, the second one from the same Gram matrix
+  int rc = se3et_linear_gnstats_gram(a, lda, m, k, w1_bf16, ldw1, n1, bias1, seg_offsets, nseg, groups1, rows_per_point, 0,
+                                     workspace, workspace_bytes, stats1, stream);
+  if (rc) return rc;
+  gram_finalize_kernel<<<dim3((unsigned)groups2, (unsigned)nseg), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const double*>(workspace), (int)k, static_cast<const __nv_bfloat16*>(w2_bf16), ldw2, bias2, seg_offsets,
+      (int)rows_per_point, (int)(n2 / groups2), (int)groups2, stats2);
+  SE3ET_LAUNCH_CHECK();
+  return SE3ET_OK;
+}

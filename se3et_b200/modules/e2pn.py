@@ -18,8 +18,8 @@ from torch.nn.parameter import Parameter
 
 from .. import _lib
 from ..ops import e2pn_ops as K
-from ..ops.gemm import (_gn_fusable, dual_apply_supported, linear_bf16, linear_gn_apply, linear_gn_apply_dual,
-                        linear_gn_stats)
+from ..ops.gemm import (_gn_fusable, dual_apply_supported, gram2_supported, linear_bf16, linear_gn_apply,
+                        linear_gn_apply_dual, linear_gn_stats, linear_gn_stats_gram2)
 from . import octahedral
 
 
@@ -421,22 +421,33 @@ class ResnetBottleneckBlockEPN(nn.Module):
         seg = _seg(seg, nq, q_pts.device)
         x = _act(x).contiguous()
         skip = x
+        st_skip = None   # statistics of the shortcut Linear when they come from the shared Gram pass below
+        has_skip_conv = isinstance(self.skip_conv, UnaryBlockEPN)
         if isinstance(self.unary1, UnaryBlockEPN):
             s_seg = _seg(s_seg, s_pts.shape[0], s_pts.device) if 'strided' in self.block_name else seg
-            y = self.unary1(x, seg=s_seg)
+            u1, sc = self.unary1, self.skip_conv
+            if ('strided' not in self.block_name and has_skip_conv and nq > 0 and gram2_supported(self.in_dim)
+                    and u1.two_pass_ok() and sc.two_pass_ok() and x.stride(-1) == 1):
+                # the block input feeds unary1 AND the shortcut Linear: one Gram pass over x gives both statistics
+                x2 = x.reshape(-1, self.in_dim)
+                st1, st_skip = linear_gn_stats_gram2(
+                    x2, u1._w_cache.get(u1.mlp.weight), u1.mlp.bias, u1.norm.num_groups,
+                    sc._w_cache.get(sc.mlp.weight), sc.mlp.bias, sc.norm.num_groups, seg, 6)
+                y = u1.apply(x, st1, seg, 6, 0.1).view(nq, 6, u1.out_dim)
+            else:
+                y = self.unary1(x, seg=s_seg)
         else:
             y = x
         y = _conv_double_norm(self.interso3, self.norm, y, q_pts, s_pts, neighb_inds, seg)
         if 'strided' in self.block_name:
             skip = K.maxpool_nbr(skip, neighb_inds.contiguous(), seg if sub_width is not None else None, sub_width)
-        has_skip_conv = isinstance(self.skip_conv, UnaryBlockEPN)
         if nq > 0 and self.unary2.two_pass_ok() and (not has_skip_conv or self.skip_conv.two_pass_ok()):
             # statistics passes, then the Linear(s) recomputed with normalisation + residual + LeakyReLU in the
             # GEMM epilogue: the (N, A, out_dim) pre-norm tensors never reach global memory
             y3 = y.view(nq, 6, -1)
             _, st2 = self.unary2.pre_norm(y3, seg, 6, store=False)
             if has_skip_conv:
-                _, st_s = self.skip_conv.pre_norm(skip, seg, 6, store=False)
+                st_s = st_skip if st_skip is not None else self.skip_conv.pre_norm(skip, seg, 6, store=False)[1]
                 if _GFLAGS['dual_apply'] and dual_apply_supported(self.out_dim, y3.shape[-1], self.in_dim):
                     # both Linears recomputed into two accumulators of one kernel: the normalised shortcut is never stored
                     u2, sc = self.unary2, self.skip_conv

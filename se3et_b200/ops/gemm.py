@@ -185,7 +185,7 @@ def dual_apply_supported(n, k1, k2):
     return n % 32 == 0 and k1 % 8 == 0 and k2 % 8 == 0
 
 
-_GRAM = {'on': True, 'min_n': 0}
+_GRAM = {'on': True, 'min_n': 0, 'shared': True}
 
 
 # A/B switch (tests, measurements): the streaming statistics pass is the product path
@@ -234,3 +234,27 @@ def linear_gn_stats_gram(a, w, bias, groups, seg_off, rows_per_point):
         _lib.i64(groups), _lib.i64(rows_per_point), _lib.i64(0), _lib.ptr(ws), ctypes.c_size_t(ws.numel()),
         _lib.ptr(stats), _lib.stream_ptr()), "linear_gnstats_gram")
     return stats
+
+
+def gram2_supported(k):
+    return _GRAM['on'] and _GRAM['shared'] and k in (32, 64, 128)
+
+
+def linear_gn_stats_gram2(a, w1, bias1, groups1, w2, bias2, groups2, seg_off, rows_per_point):
+    """GroupNorm statistics of a @ w1.T + bias1 AND a @ w2.T + bias2 from ONE Gram pass over `a`
+    (se3et_linear_gnstats_gram2).  -> (stats1, stats2), double (nseg, groups, 2) each."""
+    _check_ab(a, w1, bias1)
+    _check_ab(a, w2, bias2)
+    m, k = a.shape
+    n1, n2 = w1.shape[0], w2.shape[0]
+    nseg = seg_off.numel() - 1
+    st1 = torch.empty((nseg, groups1, 2), dtype=torch.float64, device=a.device)
+    st2 = torch.empty((nseg, groups2, 2), dtype=torch.float64, device=a.device)
+    ws = _lib.workspace.get(8 * nseg * (k + 1) * k, a.device)
+    _lib.check(_lib.lib().se3et_linear_gnstats_gram2(
+        _lib.ptr(a), _lib.i64(a.stride(0) if m > 1 else k), _lib.i64(m), _lib.i64(k),
+        _lib.ptr(w1), _lib.i64(w1.stride(0) if n1 > 1 else k), _lib.i64(n1), _lib.ptr(bias1), _lib.i64(groups1), _lib.ptr(st1),
+        _lib.ptr(w2), _lib.i64(w2.stride(0) if n2 > 1 else k), _lib.i64(n2), _lib.ptr(bias2), _lib.i64(groups2), _lib.ptr(st2),
+        _lib.ptr(seg_off), _lib.i64(nseg), _lib.i64(rows_per_point), _lib.ptr(ws), ctypes.c_size_t(ws.numel()),
+        _lib.stream_ptr()), "linear_gnstats_gram2")
+    return st1, st2

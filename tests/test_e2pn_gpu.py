@@ -403,6 +403,34 @@ def test_linear_gnstats_gram(n_out, groups, k, rpp):
     assert float(((got - ep.cpu()).abs() / scale.unsqueeze(-1)).max()) < 1e-4
 
 
+@pytest.mark.parametrize("k,n1,n2", [(64, 32, 128), (128, 64, 256), (32, 16, 64)])
+def test_one_gram_pass_serves_two_linears(k, n1, n2):
+    """se3et_linear_gnstats_gram2: the statistics of a narrowing and a widening Linear on the same input (unary1 and the
+    shortcut of a bottleneck block) from ONE Gram pass equal those of two separate passes and fp64 torch."""
+    from se3et_b200.ops import gemm as G
+    g = torch.Generator().manual_seed(k + n1)
+    pts = [150, 0, 333, 5, 2100]
+    seg = torch.tensor(np.concatenate([[0], np.cumsum(pts)]), dtype=torch.int64, device=DEV)
+    a = (torch.randn(6 * sum(pts), k, generator=g) + 0.3).to(torch.bfloat16)
+    lin = []
+    for n in (n1, n2):
+        lin.append(((torch.randn(n, k, generator=g) / k ** 0.5).to(torch.bfloat16), torch.randn(n, generator=g), min(n, 32)))
+    ad = a.to(DEV)
+    got = G.linear_gn_stats_gram2(ad, lin[0][0].to(DEV), lin[0][1].to(DEV), lin[0][2], lin[1][0].to(DEV), lin[1][1].to(DEV),
+                                  lin[1][2], seg, 6)
+    for (w, b, groups), st in zip(lin, got):
+        one = G.linear_gn_stats_gram(ad, w.to(DEV), b.to(DEV), groups, seg, 6)
+        # two passes differ by the fp32 partial sums of differently scheduled tiles
+        assert float((st - one).abs().max()) / max(float(one.abs().max()), 1.0) < 1e-5
+        y = a.double() @ w.double().t() + b.double()
+        for i in range(len(pts)):
+            blk = y[6 * int(seg[i]):6 * int(seg[i + 1])].view(-1, groups, w.shape[0] // groups)
+            want_s, want_q = blk.sum(dim=(0, 2)), (blk * blk).sum(dim=(0, 2))
+            scale = max(float(want_q.abs().max()), 1.0)
+            assert float((st[i, :, 0].cpu() - want_s).abs().max()) / scale < 2e-5
+            assert float((st[i, :, 1].cpu() - want_q).abs().max()) / scale < 2e-5
+
+
 @pytest.mark.parametrize("n_out,groups,k,rpp", [(32, 32, 64, 6), (32, 32, 128, 6), (64, 32, 256, 6), (128, 32, 32, 6),
                                                  (256, 32, 1024, 6), (512, 32, 128, 1), (2048, 32, 64, 6),
                                                  (64, 16, 40, 1)])
