@@ -40,6 +40,7 @@ enum {
   SE3ET_STATUS_M_TOTAL = 1,   /* grid_subsample: total number of output points */
   SE3ET_STATUS_MAX_COUNT = 2, /* radius_neighbors: max neighbour count over all queries */
   SE3ET_STATUS_REQ_KCELLS = 3, /* grid_subsample: on GRID_TOO_LARGE, cells needed / 1024 (rounded up, saturating) */
+  SE3ET_STATUS_MAX_LENGTH = 4, /* grid_subsample: largest output cloud (the 2000-superpoint cap is checked without another read-back) */
   SE3ET_STATUS_WORDS = 8
 };
 enum {

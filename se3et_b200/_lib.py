@@ -16,7 +16,7 @@ from . import build as _build
 _HEADER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "include", "se3et_b200.h")
 
 SE3ET_STATUS_WORDS = 8
-STATUS_ERROR, STATUS_M_TOTAL, STATUS_MAX_COUNT, STATUS_REQ_KCELLS = 0, 1, 2, 3
+STATUS_ERROR, STATUS_M_TOTAL, STATUS_MAX_COUNT, STATUS_REQ_KCELLS, STATUS_MAX_LENGTH = 0, 1, 2, 3, 4
 DEV_GRID_TOO_LARGE, DEV_INDEX_RANGE = 1, 2
 
 _ERRORS = {-1: "CUDA error", -2: "invalid argument", -3: "workspace too small", -4: "unsupported configuration"}

@@ -306,8 +306,10 @@ __global__ void subsample_lengths_kernel(const CloudGrid* __restrict__ grids, in
   for (int b = threadIdx.x; b < batch; b += blockDim.x) {
     const int64_t lo = grids[b].base;
     const int64_t hi = (b + 1 < batch) ? grids[b + 1].base : total_words[1];
-    s_lengths[b] = (int64_t)rank_of_cell(hi, bitmap, word_rank, total_words[0], m) -
-                   (int64_t)rank_of_cell(lo, bitmap, word_rank, total_words[0], m);
+    const int64_t len = (int64_t)rank_of_cell(hi, bitmap, word_rank, total_words[0], m) -
+                        (int64_t)rank_of_cell(lo, bitmap, word_rank, total_words[0], m);
+    s_lengths[b] = len;
+    atomicMax(&status[SE3ET_STATUS_MAX_LENGTH], (int32_t)len);
   }
   if (threadIdx.x == 0) status[SE3ET_STATUS_M_TOTAL] = (int32_t)m;
 }

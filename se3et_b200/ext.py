@@ -8,6 +8,7 @@ are canonical (ascending voxel key; (d2, index) ascending).
     sys.modules['geotransformer.ext'] = se3et_b200.ext
 """
 import ctypes
+import threading
 
 import torch
 
@@ -59,6 +60,21 @@ def grid_subsampling_raw(points, lengths, normals, voxel_size, max_cells=None):
     return s_points, s_lengths, s_normals, status
 
 
+# size of the largest cloud of the calling thread's last grid_subsampling (launch sequences run one per host thread)
+class _Last(threading.local):
+    def __init__(self):
+        self.d = {}
+
+    def __setitem__(self, k, v):
+        self.d[k] = v
+
+    def get(self, k, default=None):
+        return self.d.get(k, default)
+
+
+LAST = _Last()
+
+
 def grid_subsampling(points, lengths, normals, voxel_size):
     """ext.grid_subsampling(points, lengths, normals, voxel_size) -> [s_points, s_lengths, s_normals]
     (grid_subsampling.h:6-11)."""
@@ -75,6 +91,7 @@ def grid_subsampling(points, lengths, normals, voxel_size):
         if err:
             raise RuntimeError("grid_subsampling: device status %d" % err)
         m = int(st[_lib.STATUS_M_TOTAL])
+        LAST['max_length'] = int(st[_lib.STATUS_MAX_LENGTH])   # rides on the same read-back (precompute's superpoint cap)
         return [s_points[:m], s_lengths, s_normals[:m]]
     raise RuntimeError("grid_subsampling: voxel grid does not fit the workspace")
 

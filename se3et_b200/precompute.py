@@ -5,7 +5,7 @@ back-to-back without host syncs (their neighbour-count checks are read in one tr
 carried as zeros (the reference's open3d normals are never consumed by the model)."""
 import torch
 
-from . import _lib
+from . import _lib, ext
 from .ops import grid_subsample, radius_search_deferred
 
 
@@ -41,9 +41,10 @@ def precompute_data_stack_mode(points, lengths, num_stages, voxel_size, radius, 
                     points = torch.cat((points[:k0], points[l0:l0 + k1]), dim=0)
                     normals = torch.cat((normals[:k0], normals[l0:l0 + k1]), dim=0)
                     lengths = torch.tensor([k0, k1], dtype=torch.int64, device=points.device)
-            elif bool((lengths > 2000).any()):
+            elif ext.LAST.get('max_length', 1 << 30) > 2000 and bool((lengths > 2000).any()):
                 # stacked pairs: the same cap per cloud, so that a pair gives the same result batched and alone (the
-                # read-back rides on the grid_subsample sync just before; the slicing itself is the rare path)
+                # size of the largest cloud came back with grid_subsample's own status read-back: no extra sync unless a
+                # cloud really is over the cap; the slicing itself is the rare path)
                 host = [int(v) for v in lengths.tolist()]
                 keep, start = [], 0
                 for l in host:
